@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 hot path (BASELINE.json: DLRM fwd samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload dlrm|twotower|dcn] [--batch B]
+
+N=1 workload = BASELINE.json configs[1]: mm.DLRMModel, Criteo shape (26 cat, 13 dense, emb 64,
+bundled cardinalities = 45.6 M rows / 11.7 GB of tables), batch 65 536, README MLP dims.
+A step = one forward pass over one batch of synthetic input.  N>1 (torchrun): one replica per
+GPU on disjoint batches, no data-path collective (the forward is replica-local),
+weak scaling.
+
+Prints ONE JSON line (contract in the task statement): value = device-resident samples/s,
+e2e = the same metric through the public host-buffer call (pinned H2D + forward + D2H inside the
+timed region), roofline = dominant kernel vs measured HBM peak, cpu_baseline = CPU restatement
+of the reference op sequence on this box's host cores (rank 0, N=1 only).
+`--impl reference` times that CPU restatement alone (TensorFlow is not installable: no network).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+def build_dlrm(mm, datasets, table_seed=4321):
+    schema = datasets.criteo_schema()
+    model = mm.DLRMModel(schema, embedding_dim=64, bottom_block=mm.MLPBlock([128, 64]),
+                         top_block=mm.MLPBlock([128, 64, 32]),
+                         embedding_options=mm.EmbeddingOptions(embeddings_initializers={"hash_seed": table_seed}))
+    return schema, model
+
+
+def host_batches(datasets, schema, B, n, seed0=1234):
+    out = []
+    for i in range(n):
+        b = datasets.generate_batch(schema, B, seed=seed0 + i, index_law="uniform", index_dtype=np.int32)
+        feats, _ = datasets.split_targets(schema, b)
+        out.append(feats)
+    return out
+
+
+def dlrm_bytes_per_sample(T=26, D=64, idx_bytes=4, P=64):
+    F = T + 1
+    fused = T * D * 4 + T * idx_bytes + D * 4 + (P + F * (F - 1) // 2) * 4  # 8 676 B
+    gather = 2 * T * D * 4 + T * idx_bytes  # standalone gather: 13 416 B
+    return fused, gather
+
+
+def cpu_baseline_dlrm(model, feats_host, sample_rows, threads):
+    """CPU restatement (oracle/oracle_torch.py) on `sample_rows` samples of the same workload, with
+    the model's own tables/weights copied to the host."""
+    import torch
+    from oracle import oracle_torch
+
+    torch.set_num_threads(threads)
+    body = model.body
+    tables = {n: t.embeddings.cpu() for n, t in body.embeddings.tables.items()}
+    f2t = {f: t.table_name for f, t in body.embeddings.feature_to_table.items()}
+    layers = lambda mlp: [{"kernel": l.kernel.cpu(), "bias": l.bias.cpu(), "activation": l.activation}
+                          for l in mlp.dense_layers]
+    bottom, top = layers(body.bottom_block), layers(body.top_block)
+    hd = model.prediction.to_call
+    head = {"kernel": hd.kernel.cpu(), "bias": hd.bias.cpu(), "activation": hd.activation}
+    idx = {n: torch.from_numpy(feats_host[n][:sample_rows]) for n in f2t}
+    dense = {n: torch.from_numpy(feats_host[n][:sample_rows]) for n in body.continuous.features}
+
+    def run():
+        return oracle_torch.dlrm_forward(idx, dense, tables, f2t, bottom, top, head)
+
+    return run
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dlrm", choices=["dlrm"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import torch
+
+    import models_b200 as mm
+    from models_b200 import datasets, ops
+
+    B = args.batch
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, mm, datasets, cores)
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the B200 hot path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    schema, model = build_dlrm(mm, datasets)
+    model.build(dev)
+    n_bufs = 4
+    hosts = host_batches(datasets, schema, B, n_bufs, seed0=1234 + 1000 * rank)
+    devs = [{k: torch.from_numpy(v).to(dev) for k, v in h.items()} for h in hosts]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    # events around the dominant kernel (gather+interaction fused), recorded in-stream
+    kev = []
+
+    def step(i):
+        feats = devs[i % n_bufs]
+        bottom = model.body.bottom_forward(feats)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x = model.body.interaction_forward(feats, bottom)
+        e1.record()
+        kev.append((e0, e1))
+        return model.prediction(model.body.top_block(x))
+
+    # correctness guard: the staged step above must equal the public call
+    ref_out = model(devs[0])
+    assert torch.equal(ref_out, step(0)), "bench step diverges from model.__call__"
+    kev.clear()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev.clear()
+    t0.record()
+    for i in range(args.steps):
+        out = step(i)
+    t1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop()
+    elapsed_ms = t0.elapsed_time(t1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    # ---- e2e: public host-buffer call; pinned H2D + forward + D2H per step inside the region
+    for i in range(3):
+        model.forward_host(hosts[i % n_bufs])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(5, min(args.steps, 20))
+    e0.record()
+    for i in range(e2e_steps):
+        res = model.forward_host(hosts[i % n_bufs])
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d = int(sum(v.nbytes for v in hosts[0].values()))
+    d2h = int(res.numel() * res.element_size())
+
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([elapsed_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms, kern_ms = (float(x) for x in t.tolist())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        fused_b, gather_b = dlrm_bytes_per_sample()
+        achieved = fused_b * B / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "DLRM fwd samples/sec (Criteo shape, batch 65536/GPU)",
+            "value": world * B * args.steps / (elapsed_ms * 1e-3),
+            "unit": "samples/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "fp32",
+            "data": "synthetic (uniform indices over bundled Criteo cardinalities; hash-initialised tables, random-init MLPs)",
+            "config": {
+                "workload": "mm.DLRMModel Criteo-shape (26 cat, 13 dense, emb_dim 64), bottom [128,64], top [128,64,32]",
+                "batch_per_gpu": B, "global_batch": B * world, "index_dtype": "int32", "table_rows": 45621194,
+                "table_gb": 11.68, "parallelism": f"replicas x{world} (no data-path collective)",
+                "l2": f"inputs larger than L2: 11.7 GB of tables, {n_bufs} rotating input batches, no flush",
+                "dense_engine": mm.dense_engine(),
+            },
+            "clocks": clocks,
+            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "interact_kernel<gather-fused> (mm_dlrm_gather_interact)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": fused_b * B,
+                         "kernel_ms": kern_ms, "traffic": None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = time_cpu_baseline(model, hosts[0], min(args.cpu_sample, B), cores)
+            except Exception as e:  # the baseline must never take the bench line down
+                line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return 0
+
+
+def time_cpu_baseline(model, feats_host, sample_rows, cores, budget_s=20.0):
+    run = cpu_baseline_dlrm(model, feats_host, sample_rows, cores)
+    run()  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        run()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 50:
+            break
+    return {"value": sample_rows * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} passes over {sample_rows} samples of the same batch, same tables/weights on the host; "
+                      "PyTorch-CPU restatement of the reference TF op sequence (TensorFlow not installable)"}
+
+
+def reference_arm(args, mm, datasets, cores):
+    """`--impl reference`: the CPU restatement of the reference path on this box's host cores.
+    Tables are generated on the host by the same hash initialiser (no GPU needed)."""
+    import torch
+    from oracle import oracle, oracle_torch
+
+    torch.set_num_threads(cores)
+    B = args.batch
+    sample = min(args.cpu_sample, B)
+    schema = datasets.criteo_schema()
+    rng = np.random.default_rng(4321)
+    cat = schema.select_by_tag(mm.Tags.CATEGORICAL)
+    # host tables: random rows are touched uniformly, so the table content is irrelevant to the
+    # timing; sizes (rows x 64 fp32) are the real ones, filled by a cheap generator
+    tables = {}
+    for c in cat:
+        rows = c.int_domain.max + 1
+        t = torch.empty((rows, 64), dtype=torch.float32)
+        t.uniform_(-0.05, 0.05)
+        tables[c.name] = t
+    f2t = {c.name: c.name for c in cat}
+
+    def glorot(i, o):
+        lim = np.sqrt(6.0 / (i + o))
+        return torch.from_numpy(rng.uniform(-lim, lim, (i, o)).astype(np.float32))
+
+    def layers(dims, width, last_act="relu"):
+        out = []
+        for d in dims:
+            out.append({"kernel": glorot(width, d), "bias": torch.zeros(d), "activation": "relu"})
+            width = d
+        return out
+
+    bottom, top = layers([128, 64], 13), layers([128, 64, 32], 64 + 351)
+    head = {"kernel": glorot(32, 1), "bias": torch.zeros(1), "activation": "sigmoid"}
+    batch = datasets.generate_batch(schema, sample, seed=1234, index_law="uniform", index_dtype=np.int32)
+    feats, _ = datasets.split_targets(schema, batch)
+    idx = {n: torch.from_numpy(feats[n]) for n in f2t}
+    dense = {c.name: torch.from_numpy(feats[c.name]) for c in schema.select_by_tag(mm.Tags.CONTINUOUS)}
+
+    def run():
+        return oracle_torch.dlrm_forward(idx, dense, tables, f2t, bottom, top, head)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        run()
+    steps = args.steps
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        run()
+        done += 1
+        if time.perf_counter() - t0 > 120.0:
+            break
+    dt = time.perf_counter() - t0
+    value = sample * done / dt
+    line = {
+        "impl": "reference",
+        "metric": "DLRM fwd samples/sec (Criteo shape, batch 65536/GPU)",
+        "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+        "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic (uniform indices over bundled Criteo cardinalities)",
+        "config": {"workload": "mm.DLRMModel Criteo-shape (26 cat, 13 dense, emb_dim 64), bottom [128,64], top [128,64,32]",
+                   "batch_per_step": sample, "note": "each step = a bounded sample of the 65536 batch"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{done} steps x {sample} samples; PyTorch-CPU restatement of the reference "
+                                   "TF op sequence (TensorFlow/merlin-core not installable: no network)"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,183 @@
+/*
+ * mm_b200.h — C-ABI of the B200-native (sm_100a) hot path of NVIDIA-Merlin/models:
+ *             embedding lookup -> MLP tower -> interaction / scoring.
+ *
+ * The reference (/root/reference, merlin/models/tf) has no FFI layer: every byte on this
+ * path is moved by TensorFlow ops called from Python.  This header declares the entry
+ * points a maintainer would bind (ctypes stub shown in INTEGRATION.md) to replace those op
+ * call sites.  Each declaration cites the reference call site it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - nothing is allocated or freed inside the library; the caller owns every buffer;
+ *   - return value: 0 = ok, <0 = argument error (MM_ERR_*), >0 = cudaError_t of the launch;
+ *     `mm_last_error()` returns a thread-local human-readable message for the last failure;
+ *   - all matrices are row-major fp32 unless stated; strides are in ELEMENTS.
+ */
+#ifndef MM_B200_H_
+#define MM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_OK 0
+#define MM_ERR_ARG (-1)        /* null pointer / negative size / bad enum */
+#define MM_ERR_UNSUPPORTED (-2) /* shape outside what the kernels implement */
+#define MM_ERR_ALIGN (-3)      /* pointer / stride alignment requirement violated */
+#define MM_ERR_DRIVER (-4)     /* driver entry point (tensor map encode) unavailable */
+
+#define MM_MAX_TABLES 64 /* tables per fused gather launch */
+
+/* index dtypes */
+#define MM_I32 0
+#define MM_I64 1
+
+/* activations (Keras names; merlin/models/tf/blocks/mlp.py:97-127 passes them to Dense) */
+#define MM_ACT_LINEAR 0
+#define MM_ACT_RELU 1
+#define MM_ACT_SIGMOID 2
+#define MM_ACT_TANH 3
+#define MM_ACT_SELU 4
+#define MM_ACT_ELU 5
+#define MM_ACT_GELU 6 /* exact erf form (Keras default approximate=False) */
+
+/* bag combiners (tf.nn.safe_embedding_lookup_sparse; inputs/embedding.py:432-441) */
+#define MM_COMBINER_MEAN 0
+#define MM_COMBINER_SUM 1
+#define MM_COMBINER_SQRTN 2
+#define MM_COMBINER_MAX 3 /* dense-sequence combiner only (inputs/embedding.py:1545-1587) */
+
+int mm_version(void);
+const char* mm_last_error(void);
+/* number of kernel launches issued through this library by the calling process */
+int64_t mm_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Deterministic table initialiser: w[i] = lo + (hi-lo) * u24(hash(seed, i)) with
+ * u24 in [0,1) on a 2^-24 grid; bit-reproducible on the CPU (oracle/oracle.py:hash_uniform).
+ * Stands in for Keras `embeddings_initializer="uniform"` (inputs/embedding.py:205) at sizes
+ * (10.9 GiB of tables) that cannot be generated on the host and shipped.
+ * ------------------------------------------------------------------------------------- */
+int mm_init_uniform_hash(float* w, int64_t n, uint64_t seed, float lo, float hi, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K1/K3/K5  Fused multi-table one-hot gather.
+ * Replaces T x tf.keras.layers.Embedding / tf.gather  (inputs/embedding.py:452,460,:1142,1146)
+ * + tf.stack / tf.concat of the results (core/aggregation.py:64,108).
+ *   out[b * out_stride + out_col[t] + d] = weights[t][ idx[t][b] * dim[t] + d ]
+ * With out_col[t] = slot(t)*D this IS StackFeatures' (B,F,D) layout; with a running sum of
+ * dims it is ConcatFeatures' layout.  Rows are copied bit-exactly.
+ * An index outside [0, rows) writes a zero row and increments *oob_count (if non-null) —
+ * TF-GPU semantics for gather; the Python wrapper turns a non-zero count into the
+ * InvalidArgumentError that TF-CPU raises.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* weights; /* (rows, dim) */
+  const void* indices;  /* (B,) int32 or int64 */
+  int64_t rows;
+  int32_t dim;
+  int32_t out_col; /* column offset (floats) of this feature inside an output row */
+} mm_gather_table;
+
+int mm_gather_multi(const mm_gather_table* tables_host, int n_tables, int idx_dtype, int64_t B,
+                    float* out, int64_t out_stride, int32_t* oob_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  Multi-hot bag lookup (ragged `name__values` + `name__offsets`).
+ * Replaces tf.nn.safe_embedding_lookup_sparse (inputs/embedding.py:432-441,:1139):
+ * ids < 0 are dropped, an empty bag yields zeros, mean = sum/count, sqrtn = sum/sqrt(count).
+ * Summation order inside a bag is left-to-right (sequential fp32 adds), as TF's
+ * segment_sum on CPU does.
+ * ------------------------------------------------------------------------------------- */
+int mm_gather_bag(const float* weights, int64_t rows, int dim, const void* values, int idx_dtype,
+                  const void* offsets, int off_dtype, int64_t B, int combiner, float* out,
+                  int64_t out_stride, int out_col, int32_t* oob_count, void* stream);
+
+/* Dense (B, L) sequence lookup + combiner over axis 1 (padding NOT masked);
+ * replaces Embedding + process_sequence_combiner (inputs/embedding.py:457-461,:1556-1587). */
+int mm_gather_seq(const float* weights, int64_t rows, int dim, const void* ids, int idx_dtype,
+                  int64_t B, int L, int combiner, float* out, int64_t out_stride, int out_col,
+                  int32_t* oob_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  Column concat with cast to fp32.
+ * Replaces ConcatFeatures (core/aggregation.py:54-66: sorted-key tf.concat + cast to float32)
+ * and ContinuousFeatures' (B,) -> (B,1) expand (inputs/continuous.py:134-138).  The caller
+ * lists the pieces in the reference's sorted-name order with running out_col offsets.
+ *   out[b, out_col[i] + c] = (float) src_i[b * src_stride_i + c],  c < width_i
+ * ------------------------------------------------------------------------------------- */
+#define MM_F32 2
+#define MM_F64 3
+typedef struct {
+  const void* src;
+  int64_t src_stride; /* elements between consecutive rows of this piece */
+  int32_t width;
+  int32_t dtype; /* MM_I32, MM_I64, MM_F32, MM_F64 */
+  int32_t out_col;
+  int32_t reserved;
+} mm_concat_piece;
+
+int mm_concat_columns(const mm_concat_piece* pieces_host, int n_pieces, int64_t B, float* out,
+                      int64_t out_stride, void* stream);
+
+/* L2Norm (transforms/regularization.py:27-82): x / sqrt(max(sum(x^2, -1), 1e-12)); in place ok */
+int mm_l2_normalize(const float* x, int64_t B, int D, int64_t x_stride, float* out,
+                    int64_t out_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K6 (+K3)  Pairwise dot-product interaction.
+ * Replaces tf.matmul(x, x, transpose_b=True) + band_part + boolean_mask
+ * (blocks/interaction.py:102,107-112) and the shortcut concat (blocks/dlrm.py:126-130).
+ *   out[b, 0:P]      = prefix[b, 0:P]                  (P = 0 / prefix NULL: no prefix)
+ *   out[b, P + p(i,j)] = sum_d x[b,i,d] * x[b,j,d]      i<j (or i<=j if self_interaction),
+ * pairs enumerated row-major over the upper triangle.  Dots accumulate in fp32, d ascending.
+ * ------------------------------------------------------------------------------------- */
+int mm_dot_interaction(const float* x, int64_t B, int F, int D, int64_t x_stride,
+                       const float* prefix, int P, int64_t prefix_stride, int self_interaction,
+                       float* out, int64_t out_stride, void* stream);
+
+/* Fused K1+K5+K6+K3 for DLRM: gather T rows per sample straight into shared memory, append
+ * the bottom-MLP vector at slot `bottom_slot`, write [bottom | interactions]; the (B,F,D)
+ * stack never touches HBM.  tables[t].out_col is interpreted as slot(t)*D.  All dims == D. */
+int mm_dlrm_gather_interact(const mm_gather_table* tables_host, int n_tables, int idx_dtype,
+                            int64_t B, int D, const float* bottom, int64_t bottom_stride,
+                            int bottom_slot, float* out, int64_t out_stride, int32_t* oob_count,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  Dense layer, exact fp32 on CUDA cores:  out = act(x @ W + bias).
+ * Replaces tf.keras.layers.Dense (blocks/mlp.py:275-280); W is the Keras kernel (K, N).
+ * If x0 is non-null the epilogue is the DCN-v2 cross:  out = x0 * (x @ W + bias) + x
+ * (blocks/cross.py:196-198; requires N == K, act ignored).
+ * ------------------------------------------------------------------------------------- */
+int mm_dense_fp32(const float* x, int64_t B, int K, int64_t x_stride, const float* W,
+                  const float* bias, int N, int act, const float* x0, int64_t x0_stride,
+                  float* out, int64_t out_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K8/K9  Two-tower scoring.
+ * mm_rowwise_dot: inference scorer  s[b] = sum_d q[b,d]*i[b,d]
+ *   (blocks/retrieval/base.py:278-281; outputs/contrastive.py:305-307).
+ * mm_inbatch_scores: training/testing logits
+ *   out[b,0]   = q[b].pos[b]  (- log(pos_prob[b]+1e-16))
+ *   out[b,1+n] = (pos_id[b]==neg_id[n] && downscore) ? false_neg_score
+ *                                                    : q[b].neg[n] (- log(neg_prob[n]+1e-16))
+ *   then every element is divided by `temperature`
+ *   (blocks/retrieval/base.py:339-343,373-396; utils/tf_utils.py:126-154;
+ *    outputs/contrastive.py:303-326; prediction_tasks/retrieval.py:135-136).
+ * ------------------------------------------------------------------------------------- */
+int mm_rowwise_dot(const float* q, const float* items, int64_t B, int D, int64_t q_stride,
+                   int64_t i_stride, float* out, void* stream);
+int mm_inbatch_scores(const float* q, const float* pos, const float* neg, int64_t B, int64_t N,
+                      int D, const void* pos_ids, const void* neg_ids, int id_dtype, int downscore,
+                      float false_neg_score, const float* pos_prob, const float* neg_prob,
+                      float temperature, float* out, int64_t out_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MM_B200_H_ */

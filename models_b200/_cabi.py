@@ -1,0 +1,115 @@
+"""ctypes binding of libmm_b200.so — the C-ABI declared in include/mm_b200.h.
+
+This is the only place the product touches native code.  There is NO fallback: if the
+library is missing or a symbol cannot be resolved, importing/using the ops raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "_lib" / "libmm_b200.so"
+HEADER_PATH = _PKG.parent / "include" / "mm_b200.h"
+
+MM_MAX_TABLES = 64
+MM_I32, MM_I64, MM_F32, MM_F64 = 0, 1, 2, 3
+ACTIVATIONS = {
+    None: 0, "linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3, "selu": 4, "elu": 5, "gelu": 6,
+}
+COMBINERS = {"mean": 0, "sum": 1, "sqrtn": 2, "max": 3}
+
+
+class GatherTable(C.Structure):
+    """mm_gather_table (include/mm_b200.h)."""
+
+    _fields_ = [
+        ("weights", C.c_void_p),
+        ("indices", C.c_void_p),
+        ("rows", C.c_int64),
+        ("dim", C.c_int32),
+        ("out_col", C.c_int32),
+    ]
+
+
+class ConcatPiece(C.Structure):
+    """mm_concat_piece (include/mm_b200.h)."""
+
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("src_stride", C.c_int64),
+        ("width", C.c_int32),
+        ("dtype", C.c_int32),
+        ("out_col", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+_vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+_tables = C.POINTER(GatherTable)
+
+# name -> (restype, argtypes); must list every function declared in include/mm_b200.h
+SIGNATURES = {
+    "mm_version": (_i, []),
+    "mm_last_error": (C.c_char_p, []),
+    "mm_launch_count": (_i64, []),
+    "mm_init_uniform_hash": (_i, [_vp, _i64, _u64, _f, _f, _vp]),
+    "mm_gather_multi": (_i, [_tables, _i, _i, _i64, _vp, _i64, _vp, _vp]),
+    "mm_gather_bag": (_i, [_vp, _i64, _i, _vp, _i, _vp, _i, _i64, _i, _vp, _i64, _i, _vp, _vp]),
+    "mm_gather_seq": (_i, [_vp, _i64, _i, _vp, _i, _i64, _i, _i, _vp, _i64, _i, _vp, _vp]),
+    "mm_concat_columns": (_i, [C.POINTER(ConcatPiece), _i, _i64, _vp, _i64, _vp]),
+    "mm_l2_normalize": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp]),
+    "mm_dot_interaction": (_i, [_vp, _i64, _i, _i, _i64, _vp, _i, _i64, _i, _vp, _i64, _vp]),
+    "mm_dlrm_gather_interact": (_i, [_tables, _i, _i, _i64, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
+    "mm_dense_fp32": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64, _vp]),
+    "mm_rowwise_dot": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
+    "mm_inbatch_scores": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _f,
+                               _vp, _i64, _vp]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Function names declared in include/mm_b200.h (parsed from the header text)."""
+    text = HEADER_PATH.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mm_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library and bind every entry point; raise loudly if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m models_b200.csrc.build` "
+            "(or __graft_entry__.build()). There is no CPU/PyTorch fallback for this path."
+        )
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover - only on a broken build
+            raise RuntimeError(f"libmm_b200.so does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().mm_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc < 0:
+        raise ValueError(f"{what}: {msg} (code {rc})")
+    raise RuntimeError(f"{what}: {msg} (cudaError {rc})")

@@ -1,0 +1,434 @@
+"""Body blocks of the hot path: MLPBlock, DotProductInteraction, CrossBlock, DLRMBlock.
+
+Constructor surface and error messages follow merlin/models/tf/blocks/{mlp,interaction,cross,dlrm}.py;
+execution is a handful of fused kernel launches (models_b200.ops), not a Keras layer graph.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Union
+
+import torch
+
+from . import ops
+from ._cabi import ACTIVATIONS
+from .core import (Block, InitializerType, SequentialBlock, TabularData, batch_size_of, concat_sorted,
+                   create_variable, default_device, unique_name)
+from .inputs import (ContinuousFeatures, EmbeddingOptions, Embeddings, EmbeddingsBlock, InputBlock, InputBlockV2,
+                     infer_embedding_dim)
+from .schema import Schema, Tags
+
+# dense-layer engine: "fp32" = exact CUDA-core kernel (mm_dense_fp32); "tc" = tcgen05 split-bf16
+_DENSE_ENGINE = ["auto"]
+
+
+def set_dense_engine(engine: str) -> None:
+    if engine not in ("auto", "fp32", "tc"):
+        raise ValueError("engine must be 'auto', 'fp32' or 'tc'")
+    _DENSE_ENGINE[0] = engine
+
+
+def dense_engine() -> str:
+    return _DENSE_ENGINE[0]
+
+
+class _Dense(Block):
+    """Keras Dense as wrapped by blocks/mlp.py:210-300: dict inputs are concat-aggregated in
+    sorted-key order first (:275-277), then act(x @ kernel + bias) with kernel (in, units)."""
+
+    def __init__(self, units: int, activation: Optional[str] = None, use_bias: bool = True,
+                 kernel_initializer: InitializerType = "glorot_uniform", bias_initializer: InitializerType = "zeros",
+                 name: Optional[str] = None, **kwargs):
+        super().__init__(name or unique_name("dense"))
+        if activation not in ACTIVATIONS:
+            raise ValueError(f"Unknown activation function: {activation!r}")
+        self.units = int(units)
+        self.activation = activation or "linear"
+        self.use_bias = use_bias
+        self.kernel_initializer = kernel_initializer
+        self.bias_initializer = bias_initializer
+        self.kernel: Optional[torch.Tensor] = None
+        self.bias: Optional[torch.Tensor] = None
+        self.input_dim: Optional[int] = None
+
+    def build(self, input_dim: Optional[int] = None, device=None) -> "_Dense":
+        if self.kernel is None:
+            if input_dim is None:
+                raise ValueError(f"{self.name}: cannot build without the input width")
+            device = device or default_device()
+            self.input_dim = int(input_dim)
+            self.kernel = create_variable((input_dim, self.units), self.kernel_initializer, device, f"{self.name}/kernel")
+            if self.use_bias:
+                self.bias = create_variable((self.units,), self.bias_initializer, device, f"{self.name}/bias")
+        self.built = True
+        return self
+
+    def set_weights(self, kernel, bias=None) -> None:
+        dev = default_device()
+        self.kernel = torch.as_tensor(kernel, dtype=torch.float32).to(dev).contiguous()
+        self.input_dim = self.kernel.shape[0]
+        if self.kernel.shape[1] != self.units:
+            raise ValueError(f"{self.name}: kernel has {self.kernel.shape[1]} columns, expected {self.units}")
+        self.bias = None if bias is None else torch.as_tensor(bias, dtype=torch.float32).to(dev).contiguous()
+        self.use_bias = bias is not None
+        self.built = True
+
+    def weights(self):
+        out = {"kernel": self.kernel}
+        if self.bias is not None:
+            out["bias"] = self.bias
+        return out
+
+    def call(self, inputs, x0: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        x = concat_sorted(inputs) if isinstance(inputs, dict) else inputs
+        if x.dim() != 2:
+            raise ValueError(f"{self.name}: expected a 2-D input, got shape {tuple(x.shape)}")
+        self.build(x.shape[1], x.device)
+        if x.shape[1] != self.input_dim:
+            raise ValueError(f"{self.name}: input width {x.shape[1]} != kernel rows {self.input_dim}")
+        out = torch.empty((x.shape[0], self.units), dtype=torch.float32, device=x.device)
+        return ops.dense_fp32(x, self.kernel, self.bias, self.activation, out, x0=x0)
+
+
+class MLP(SequentialBlock):
+    """The SequentialBlock MLPBlock() returns; `.layers` are the _Dense layers."""
+
+    def __init__(self, layers: Sequence[_Dense], filter_names: Optional[List[str]] = None, block_name: str = "MLPBlock",
+                 dropout: Optional[float] = None):
+        super().__init__(layers, block_name=block_name)
+        self.filter_names = filter_names
+        self.dropout = dropout
+
+    @property
+    def dense_layers(self) -> List[_Dense]:
+        return [l for l in self.layers if isinstance(l, _Dense)]
+
+    def build_from_width(self, width: int, device=None) -> "MLP":
+        for l in self.dense_layers:
+            l.build(width, device)
+            width = l.units
+        self.built = True
+        return self
+
+    def call(self, inputs, training: bool = False, **kwargs):
+        if self.dropout and training:
+            raise NotImplementedError("dropout in training mode is outside the forward hot path")
+        x = inputs
+        if isinstance(x, dict):
+            if self.filter_names is not None:
+                x = {k: v for k, v in x.items() if k in self.filter_names}
+            x = concat_sorted(x)
+        for l in self.dense_layers:
+            x = l(x)
+        return x
+
+    def oracle_layers(self):
+        return [{"kernel": l.kernel.cpu().numpy(), "bias": None if l.bias is None else l.bias.cpu().numpy(),
+                 "activation": l.activation} for l in self.dense_layers]
+
+
+def MLPBlock(dimensions: List[int], activation: Union[str, List[str]] = "relu", use_bias: bool = True,
+             kernel_initializer: InitializerType = "glorot_uniform", bias_initializer: InitializerType = "zeros",
+             kernel_regularizer=None, bias_regularizer=None, activity_regularizer=None, dropout: Optional[float] = None,
+             normalization=None, filter: Optional[Union[Schema, Tags, List[str]]] = None,
+             no_activation_last_layer: bool = False, block_name: str = "MLPBlock", **kwargs) -> MLP:
+    """blocks/mlp.py:35-139.  Activation is applied on every layer including the last unless
+    `no_activation_last_layer` (:99-106).  Regularizers only matter for training and are accepted
+    and ignored; `normalization` (BatchNorm) is not on the forward hot path."""
+    if isinstance(activation, list) and len(activation) != len(dimensions):
+        raise ValueError(
+            f"Activation and Dimensions length mismatch. \
+        Activation length: {len(activation)}, Dimensions length: {len(dimensions)}"
+        )
+    if normalization is not None:
+        raise NotImplementedError("MLPBlock(normalization=...) is outside the B200 hot path (see DESIGN.md)")
+    layers = []
+    for idx, dim in enumerate(dimensions):
+        act = activation or "linear"
+        act_i = act if isinstance(act, str) else act[idx]
+        if no_activation_last_layer and idx == len(dimensions) - 1:
+            act_i = "linear"
+        layers.append(_Dense(dim, activation=act_i, use_bias=use_bias, kernel_initializer=kernel_initializer,
+                             bias_initializer=bias_initializer))
+    names = None
+    if filter is not None:
+        if isinstance(filter, Schema):
+            names = filter.column_names
+        elif isinstance(filter, (list, tuple)):
+            names = list(filter)
+        else:
+            raise ValueError("MLPBlock(filter=Tags) needs a schema; pass a Schema or a list of names")
+    return MLP(layers, filter_names=names, block_name=block_name, dropout=dropout)
+
+
+_INTERACTION_TYPES = (None, "field_all", "field_each", "field_interaction")
+
+
+class DotProductInteraction(Block):
+    """blocks/interaction.py:35-130 with interaction_type=None: (B,F,D) -> (B, F(F-1)/2) strict
+    upper triangle of X X^T, row-major ((B, F(F+1)/2) with self_interaction)."""
+
+    def __init__(self, interaction_type=None, self_interaction: bool = False, name: Optional[str] = None, **kwargs):
+        if interaction_type not in _INTERACTION_TYPES:
+            raise ValueError("Unknown interaction type {}".format(interaction_type))
+        if interaction_type is not None:
+            raise NotImplementedError("FiBiNet bilinear interaction types are outside the DLRM hot path")
+        super().__init__(name or unique_name("dot_product_interaction"))
+        self.interaction_type = interaction_type
+        self.self_interaction = self_interaction
+
+    def compute_output_shape(self, input_shape):
+        F = input_shape[1]
+        return input_shape[0], (F * (F + 1) // 2 if self.self_interaction else F * (F - 1) // 2)
+
+    def call(self, inputs: torch.Tensor, prefix: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        if inputs.dim() != 3:
+            raise ValueError(f"DotProductInteraction expects (batch, features, dim), got {tuple(inputs.shape)}")
+        B, n = self.compute_output_shape(inputs.shape)
+        P = 0 if prefix is None else prefix.shape[1]
+        out = torch.empty((B, P + n), dtype=torch.float32, device=inputs.device)
+        return ops.dot_interaction(inputs.contiguous(), out, prefix=prefix, self_interaction=self.self_interaction)
+
+
+class Cross(Block):
+    """blocks/cross.py:113-221: x_{l+1} = x0 * (x_l W + b) + x_l (full rank) or W = U V."""
+
+    def __init__(self, low_rank_dim: Optional[int] = None, use_bias: bool = True,
+                 kernel_initializer: InitializerType = "truncated_normal", bias_initializer: InitializerType = "zeros",
+                 output_x0: bool = False, name: Optional[str] = None, **kwargs):
+        super().__init__(name or unique_name("cross"))
+        self.low_rank_dim = low_rank_dim
+        self.use_bias = use_bias
+        self.kernel_initializer = kernel_initializer
+        self.bias_initializer = bias_initializer
+        self.output_x0 = output_x0
+        self.dense: Optional[_Dense] = None
+        self.dense_u: Optional[_Dense] = None
+
+    def build(self, d: Optional[int] = None, device=None):
+        if self.dense is None:
+            if d is None:
+                raise ValueError("Cross: cannot build without the input width")
+            self.dense = _Dense(d, activation="linear", use_bias=self.use_bias,
+                                kernel_initializer=self.kernel_initializer, bias_initializer=self.bias_initializer,
+                                name=f"{self.name}/dense")
+            if self.low_rank_dim is not None:
+                self.dense_u = _Dense(self.low_rank_dim, activation="linear", use_bias=False,
+                                      kernel_initializer=self.kernel_initializer, name=f"{self.name}/dense_u")
+                self.dense_u.build(d, device)
+                self.dense.build(self.low_rank_dim, device)
+            else:
+                self.dense.build(d, device)
+        self.built = True
+        return self
+
+    def weights(self):
+        out = {f"dense/{k}": v for k, v in self.dense.weights().items()}
+        if self.dense_u is not None:
+            out["dense_u/kernel"] = self.dense_u.kernel
+        return out
+
+    def call(self, inputs, **kwargs):
+        x0, x = inputs if isinstance(inputs, tuple) else (inputs, inputs)
+        if tuple(x0.shape) != tuple(x.shape):
+            raise ValueError("`x0` ({}) and `x` ({}) shapes mismatch!".format(tuple(x0.shape), tuple(x.shape)))
+        self.build(x.shape[1], x.device)
+        if self.dense_u is None:
+            out = self.dense(x, x0=x0)  # fused epilogue x0 * (xW + b) + x
+        else:
+            u = self.dense_u(x)
+            proj = torch.empty_like(x)
+            # low rank: the fused cross epilogue needs a square kernel, so run V with the cross
+            # epilogue reading x as the residual: out = x0 * (u V + b) + x  (K = r, N = d)
+            out = _cross_lowrank(u, self.dense, x0, x, proj)
+        return (x0, out) if self.output_x0 else out
+
+
+def _cross_lowrank(u, dense: _Dense, x0, x, out):
+    raise NotImplementedError("CrossBlock(low_rank_dim=...) is not implemented on the B200 path yet")
+
+
+class CrossBlockSeq(SequentialBlock):
+    def __init__(self, layers, inputs: Optional[Block] = None):
+        super().__init__(layers, block_name="CrossBlock")
+        self.inputs = inputs
+
+    @property
+    def cross_layers(self) -> List[Cross]:
+        return [l for l in self.layers if isinstance(l, Cross)]
+
+    def call(self, x, **kwargs):
+        if self.inputs is not None:
+            x = self.inputs(x)
+        if isinstance(x, dict):
+            x = concat_sorted(x)
+        for l in self.cross_layers:
+            x = l(x)
+        return x
+
+    def oracle_layers(self):
+        return [{"kernel": l.dense.kernel.cpu().numpy(),
+                 "bias": None if l.dense.bias is None else l.dense.bias.cpu().numpy()} for l in self.cross_layers]
+
+
+def CrossBlock(depth: int = 1, filter=None, low_rank_dim: Optional[int] = None, use_bias: bool = True,
+               kernel_initializer: InitializerType = "truncated_normal", bias_initializer: InitializerType = "zeros",
+               kernel_regularizer=None, bias_regularizer=None, inputs: Optional[Block] = None, **kwargs) -> CrossBlockSeq:
+    """blocks/cross.py:29-109."""
+    if depth <= 0:
+        raise ValueError(f"Number of cross layers (depth) should be positive but is {depth}.")
+    layers = [Cross(low_rank_dim=low_rank_dim, use_bias=use_bias, kernel_initializer=kernel_initializer,
+                    bias_initializer=bias_initializer, output_x0=i < depth - 1) for i in range(depth)]
+    return CrossBlockSeq(layers, inputs=inputs)
+
+
+class DLRM(Block):
+    """What DLRMBlock() returns (blocks/dlrm.py:32-133).
+
+    forward:  embeddings (T x (B,D))  +  bottom MLP(continuous) (B,D)
+              -> stack in sorted(name) order, "bottom_block" last for C*/I* style names
+              -> pairwise dots (B, F(F-1)/2) -> [bottom | interactions] -> top MLP
+    `fused=True` runs gather + stack + interaction + concat as ONE kernel (the (B,F,D) stack never
+    reaches HBM); `fused=False` keeps the reference's staging ((B,F,D) materialised once) for
+    block-level parity tests.
+    """
+
+    def __init__(self, embeddings: EmbeddingsBlock, continuous: Optional[ContinuousFeatures], bottom_block: Optional[MLP],
+                 top_block: Optional[MLP], embedding_dim: int, fused: bool = True):
+        super().__init__(unique_name("dlrm_block"))
+        self.embeddings = embeddings
+        self.continuous = continuous
+        self.bottom_block = bottom_block
+        self.top_block = top_block
+        self.embedding_dim = embedding_dim
+        self.fused = fused
+
+    # stack order = sorted over {feature names} U {"bottom_block"} (core/aggregation.py:104-108)
+    def slots(self) -> Dict[str, int]:
+        keys = list(self.embeddings.feature_names)
+        if self.bottom_block is not None:
+            keys.append("bottom_block")
+        return {k: i for i, k in enumerate(sorted(keys))}
+
+    def build(self, device=None):
+        self.embeddings.build(device)
+        if self.bottom_block is not None:
+            self.bottom_block.build_from_width(len(self.continuous.features), device)
+        if self.top_block is not None:
+            self.top_block.build_from_width(self.output_width_before_top(), device)
+        self.built = True
+        return self
+
+    def output_width_before_top(self) -> int:
+        F = len(self.embeddings.feature_names) + (1 if self.bottom_block is not None else 0)
+        return F * (F - 1) // 2 + (self.embedding_dim if (self.bottom_block is not None and self.top_block is not None) else 0)
+
+    def weights(self):
+        out = {f"embeddings/{k}": v for k, v in self.embeddings.weights().items()}
+        if self.bottom_block is not None:
+            out.update({f"bottom_block/{k}": v for k, v in self.bottom_block.weights().items()})
+        if self.top_block is not None:
+            out.update({f"top_block/{k}": v for k, v in self.top_block.weights().items()})
+        return out
+
+    def bottom_forward(self, inputs: TabularData) -> Optional[torch.Tensor]:
+        if self.bottom_block is None:
+            return None
+        return self.bottom_block(self.continuous(inputs))
+
+    def interaction_forward(self, inputs: TabularData, bottom: Optional[torch.Tensor]) -> torch.Tensor:
+        """[bottom |] interactions, (B, P + F(F-1)/2)."""
+        self.build(next(iter(inputs.values())).device)
+        D = self.embedding_dim
+        slots = self.slots()
+        F = len(slots)
+        B = batch_size_of(inputs)
+        dev = next(iter(inputs.values())).device
+        with_prefix = bottom is not None and self.top_block is not None
+        P = D if with_prefix else 0
+        out = torch.empty((B, P + F * (F - 1) // 2), dtype=torch.float32, device=dev)
+        emb = self.embeddings
+        feats = emb.feature_names
+        from .core import get_feature
+        from .inputs import _as_index, _raise_on_oob
+
+        all_onehot = all(emb.feature_to_table[f].lookup_kind(get_feature(inputs, f)) == "onehot" for f in feats)
+        if self.fused and all_onehot and with_prefix == (bottom is not None):
+            oob = torch.zeros(1, dtype=torch.int32, device=dev) if emb.check_indices else None
+            idx = [_as_index(get_feature(inputs, f)).reshape(-1) for f in feats]
+            if len({i.dtype for i in idx}) > 1:
+                idx = [i.to(torch.int64) for i in idx]
+            ops.dlrm_gather_interact([emb.feature_to_table[f].table for f in feats], idx, [slots[f] for f in feats], D,
+                                     bottom, slots.get("bottom_block", -1), out, oob)
+            if oob is not None:
+                _raise_on_oob(oob, ",".join(emb.tables))
+            return out
+        # staged path: one fused gather into the (B,F,D) stack, then the interaction kernel
+        stack = torch.empty((B, F * D), dtype=torch.float32, device=dev)
+        emb.lookup_all_into(inputs, stack, {f: slots[f] * D for f in feats})
+        if bottom is not None:
+            ops.concat_columns([bottom], stack, [slots["bottom_block"] * D])
+        return ops.dot_interaction(stack.view(B, F, D), out, prefix=bottom if with_prefix else None)
+
+    def call(self, inputs: TabularData, **kwargs) -> torch.Tensor:
+        bottom = self.bottom_forward(inputs)
+        x = self.interaction_forward(inputs, bottom)
+        if self.top_block is not None:
+            x = self.top_block(x)
+        return x
+
+
+def DLRMBlock(schema: Schema, *, embedding_dim: int = None, embedding_options: EmbeddingOptions = None,
+              embeddings: Optional[EmbeddingsBlock] = None, bottom_block: Optional[MLP] = None,
+              top_block: Optional[MLP] = None) -> DLRM:
+    """blocks/dlrm.py:32-133 (same checks, same messages)."""
+    if schema is None:
+        raise ValueError("The schema is required by DLRM")
+    con_schema = schema.select_by_tag(Tags.CONTINUOUS).excluding_by_tag(Tags.TARGET)
+    cat_schema = schema.select_by_tag(Tags.CATEGORICAL).excluding_by_tag(Tags.TARGET)
+    if not len(cat_schema) > 0:
+        raise ValueError("DLRM requires categorical features")
+    if embeddings is not None and embedding_options is not None:
+        raise ValueError("Only one-of `embeddings` or `embedding_options` may be provided.")
+    if embeddings is None:
+        embeddings = _get_embeddings(embedding_dim, embedding_options, bottom_block, cat_schema)
+    dims = set(embeddings.output_dims().values())
+    if len(dims) != 1:
+        raise ValueError(f"DLRM needs all embedding tables to share one dimension, got {sorted(dims)}")
+    dim = dims.pop()
+    continuous = None
+    if len(con_schema) > 0:
+        if bottom_block is None:
+            raise ValueError(
+                "The bottom_block is required by DLRM when "
+                "continuous features are available in the schema"
+            )
+        continuous = ContinuousFeatures.from_schema(con_schema)
+        last_units = bottom_block.dense_layers[-1].units
+        if last_units != dim:
+            raise ValueError(
+                f"The embedding_dim ({dim}) needs to match the "
+                f"last layer of bottom MLP ({last_units}) "
+            )
+    else:
+        bottom_block = None
+    return DLRM(embeddings, continuous, bottom_block, top_block, dim)
+
+
+def _get_embeddings(embedding_dim, embedding_options, bottom_block, cat_schema) -> EmbeddingsBlock:
+    """blocks/dlrm.py:136-166."""
+    if embedding_dim is None:
+        raise ValueError("The embedding_dim is required")
+    if embedding_options is not None:
+        embedding_options.embedding_dim_default = embedding_dim
+    else:
+        embedding_options = EmbeddingOptions(embedding_dim_default=embedding_dim)
+    if embedding_dim is not None and bottom_block is not None:
+        last = bottom_block.dense_layers[-1]
+        if embedding_dim != last.units:
+            raise ValueError(
+                f"The embedding_dim ({embedding_dim}) needs to match the "
+                f"last layer of bottom MLP ({last.units}) "
+            )
+    return Embeddings(cat_schema, sequence_combiner=embedding_options.combiner,
+                      embeddings_initializer=embedding_options.embeddings_initializers,
+                      dim=embedding_options.embedding_dim_default)

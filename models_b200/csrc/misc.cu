@@ -1,0 +1,129 @@
+// Column concat (+cast to fp32) and row-wise L2 normalisation.
+// Replaces ConcatFeatures (merlin/models/tf/core/aggregation.py:54-66), ContinuousFeatures'
+// expand_dims (inputs/continuous.py:134-138) and L2Norm (transforms/regularization.py:27-82).
+#include <cstring>
+
+#include "mm_common.cuh"
+
+namespace mm {
+
+constexpr int MAX_PIECES = 64;
+struct ConcatParams {
+  mm_concat_piece p[MAX_PIECES];
+  int n;
+  int total_width;
+};
+
+__device__ __forceinline__ float load_as_f32(const void* src, long long i, int dtype) {
+  switch (dtype) {
+    case MM_I32: return (float)reinterpret_cast<const int32_t*>(src)[i];
+    case MM_I64: return (float)reinterpret_cast<const long long*>(src)[i];
+    case MM_F64: return (float)reinterpret_cast<const double*>(src)[i];
+    default: return reinterpret_cast<const float*>(src)[i];
+  }
+}
+
+// One thread per (row, piece-column); consecutive threads walk the pieces of one row, so the
+// writes of a row are contiguous and the reads of width-1 pieces are coalesced across rows in
+// the transposed launch below.
+__global__ void concat_columns_kernel(const __grid_constant__ ConcatParams cp, long long B,
+                                      float* __restrict__ out, long long out_stride) {
+  // blockDim.x threads cover 32 rows x (piece columns); smem transposes so that both the
+  // per-column reads (stride 1 across rows) and the row writes are coalesced.
+  extern __shared__ float tile[];  // [32][W+1]
+  const int W = cp.total_width;
+  const long long b0 = (long long)blockIdx.x * 32;
+  // read: thread -> (column c, row r) with r fastest
+  for (int e = threadIdx.x; e < W * 32; e += blockDim.x) {
+    const int r = e & 31, c = e >> 5;
+    // find the piece of flat column c
+    int pi = 0, base = 0;
+    while (pi < cp.n - 1 && c >= base + cp.p[pi].width) {
+      base += cp.p[pi].width;
+      ++pi;
+    }
+    const long long b = b0 + r;
+    float v = 0.0f;
+    if (b < B) v = load_as_f32(cp.p[pi].src, b * cp.p[pi].src_stride + (c - base), cp.p[pi].dtype);
+    tile[r * (W + 1) + c] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < W * 32; e += blockDim.x) {
+    const int c = e % W, r = e / W;
+    int pi = 0, base = 0;
+    while (pi < cp.n - 1 && c >= base + cp.p[pi].width) {
+      base += cp.p[pi].width;
+      ++pi;
+    }
+    const long long b = b0 + r;
+    if (b < B) out[b * out_stride + cp.p[pi].out_col + (c - base)] = tile[r * (W + 1) + c];
+  }
+}
+
+__global__ void l2_normalize_kernel(const float* __restrict__ x, long long B, int D, long long x_stride,
+                                    float* __restrict__ out, long long out_stride) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long b = warp0; b < B; b += n_warps) {
+    float ss = 0.0f;
+    for (int d = lane; d < D; d += 32) {
+      const float v = x[b * x_stride + d];
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(fmaxf(ss, 1e-12f));
+    for (int d = lane; d < D; d += 32) out[b * out_stride + d] = x[b * x_stride + d] / nrm;
+  }
+}
+
+}  // namespace mm
+
+extern "C" {
+
+int mm_concat_columns(const mm_concat_piece* pieces_host, int n_pieces, int64_t B, float* out,
+                      int64_t out_stride, void* stream) {
+  MM_REQUIRE(pieces_host && out && n_pieces > 0 && B >= 0, MM_ERR_ARG,
+             "mm_concat_columns: null pointer or no pieces");
+  if (B == 0) return MM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = 0; s < n_pieces; s += mm::MAX_PIECES) {
+    mm::ConcatParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.n = (n_pieces - s < mm::MAX_PIECES) ? n_pieces - s : mm::MAX_PIECES;
+    for (int i = 0; i < cp.n; ++i) {
+      const mm_concat_piece& pc = pieces_host[s + i];
+      MM_REQUIRE(pc.src && pc.width > 0 && pc.src_stride >= 0 && pc.out_col >= 0 &&
+                     (int64_t)pc.out_col + pc.width <= out_stride,
+                 MM_ERR_ARG, "mm_concat_columns: piece %d: null src, bad width or out of row", s + i);
+      MM_REQUIRE(pc.dtype >= MM_I32 && pc.dtype <= MM_F64, MM_ERR_ARG,
+                 "mm_concat_columns: piece %d: unknown dtype %d", s + i, pc.dtype);
+      cp.p[i] = pc;
+      cp.total_width += pc.width;
+    }
+    const size_t smem = (size_t)32 * (cp.total_width + 1) * sizeof(float);
+    MM_REQUIRE(smem <= 48 * 1024, MM_ERR_UNSUPPORTED,
+               "mm_concat_columns: %d columns per launch exceed the 48 KB tile", cp.total_width);
+    const unsigned blocks = (unsigned)((B + 31) / 32);
+    mm::concat_columns_kernel<<<blocks, 256, smem, st>>>(cp, B, out, out_stride);
+    int rc = mm::check_launch("mm_concat_columns");
+    if (rc) return rc;
+  }
+  return MM_OK;
+}
+
+int mm_l2_normalize(const float* x, int64_t B, int D, int64_t x_stride, float* out,
+                    int64_t out_stride, void* stream) {
+  MM_REQUIRE(x && out && B >= 0 && D > 0 && x_stride >= D && out_stride >= D, MM_ERR_ARG,
+             "mm_l2_normalize: null pointer, D<=0 or stride < D");
+  if (B == 0) return MM_OK;
+  const int threads = 256;
+  long long blocks = (B * 32 + threads - 1) / threads;
+  const long long cap = (long long)mm::sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  mm::l2_normalize_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(x, B, D, x_stride, out,
+                                                                                out_stride);
+  return mm::check_launch("mm_l2_normalize");
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+"""Model factories behind the reference constructors: DLRMModel, DCNModel, TwoTowerModel.
+
+Reference: merlin/models/tf/models/ranking.py:23-168, models/retrieval.py:106-203,
+models/base.py:1805-1854 (Model.call protocol), outputs/classification.py:72-123 (BinaryOutput),
+prediction_tasks/classification.py:59-116 (BinaryClassificationTask).  Only construction and the
+forward call are in scope — fit/compile/optimizers/metrics are not.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .blocks import MLP, CrossBlock, CrossBlockSeq, DLRM, DLRMBlock, MLPBlock, _Dense
+from .core import Block, Prediction, TabularData, default_device, to_device, unique_name
+from .inputs import EmbeddingOptions, EmbeddingsBlock, InputBlockV2
+from .retrieval import ItemRetrievalTask, TwoTowerBlock
+from .schema import Schema, Tags
+
+
+class BinaryOutput(Block):
+    """outputs/classification.py:72-123: Dense(1, activation="sigmoid") on the body output."""
+
+    def __init__(self, target: Optional[Union[str, object]] = None, name: Optional[str] = None, **kwargs):
+        tname = getattr(target, "name", target)
+        super().__init__(name or (f"{tname}/binary_output" if tname else unique_name("binary_output")))
+        self.target = tname
+        self.to_call = _Dense(1, activation="sigmoid", name=f"{self.name}/dense")
+
+    def build(self, width: Optional[int] = None, device=None):
+        self.to_call.build(width, device)
+        self.built = True
+        return self
+
+    def weights(self):
+        return {f"dense/{k}": v for k, v in self.to_call.weights().items()}
+
+    def call(self, inputs: torch.Tensor, **kwargs) -> torch.Tensor:
+        return self.to_call(inputs)
+
+
+class BinaryClassificationTask(BinaryOutput):
+    """prediction_tasks/classification.py:59-116 (v1): Dense(1, linear) followed by an fp32 sigmoid —
+    the same function as BinaryOutput, fused in the layer epilogue here."""
+
+    def __init__(self, target: Optional[str] = None, task_name: Optional[str] = None, **kwargs):
+        super().__init__(target, name=task_name or (f"{target}/binary_classification_task" if target else None))
+
+
+def parse_prediction_blocks(schema: Schema, prediction_blocks=None) -> Block:
+    """models/utils.py:12-31 / outputs/block.py:79-128: default = BinaryOutput for the (single)
+    binary-classification target of the schema."""
+    if prediction_blocks is None:
+        targets = schema.select_by_tag(Tags.BINARY_CLASSIFICATION)
+        if not len(targets):
+            targets = schema.select_by_tag(Tags.TARGET)
+        if not len(targets):
+            raise ValueError("The schema has no target column: pass `prediction_tasks` explicitly")
+        if len(targets) > 1:
+            binary = [c.name for c in targets if c.has_tag(Tags.BINARY_CLASSIFICATION)]
+            if len(binary) != 1:
+                raise NotImplementedError("multi-task outputs are outside the hot path; pass one BinaryOutput")
+            return BinaryOutput(binary[0])
+        return BinaryOutput(targets.first.name)
+    if isinstance(prediction_blocks, (list, tuple)):
+        if len(prediction_blocks) != 1:
+            raise NotImplementedError("multi-task outputs are outside the hot path")
+        prediction_blocks = prediction_blocks[0]
+    if not isinstance(prediction_blocks, Block):
+        raise ValueError(f"Unsupported prediction task {prediction_blocks!r}")
+    return prediction_blocks
+
+
+def expected_input_columns(schema: Schema) -> List[str]:
+    """models/base.py:1730-1749: non-target columns; list columns as `__values` + `__offsets`."""
+    cols = []
+    for c in schema.excluding_by_tag(Tags.TARGET):
+        if c.is_list and c.is_ragged:
+            cols += [c.name + "__values", c.name + "__offsets"]
+        else:
+            cols.append(c.name)
+    return cols
+
+
+class Model(Block):
+    """models/base.py:1621-2245, forward only: model(inputs, targets=None, training=False,
+    testing=False) with `inputs` a dict keyed by schema column names."""
+
+    def __init__(self, body: Block, prediction: Block, schema: Schema):
+        super().__init__(unique_name("model"))
+        self.body = body
+        self.prediction = prediction
+        self.schema = schema
+        self._pinned: Dict[str, torch.Tensor] = {}
+
+    @property
+    def blocks(self) -> List[Block]:
+        return [self.body, self.prediction]
+
+    def weights(self):
+        out = {f"body/{k}": v for k, v in self.body.weights().items()}
+        out.update({f"prediction/{k}": v for k, v in self.prediction.weights().items()})
+        return out
+
+    def _check_inputs(self, inputs: TabularData) -> None:
+        if not isinstance(inputs, dict):
+            raise ValueError(f"Model inputs must be a dict of features, got {type(inputs).__name__}")
+        missing = [c for c in self.input_columns() if c not in inputs]
+        if missing:
+            raise ValueError(f"Missing input features: {missing}")
+
+    def input_columns(self) -> List[str]:
+        return expected_input_columns(self.schema)
+
+    def call(self, inputs: TabularData, targets=None, training: bool = False, testing: bool = False, **kwargs):
+        self._check_inputs(inputs)
+        x = self.body(inputs, training=training, testing=testing)
+        return self.prediction(x, features=inputs, targets=targets, training=training, testing=testing)
+
+    # -- host-buffer entry point (the e2e path of bench.py) -----------------------------------
+    def forward_host(self, batch: Dict[str, np.ndarray], stream: Optional[torch.cuda.Stream] = None, **kwargs):
+        """Host numpy batch -> pinned staging -> H2D -> forward -> D2H of the predictions."""
+        dev = default_device()
+        dev_inputs = {}
+        for k in self.input_columns():
+            src = torch.from_numpy(np.ascontiguousarray(batch[k]))
+            pin = self._pinned.get(k)
+            if pin is None or pin.shape != src.shape or pin.dtype != src.dtype:
+                pin = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+                self._pinned[k] = pin
+            pin.copy_(src)
+            dev_inputs[k] = pin.to(dev, non_blocking=True)
+        out = self.call(dev_inputs, **kwargs)
+        pred = out.outputs if isinstance(out, Prediction) else out
+        return pred.cpu()
+
+
+class RankingModel(Model):
+    """DLRM / DCN: body -> (B, h) -> BinaryOutput (B,1)."""
+
+    def build(self, device=None):
+        self.body.build(device)
+        self.prediction.build(self.body_width(), device)
+        self.built = True
+        return self
+
+    def body_width(self) -> int:
+        if isinstance(self.body, DLRM):
+            if self.body.top_block is not None:
+                return self.body.top_block.dense_layers[-1].units
+            return self.body.output_width_before_top()
+        return self.body.output_width()
+
+    def call(self, inputs: TabularData, targets=None, training: bool = False, testing: bool = False, **kwargs):
+        self._check_inputs(inputs)
+        if not self.built:
+            self.build(next(iter(inputs.values())).device)
+        x = self.body(inputs, training=training)
+        return self.prediction(x)
+
+
+def DLRMModel(schema: Schema, *, embeddings: Optional[EmbeddingsBlock] = None, embedding_dim: Optional[int] = None,
+              embedding_options: Optional[EmbeddingOptions] = None, bottom_block: Optional[MLP] = None,
+              top_block: Optional[MLP] = None, prediction_tasks=None) -> RankingModel:
+    """models/ranking.py:23-92."""
+    prediction = parse_prediction_blocks(schema, prediction_tasks)
+    body = DLRMBlock(schema, embedding_dim=embedding_dim, embedding_options=embedding_options, embeddings=embeddings,
+                     bottom_block=bottom_block, top_block=top_block)
+    return RankingModel(body, prediction, schema)
+
+
+class DCNBody(Block):
+    """input_block.connect(CrossBlock(depth), deep_block) (stacked) or connect_branch(..., "concat")."""
+
+    def __init__(self, input_block: InputBlockV2, cross: CrossBlockSeq, deep: MLP, stacked: bool):
+        super().__init__(unique_name("dcn_body"))
+        self.input_block, self.cross, self.deep, self.stacked = input_block, cross, deep, stacked
+
+    def build(self, device=None):
+        self.input_block.build(device)
+        _, _, d = self.input_block.layout()
+        for l in self.cross.cross_layers:
+            l.build(d, device)
+        self.deep.build_from_width(d, device)
+        self.built = True
+        return self
+
+    def output_width(self) -> int:
+        _, _, d = self.input_block.layout()
+        last = self.deep.dense_layers[-1].units
+        return last if self.stacked else d + last
+
+    def weights(self):
+        out = {f"input/{k}": v for k, v in self.input_block.weights().items()}
+        for l in self.cross.cross_layers:
+            out.update({f"{l.name}/{k}": v for k, v in l.weights().items()})
+        out.update({f"deep/{k}": v for k, v in self.deep.weights().items()})
+        return out
+
+    def call(self, inputs: TabularData, **kwargs):
+        x0 = self.input_block(inputs)
+        c = self.cross(x0)
+        if self.stacked:
+            return self.deep(c)
+        d = self.deep(x0)
+        out = torch.empty((x0.shape[0], c.shape[1] + d.shape[1]), dtype=torch.float32, device=x0.device)
+        return ops.concat_columns([c, d], out)
+
+
+def DCNModel(schema: Schema, depth: int, deep_block: Optional[MLP] = None, stacked: bool = True,
+             input_block: Optional[InputBlockV2] = None, prediction_tasks=None, **kwargs) -> RankingModel:
+    """models/ranking.py:95-168 (default deep_block = MLPBlock([512, 256]))."""
+    deep_block = deep_block if deep_block is not None else MLPBlock([512, 256])
+    input_block = input_block or InputBlockV2(schema, **kwargs)
+    prediction = parse_prediction_blocks(schema, prediction_tasks)
+    body = DCNBody(input_block, CrossBlock(depth), deep_block, stacked)
+    return RankingModel(body, prediction, schema)
+
+
+class RetrievalModel(Model):
+    """models/base.py:2259-2489, forward only."""
+
+    def build(self, device=None):
+        self.body.build(device)
+        self.built = True
+        return self
+
+    def input_columns(self) -> List[str]:
+        tb: TwoTowerBlock = self.body
+        used = Schema(list(tb.query.inputs.schema) + [c for c in tb.item.inputs.schema
+                                                      if c.name not in tb.query.inputs.schema])
+        return expected_input_columns(used)
+
+    def call(self, inputs: TabularData, targets=None, training: bool = False, testing: bool = False, **kwargs):
+        self._check_inputs(inputs)
+        if not self.built:
+            self.build(next(iter(inputs.values())).device)
+        emb = self.body(inputs, training=False)
+        return self.prediction(emb, features=inputs, training=training, testing=testing)
+
+
+def TwoTowerModel(schema: Schema, query_tower: MLP, item_tower: Optional[MLP] = None, query_tower_tag=Tags.USER,
+                  item_tower_tag=Tags.ITEM,
+                  embedding_options: EmbeddingOptions = EmbeddingOptions(embedding_dims=None, embedding_dim_default=64,
+                                                                         infer_embedding_sizes=False,
+                                                                         infer_embedding_sizes_multiplier=2.0),
+                  post: Optional[Block] = None, prediction_tasks=None, logits_temperature: float = 1.0,
+                  samplers: Sequence = (), **kwargs) -> RetrievalModel:
+    """models/retrieval.py:106-203."""
+    if not prediction_tasks:
+        prediction_tasks = ItemRetrievalTask(schema, logits_temperature=logits_temperature, samplers=list(samplers))
+    if isinstance(prediction_tasks, (list, tuple)):
+        prediction_tasks = prediction_tasks[0]
+    two_tower = TwoTowerBlock(schema=schema, query_tower=query_tower, item_tower=item_tower,
+                              query_tower_tag=query_tower_tag, item_tower_tag=item_tower_tag,
+                              embedding_options=embedding_options, post=post)
+    return RetrievalModel(two_tower, prediction_tasks, schema)

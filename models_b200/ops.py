@@ -1,0 +1,275 @@
+"""Torch-tensor front end of the C-ABI (include/mm_b200.h).
+
+PyTorch is used for device memory and streams only: every function here checks its
+arguments, takes raw device pointers and calls one entry point of libmm_b200.so on the
+current CUDA stream.  There is no CPU path — a CPU tensor is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import ACTIVATIONS, COMBINERS, GatherTable, MM_I32, MM_I64, MM_MAX_TABLES
+
+
+def _lib():
+    return _cabi.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: the models_b200 hot path only runs on CUDA (no CPU fallback)"
+        )
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _idx_dtype(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.int32:
+        return MM_I32
+    if t.dtype == torch.int64:
+        return MM_I64
+    raise TypeError(f"{name} must be int32 or int64, got {t.dtype}")
+
+
+def _row_stride(t: torch.Tensor, name: str) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0)
+
+
+def launch_count() -> int:
+    return int(_lib().mm_launch_count())
+
+
+def init_uniform_hash(w: torch.Tensor, seed: int, lo: float = -0.05, hi: float = 0.05) -> torch.Tensor:
+    _dev(w, "w", torch.float32)
+    if not w.is_contiguous():
+        raise ValueError("w must be contiguous")
+    _cabi.check(_lib().mm_init_uniform_hash(w.data_ptr(), w.numel(), seed & (2**64 - 1), lo, hi, _stream()),
+                "mm_init_uniform_hash")
+    return w
+
+
+def _table_array(weights: Sequence[torch.Tensor], indices: Sequence[torch.Tensor], out_cols: Sequence[int], B: int):
+    n = len(weights)
+    if not (1 <= n <= MM_MAX_TABLES):
+        raise ValueError(f"between 1 and {MM_MAX_TABLES} tables per launch, got {n}")
+    if not (len(indices) == n and len(out_cols) == n):
+        raise ValueError("weights / indices / out_cols length mismatch")
+    arr = (GatherTable * n)()
+    dt = _idx_dtype(indices[0], "indices[0]")
+    for t in range(n):
+        w = _dev(weights[t], f"weights[{t}]", torch.float32)
+        ix = _dev(indices[t], f"indices[{t}]")
+        if w.dim() != 2 or not w.is_contiguous():
+            raise ValueError(f"weights[{t}] must be a contiguous (rows, dim) matrix")
+        if _idx_dtype(ix, f"indices[{t}]") != dt:
+            raise TypeError("all index tensors of one launch must share a dtype")
+        if ix.numel() != B or not ix.is_contiguous():
+            raise ValueError(f"indices[{t}] must be contiguous with {B} elements, got {tuple(ix.shape)}")
+        arr[t].weights = w.data_ptr()
+        arr[t].indices = ix.data_ptr()
+        arr[t].rows = w.shape[0]
+        arr[t].dim = w.shape[1]
+        arr[t].out_col = int(out_cols[t])
+    return arr, n, dt
+
+
+def gather_multi(weights, indices, out_cols, out: torch.Tensor, oob: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b, out_cols[t] : out_cols[t]+dim_t] = weights[t][indices[t][b]]   (mm_gather_multi)."""
+    _dev(out, "out", torch.float32)
+    B = out.shape[0]
+    stride = _row_stride(out, "out")
+    for s in range(0, len(weights), MM_MAX_TABLES):
+        e = min(len(weights), s + MM_MAX_TABLES)
+        arr, n, dt = _table_array(weights[s:e], indices[s:e], out_cols[s:e], B)
+        _cabi.check(_lib().mm_gather_multi(arr, n, dt, B, out.data_ptr(), stride, _ptr(oob), _stream()),
+                    "mm_gather_multi")
+    return out
+
+
+def gather_bag(weight, values, offsets, combiner: str, out: torch.Tensor, out_col: int = 0,
+               oob: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(weight, "weight", torch.float32), _dev(values, "values"), _dev(offsets, "offsets"), _dev(out, "out", torch.float32)
+    if combiner not in ("mean", "sum", "sqrtn"):
+        raise ValueError(f"combiner must be mean, sum or sqrtn, got {combiner!r}")
+    B = out.shape[0]
+    if offsets.numel() != B + 1:
+        raise ValueError(f"offsets must have B+1={B + 1} elements, got {offsets.numel()}")
+    _cabi.check(
+        _lib().mm_gather_bag(weight.data_ptr(), weight.shape[0], weight.shape[1], values.data_ptr(),
+                             _idx_dtype(values, "values"), offsets.data_ptr(), _idx_dtype(offsets, "offsets"),
+                             B, COMBINERS[combiner], out.data_ptr(), _row_stride(out, "out"), out_col,
+                             _ptr(oob), _stream()),
+        "mm_gather_bag")
+    return out
+
+
+def gather_seq(weight, ids, combiner: str, out: torch.Tensor, out_col: int = 0,
+               oob: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(weight, "weight", torch.float32), _dev(ids, "ids"), _dev(out, "out", torch.float32)
+    if combiner not in ("mean", "sum", "max"):
+        raise ValueError(f"sequence combiner must be mean, sum or max, got {combiner!r}")
+    if ids.dim() != 2 or not ids.is_contiguous():
+        raise ValueError("ids must be a contiguous (B, L) matrix")
+    B, L = ids.shape
+    _cabi.check(
+        _lib().mm_gather_seq(weight.data_ptr(), weight.shape[0], weight.shape[1], ids.data_ptr(),
+                             _idx_dtype(ids, "ids"), B, L, COMBINERS[combiner], out.data_ptr(),
+                             _row_stride(out, "out"), out_col, _ptr(oob), _stream()),
+        "mm_gather_seq")
+    return out
+
+
+def dot_interaction(x: torch.Tensor, out: torch.Tensor, prefix: Optional[torch.Tensor] = None,
+                    self_interaction: bool = False) -> torch.Tensor:
+    """x (B,F,D) -> out[:, :P] = prefix, out[:, P:] = upper-triangle pairwise dots."""
+    _dev(x, "x", torch.float32), _dev(out, "out", torch.float32)
+    if x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous (B, F, D) tensor")
+    B, F, D = x.shape
+    P = 0 if prefix is None else prefix.shape[1]
+    _cabi.check(
+        _lib().mm_dot_interaction(x.data_ptr(), B, F, D, F * D, _ptr(prefix), P,
+                                  0 if prefix is None else _row_stride(_dev(prefix, "prefix", torch.float32), "prefix"),
+                                  int(self_interaction), out.data_ptr(), _row_stride(out, "out"), _stream()),
+        "mm_dot_interaction")
+    return out
+
+
+def dlrm_gather_interact(weights, indices, slots, D: int, bottom: Optional[torch.Tensor], bottom_slot: int,
+                         out: torch.Tensor, oob: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(out, "out", torch.float32)
+    B = out.shape[0]
+    arr, n, dt = _table_array(weights, indices, [s * D for s in slots], B)
+    _cabi.check(
+        _lib().mm_dlrm_gather_interact(arr, n, dt, B, D, _ptr(bottom),
+                                       0 if bottom is None else _row_stride(_dev(bottom, "bottom", torch.float32), "bottom"),
+                                       bottom_slot, out.data_ptr(), _row_stride(out, "out"), _ptr(oob), _stream()),
+        "mm_dlrm_gather_interact")
+    return out
+
+
+def dense_fp32(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], act: Optional[str],
+               out: torch.Tensor, x0: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(x @ W + bias)   or, with x0, the DCN-v2 cross  out = x0 * (x @ W + bias) + x."""
+    _dev(x, "x", torch.float32), _dev(W, "W", torch.float32), _dev(out, "out", torch.float32)
+    if act not in ACTIVATIONS:
+        raise ValueError(f"unsupported activation {act!r}; supported: {sorted(k for k in ACTIVATIONS if k)}")
+    if W.dim() != 2 or not W.is_contiguous():
+        raise ValueError("W must be a contiguous (K, N) matrix")
+    K, N = W.shape
+    if x.shape[1] != K:
+        raise ValueError(f"x has {x.shape[1]} columns but the kernel has {K} rows")
+    B = x.shape[0]
+    _cabi.check(
+        _lib().mm_dense_fp32(x.data_ptr(), B, K, _row_stride(x, "x"), W.data_ptr(), _ptr(bias), N,
+                             ACTIVATIONS[act], _ptr(x0), 0 if x0 is None else _row_stride(x0, "x0"),
+                             out.data_ptr(), _row_stride(out, "out"), _stream()),
+        "mm_dense_fp32")
+    return out
+
+
+def rowwise_dot(q: torch.Tensor, items: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _dev(q, "q", torch.float32), _dev(items, "items", torch.float32), _dev(out, "out", torch.float32)
+    B, D = q.shape
+    _cabi.check(_lib().mm_rowwise_dot(q.data_ptr(), items.data_ptr(), B, D, _row_stride(q, "q"),
+                                      _row_stride(items, "items"), out.data_ptr(), _stream()),
+                "mm_rowwise_dot")
+    return out
+
+
+def inbatch_scores(q, pos, neg, out, pos_ids=None, neg_ids=None, downscore=True,
+                   false_neg_score: float = -655.04, pos_prob=None, neg_prob=None,
+                   temperature: float = 1.0) -> torch.Tensor:
+    for n_, t_ in (("q", q), ("pos", pos), ("neg", neg), ("out", out)):
+        _dev(t_, n_, torch.float32)
+        if not t_.is_contiguous():
+            raise ValueError(f"{n_} must be contiguous")
+    B, D = q.shape
+    N = neg.shape[0]
+    id_dt = MM_I64
+    if downscore:
+        if pos_ids is None or neg_ids is None:
+            raise ValueError("downscore_false_negatives requires positive and negative item ids")
+        neg_ids = neg_ids.reshape(-1).contiguous()
+        # reference: positive ids are cast to the negative ids' dtype (utils/tf_utils.py:136)
+        pos_ids = pos_ids.reshape(-1).to(neg_ids.dtype).contiguous()
+        id_dt = _idx_dtype(neg_ids, "neg_ids")
+    _cabi.check(
+        _lib().mm_inbatch_scores(q.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, N, D, _ptr(pos_ids),
+                                 _ptr(neg_ids), id_dt, int(bool(downscore)), float(false_neg_score),
+                                 _ptr(pos_prob), _ptr(neg_prob), float(temperature), out.data_ptr(),
+                                 out.stride(0), _stream()),
+        "mm_inbatch_scores")
+    return out
+
+
+_CONCAT_DTYPES = {torch.int32: _cabi.MM_I32, torch.int64: _cabi.MM_I64, torch.float32: _cabi.MM_F32,
+                  torch.float64: _cabi.MM_F64}
+
+
+def concat_columns(pieces: Sequence[torch.Tensor], out: torch.Tensor, out_cols: Optional[Sequence[int]] = None,
+                   max_width: int = 256) -> torch.Tensor:
+    """out[:, out_cols[i] : out_cols[i]+w_i] = float32(pieces[i])  — (B,) pieces count as (B,1).
+
+    Pieces must already be in the reference's sorted-name order (core/aggregation.py:54-66)."""
+    _dev(out, "out", torch.float32)
+    B = out.shape[0]
+    stride = _row_stride(out, "out")
+    flat = []
+    col = 0
+    for i, t in enumerate(pieces):
+        _dev(t, f"pieces[{i}]")
+        if t.dtype not in _CONCAT_DTYPES:
+            raise TypeError(f"pieces[{i}]: unsupported dtype {t.dtype}")
+        if t.dim() == 1:
+            t = t.unsqueeze(1)
+        if t.dim() != 2 or t.shape[0] != B or (t.shape[1] > 1 and t.stride(1) != 1):
+            raise ValueError(f"pieces[{i}] must be (B,) or (B,w) with unit inner stride, got {tuple(t.shape)}")
+        w = t.shape[1]
+        oc = col if out_cols is None else int(out_cols[i])
+        for c0 in range(0, w, max_width):  # split very wide pieces so a launch tile fits in smem
+            flat.append((t.data_ptr() + c0 * t.element_size(), t.stride(0), min(max_width, w - c0),
+                         _CONCAT_DTYPES[t.dtype], oc + c0))
+        col = oc + w
+    groups, cur, cur_w = [], [], 0
+    for f in flat:
+        if cur and (cur_w + f[2] > max_width or len(cur) == 64):
+            groups.append(cur)
+            cur, cur_w = [], 0
+        cur.append(f)
+        cur_w += f[2]
+    if cur:
+        groups.append(cur)
+    for g in groups:
+        arr = (_cabi.ConcatPiece * len(g))()
+        for i, (ptr, sstride, w, dt, oc) in enumerate(g):
+            arr[i].src, arr[i].src_stride, arr[i].width, arr[i].dtype, arr[i].out_col = ptr, sstride, w, dt, oc
+        _cabi.check(_lib().mm_concat_columns(arr, len(g), B, out.data_ptr(), stride, _stream()), "mm_concat_columns")
+    return out
+
+
+def l2_normalize(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(x, "x", torch.float32)
+    if out is None:
+        out = torch.empty_like(x)
+    _cabi.check(_lib().mm_l2_normalize(x.data_ptr(), x.shape[0], x.shape[1], _row_stride(x, "x"), out.data_ptr(),
+                                       _row_stride(out, "out"), _stream()), "mm_l2_normalize")
+    return out
