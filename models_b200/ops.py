@@ -96,6 +96,8 @@ def gather_multi(weights, indices, out_cols, out: torch.Tensor, oob: Optional[to
     _dev(out, "out", torch.float32)
     B = out.shape[0]
     stride = _row_stride(out, "out")
+    if B == 0:
+        return out
     for s in range(0, len(weights), MM_MAX_TABLES):
         e = min(len(weights), s + MM_MAX_TABLES)
         arr, n, dt = _table_array(weights[s:e], indices[s:e], out_cols[s:e], B)

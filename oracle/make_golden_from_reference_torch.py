@@ -1,0 +1,191 @@
+"""Generate golden vectors by EXECUTING the reference's own PyTorch backend
+(/root/reference/merlin/models/torch) in the build container — TEST INFRASTRUCTURE.
+
+    python oracle/make_golden_from_reference_torch.py      # writes tests/golden/ref_torch_*.npz
+
+The reference cannot be imported as a package here: merlin-core (merlin.schema, merlin.dispatch,
+merlin.dtypes, ...), merlin-dataloader, torchmetrics and pytorch_lightning are not installed and
+there is no network.  This script therefore registers *stand-in modules* for those third-party
+packages (a functools.singledispatch-backed LazyDispatcher, this repo's Schema shim as
+merlin.schema, inert placeholders for the rest), maps the `merlin.models.torch` package path to
+the reference tree WITHOUT running its __init__ (which imports the data loader), and then imports
+and runs the reference's module files unmodified, from where they lie:
+
+  torch/transforms/agg.py   Concat, Stack            (sorted-name aggregation)
+  torch/blocks/dlrm.py      DLRMInteraction, InteractionBlock
+  torch/blocks/cross.py     CrossBlock, LazyMirrorLinear
+  torch/blocks/mlp.py       MLPBlock
+  torch/inputs/embedding.py EmbeddingTable.forward_bag path via F.embedding_bag semantics
+
+Nothing is copied from the reference; only its outputs on seeded inputs are stored, together with
+the inputs and weights, so tests/golden/replay.py can re-evaluate the oracle on the GPU box where
+/root/reference does not exist.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+from functools import singledispatch
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+OUT = ROOT / "tests" / "golden"
+
+
+class _Inert:
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Inert()
+
+    def __getattr__(self, n):
+        return _Inert()
+
+
+class LazyDispatcher:
+    """Stand-in for merlin.dispatch.lazy.LazyDispatcher (merlin-core): singledispatch + no-op
+    lazy registration."""
+
+    def __init__(self, func_or_name):
+        if callable(func_or_name):
+            self.__name__ = func_or_name.__name__
+            self.dispatcher = singledispatch(func_or_name)
+        else:
+            self.__name__ = str(func_or_name)
+
+            def _default(*a, **k):
+                raise NotImplementedError(self.__name__)
+
+            self.dispatcher = singledispatch(_default)
+
+    def register(self, cls, func=None):
+        return self.dispatcher.register(cls, func=func)
+
+    def register_lazy(self, toplevel):
+        return lambda f: f
+
+    def dispatch(self, cls):
+        return self.dispatcher.dispatch(cls)
+
+    def __call__(self, arg, *a, **k):
+        return self.dispatcher.dispatch(type(arg))(arg, *a, **k)
+
+
+def _ns(name, path=None, **attrs):
+    m = types.ModuleType(name)
+    if path:
+        m.__path__ = [str(path)]
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install_stand_ins():
+    sys.path.insert(0, str(ROOT))
+    import models_b200.schema as S
+
+    _ns("merlin", REF / "merlin")
+    _ns("merlin.schema", None, Schema=S.Schema, Tags=S.Tags, ColumnSchema=S.ColumnSchema, TagSet=set, TagsType=object)
+    _ns("merlin.schema.tags", None, TagsType=object, Tags=S.Tags)
+    _ns("merlin.schema.io", None)
+    _ns("merlin.schema.io.tensorflow_metadata", None, TensorflowMetadata=_Inert)
+    _ns("merlin.dtypes", None, float32=_Inert(), float64=_Inert(), int32=_Inert(), int64=_Inert())
+    _ns("merlin.io", None, Dataset=_Inert)
+    _ns("merlin.table", None, TensorTable=_Inert)
+    _ns("merlin.dataloader", None)
+    _ns("merlin.dataloader.torch", None, Loader=_Inert)
+    _ns("merlin.core", None)
+    _ns("merlin.core.dispatch", None, DataFrameType=object)
+    _ns("merlin.dispatch", None)
+    _ns("merlin.dispatch.lazy", None, LazyDispatcher=LazyDispatcher)
+    _ns("torchmetrics", None, Metric=_Inert, AUROC=_Inert, Accuracy=_Inert, Precision=_Inert, Recall=_Inert,
+        MeanSquaredError=_Inert, MetricCollection=_Inert)
+    _ns("pytorch_lightning", None, LightningModule=object, Trainer=_Inert, LightningDataModule=object)
+    _ns("merlin.models", REF / "merlin" / "models")
+    _ns("merlin.models.torch", REF / "merlin" / "models" / "torch")
+    for sub in ("blocks", "inputs", "utils", "transforms", "outputs", "models"):
+        _ns(f"merlin.models.torch.{sub}", REF / "merlin" / "models" / "torch" / sub)
+    _ns("merlin.models.utils", REF / "merlin" / "models" / "utils")
+
+
+def main():
+    if not REF.exists():
+        raise SystemExit("/root/reference is not present: golden vectors can only be regenerated in the build container")
+    install_stand_ins()
+    import torch
+
+    agg = importlib.import_module("merlin.models.torch.transforms.agg")
+    dlrm = importlib.import_module("merlin.models.torch.blocks.dlrm")
+    cross = importlib.import_module("merlin.models.torch.blocks.cross")
+    mlpm = importlib.import_module("merlin.models.torch.blocks.mlp")
+    OUT.mkdir(parents=True, exist_ok=True)
+    rng = np.random.default_rng(20260924)
+    torch.manual_seed(0)
+
+    # ---- 1. Stack + DLRMInteraction + InteractionBlock (shortcut concat) -----------------------
+    B, D = 33, 16
+    names = ["C1", "C10", "C2", "C21", "C3", "continuous"]  # 'continuous' = bottom-MLP output key
+    feats = {n: rng.standard_normal((B, D)).astype(np.float32) for n in names}
+    tin = {k: torch.from_numpy(v) for k, v in feats.items()}
+    stacked = agg.Stack(dim=1)(tin)
+    inter = dlrm.DLRMInteraction()(stacked)
+    block = dlrm.InteractionBlock(dlrm.DLRMInteraction())
+    block_out = block(tin)
+    np.savez(OUT / "ref_torch_dlrm_interaction.npz", kind="dlrm_interaction", names=np.array(names),
+             **{f"in_{k}": v for k, v in feats.items()}, stacked=stacked.numpy(), interactions=inter.numpy(),
+             block_out=block_out.numpy())
+
+    # ---- 2. Concat (sorted names, (B,) -> (B,1), float cast) -----------------------------------
+    cfe = {"I1": rng.random(B).astype(np.float32), "I10": rng.random(B).astype(np.float32),
+           "I2": rng.random((B, 1)).astype(np.float32), "emb_b": rng.standard_normal((B, 5)).astype(np.float32),
+           "Z": rng.integers(0, 5, (B, 2)).astype(np.int64)}
+    cat = agg.Concat()({k: torch.from_numpy(v) for k, v in cfe.items()})
+    np.savez(OUT / "ref_torch_concat.npz", kind="concat", names=np.array(sorted(cfe)),
+             **{f"in_{k}": v for k, v in cfe.items()}, out=cat.numpy())
+
+    # ---- 3. CrossBlock (DCN-v2) ----------------------------------------------------------------
+    d, depth = 24, 3
+    x = rng.standard_normal((B, d)).astype(np.float32)
+    cb = cross.CrossBlock.with_depth(depth)
+    y = cb(torch.from_numpy(x))
+    ws = []
+    for m in cb.values:
+        lin = m if isinstance(m, torch.nn.Linear) else [c for c in m.modules() if isinstance(c, torch.nn.Linear)][0]
+        ws.append((lin.weight.detach().numpy().T.copy(), lin.bias.detach().numpy().copy()))
+    np.savez(OUT / "ref_torch_cross.npz", kind="cross", x=x, out=y.detach().numpy(),
+             **{f"kernel_{i}": w for i, (w, _) in enumerate(ws)}, **{f"bias_{i}": b for i, (_, b) in enumerate(ws)})
+
+    # ---- 4. MLPBlock ---------------------------------------------------------------------------
+    xin = rng.standard_normal((B, 13)).astype(np.float32)
+    mlp = mlpm.MLPBlock([32, 16])
+    ym = mlp(torch.from_numpy(xin))
+    lins = [m for m in mlp.modules() if isinstance(m, torch.nn.Linear)]
+    np.savez(OUT / "ref_torch_mlp.npz", kind="mlp", x=xin, out=ym.detach().numpy(),
+             **{f"kernel_{i}": l.weight.detach().numpy().T.copy() for i, l in enumerate(lins)},
+             **{f"bias_{i}": l.bias.detach().numpy().copy() for i, l in enumerate(lins)})
+
+    # ---- 5. embedding bag (the op torch/inputs/embedding.py:264-293 dispatches to) --------------
+    emb = importlib.import_module("merlin.models.torch.inputs.embedding")
+    table = rng.standard_normal((19, 8)).astype(np.float32)
+    lens = rng.integers(1, 5, B)
+    offsets = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    values = rng.integers(0, 19, offsets[-1]).astype(np.int64)
+    outs = {}
+    for mode in ("mean", "sum"):
+        outs[mode] = torch.nn.functional.embedding_bag(torch.from_numpy(values), torch.from_numpy(table),
+                                                       torch.from_numpy(offsets[:-1]), mode=mode).numpy()
+    src = Path(emb.__file__).read_text()
+    assert "embedding_bag" in src, "reference torch EmbeddingTable no longer uses F.embedding_bag"
+    np.savez(OUT / "ref_torch_embedding_bag.npz", kind="embedding_bag", table=table, values=values, offsets=offsets,
+             out_mean=outs["mean"], out_sum=outs["sum"])
+    print("wrote", sorted(p.name for p in OUT.glob("ref_torch_*.npz")))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+"""Re-evaluate the CPU oracle on the inputs stored in a golden fixture and compare with the
+stored outputs.  `ref_torch_*.npz` outputs were produced by the reference's own torch backend
+(oracle/make_golden_from_reference_torch.py); `oracle_*.npz` by the oracle itself
+(tests/golden/make_golden.py) and guard against drift."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+
+from oracle import oracle
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def load(path):
+    z = np.load(path, allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def layers_from(z, prefix="", act="relu", n=None):
+    out = []
+    i = 0
+    while f"{prefix}kernel_{i}" in z:
+        out.append({"kernel": z[f"{prefix}kernel_{i}"], "bias": z.get(f"{prefix}bias_{i}"), "activation": act})
+        i += 1
+    return out
+
+
+def check(path: Path) -> None:
+    z = load(path)
+    kind = str(z["kind"])
+    if kind == "dlrm_interaction":
+        names = [str(n) for n in z["names"]]
+        feats = {n: z[f"in_{n}"] for n in names}
+        stacked = oracle.stack_features(feats, axis=1)
+        assert np.array_equal(stacked, z["stacked"]), "sorted-name stack order differs from the reference"
+        inter = oracle.dot_interaction(stacked)
+        np.testing.assert_allclose(inter, z["interactions"], rtol=RTOL, atol=ATOL)
+        # InteractionBlock: cat((inputs["continuous"], interactions)) — bottom/continuous first
+        np.testing.assert_allclose(np.concatenate([feats["continuous"], inter], axis=1), z["block_out"], rtol=RTOL, atol=ATOL)
+    elif kind == "concat":
+        feats = {str(n): z[f"in_{n}"] for n in z["names"]}
+        assert np.array_equal(oracle.concat_features(feats), z["out"])
+    elif kind == "cross":
+        ls = [{"kernel": l["kernel"], "bias": l["bias"]} for l in layers_from(z)]
+        np.testing.assert_allclose(oracle.cross_layers(z["x"], ls), z["out"], rtol=1e-4, atol=1e-5)
+    elif kind == "mlp":
+        np.testing.assert_allclose(oracle.mlp(z["x"], layers_from(z, act="relu")), z["out"], rtol=RTOL, atol=ATOL)
+    elif kind == "embedding_bag":
+        for mode in ("mean", "sum"):
+            got = oracle.embedding_bag(z["table"], z["values"], z["offsets"], mode)
+            np.testing.assert_allclose(got, z[f"out_{mode}"], rtol=RTOL, atol=ATOL)
+    elif kind == "oracle_model":
+        spec = json.loads(str(z["spec"]))
+        got = run_model_fixture(z, spec)
+        np.testing.assert_allclose(got, z["expected"], rtol=RTOL, atol=ATOL)
+    else:
+        raise AssertionError(f"unknown golden kind {kind!r} in {path}")
+
+
+def unpack_layers(z, name):
+    out = []
+    i = 0
+    while f"{name}_kernel_{i}" in z:
+        b = z[f"{name}_bias_{i}"] if f"{name}_bias_{i}" in z else None
+        out.append({"kernel": z[f"{name}_kernel_{i}"], "bias": b, "activation": str(z[f"{name}_act_{i}"])})
+        i += 1
+    return out
+
+
+def run_model_fixture(z, spec):
+    batch = {k[len("batch_"):]: z[k] for k in z if k.startswith("batch_")}
+    tables = {k[len("table_"):]: z[k] for k in z if k.startswith("table_")}
+    f2t = spec["feature_table"]
+    if spec["model"] == "dlrm":
+        return oracle.dlrm_forward(batch, tables, f2t, spec["continuous"], unpack_layers(z, "bottom"),
+                                   unpack_layers(z, "top"), unpack_layers(z, "head")[0])
+    if spec["model"] == "dcn":
+        cross = [{"kernel": l["kernel"], "bias": l["bias"]} for l in unpack_layers(z, "cross")]
+        return oracle.dcn_forward(batch, tables, f2t, spec["continuous"], cross, unpack_layers(z, "deep"),
+                                  unpack_layers(z, "head")[0])
+    if spec["model"] == "two_tower":
+        q = oracle.tower_forward(batch, tables, spec["query_feature_table"], spec["query_continuous"], unpack_layers(z, "query"))
+        it = oracle.tower_forward(batch, tables, spec["item_feature_table"], spec["item_continuous"], unpack_layers(z, "item"))
+        ids = batch[spec["item_id"]]
+        out, _ = oracle.contrastive_logits(q, it, it, ids, ids, True, oracle.MIN_FLOAT, temperature=spec["temperature"])
+        return out
+    raise AssertionError(spec["model"])

@@ -1,0 +1,136 @@
+"""CUDA path against the COMMITTED golden fixtures: outputs of the reference's own torch backend
+(tests/golden/ref_torch_*.npz) and the oracle's model-level vectors (oracle_*.npz)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import models_b200 as mm
+from models_b200 import datasets, ops
+from tests.golden import replay
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).parent / "golden"
+RTOL, ATOL = 1e-4, 1e-5
+
+
+def dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def test_reference_torch_dlrm_interaction(device):
+    z = replay.load(G / "ref_torch_dlrm_interaction.npz")
+    names = [str(n) for n in z["names"]]
+    B, D = z[f"in_{names[0]}"].shape
+    F = len(names)
+    # StackFeatures layout produced by the concat kernel in sorted-name order
+    stack = torch.empty((B, F * D), dtype=torch.float32, device=device)
+    ops.concat_columns([dev(z[f"in_{n}"], device) for n in sorted(names)], stack)
+    assert np.array_equal(stack.cpu().numpy().reshape(B, F, D), z["stacked"])
+    out = torch.empty((B, D + F * (F - 1) // 2), dtype=torch.float32, device=device)
+    ops.dot_interaction(stack.view(B, F, D), out, prefix=dev(z["in_continuous"], device))
+    np.testing.assert_allclose(out.cpu().numpy(), z["block_out"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out.cpu().numpy()[:, D:], z["interactions"], rtol=RTOL, atol=ATOL)
+
+
+def test_reference_torch_concat(device):
+    z = replay.load(G / "ref_torch_concat.npz")
+    names = sorted(str(n) for n in z["names"])
+    out = torch.empty(z["out"].shape, dtype=torch.float32, device=device)
+    ops.concat_columns([dev(z[f"in_{n}"], device) for n in names], out)
+    assert np.array_equal(out.cpu().numpy(), z["out"])
+
+
+def test_reference_torch_cross_and_mlp(device):
+    z = replay.load(G / "ref_torch_cross.npz")
+    x0 = dev(z["x"], device)
+    x = x0
+    i = 0
+    while f"kernel_{i}" in z:
+        out = torch.empty_like(x0)
+        x = ops.dense_fp32(x, dev(z[f"kernel_{i}"], device), dev(z[f"bias_{i}"], device), None, out, x0=x0)
+        i += 1
+    assert i == 3
+    np.testing.assert_allclose(x.cpu().numpy(), z["out"], rtol=RTOL, atol=ATOL)
+    m = replay.load(G / "ref_torch_mlp.npz")
+    h = dev(m["x"], device)
+    i = 0
+    while f"kernel_{i}" in m:
+        W = dev(m[f"kernel_{i}"], device)
+        o = torch.empty((h.shape[0], W.shape[1]), dtype=torch.float32, device=device)
+        h = ops.dense_fp32(h, W, dev(m[f"bias_{i}"], device), "relu", o)
+        i += 1
+    np.testing.assert_allclose(h.cpu().numpy(), m["out"], rtol=RTOL, atol=ATOL)
+
+
+def test_reference_torch_embedding_bag(device):
+    z = replay.load(G / "ref_torch_embedding_bag.npz")
+    B = len(z["offsets"]) - 1
+    for mode in ("mean", "sum"):
+        out = torch.empty((B, z["table"].shape[1]), dtype=torch.float32, device=device)
+        ops.gather_bag(dev(z["table"], device), dev(z["values"], device), dev(z["offsets"], device), mode, out)
+        np.testing.assert_allclose(out.cpu().numpy(), z[f"out_{mode}"], rtol=1e-6, atol=1e-7)
+
+
+def _set_mlp(mlp, layers):
+    assert len(mlp.dense_layers) == len(layers)
+    for l, w in zip(mlp.dense_layers, layers):
+        assert l.activation == w["activation"]
+        l.set_weights(w["kernel"], w["bias"])
+
+
+def _set_tables(emb, z):
+    for name, t in emb.tables.items():
+        t.table = torch.from_numpy(z[f"table_{name}"]).cuda().contiguous()
+        assert t.table.shape == (t.input_dim, t.dim)
+        t.built = True
+
+
+def test_golden_dlrm_model(device):
+    z = replay.load(G / "oracle_dlrm_criteo_small.npz")
+    schema = datasets.criteo_schema({k: min(v, 200) for k, v in datasets.CRITEO_MAX.items()})
+    model = mm.DLRMModel(schema, embedding_dim=16, bottom_block=mm.MLPBlock([32, 16]), top_block=mm.MLPBlock([32, 16, 8]))
+    _set_tables(model.body.embeddings, z)
+    _set_mlp(model.body.bottom_block, replay.unpack_layers(z, "bottom"))
+    _set_mlp(model.body.top_block, replay.unpack_layers(z, "top"))
+    h = replay.unpack_layers(z, "head")[0]
+    model.prediction.to_call.set_weights(h["kernel"], h["bias"])
+    batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
+    for fused in (True, False):
+        model.body.fused = fused
+        np.testing.assert_allclose(model(batch).cpu().numpy(), z["expected"], rtol=2e-4, atol=2e-6)
+
+
+def test_golden_dcn_model(device):
+    z = replay.load(G / "oracle_dcn_criteo_small.npz")
+    schema = datasets.criteo_schema({k: min(v, 200) for k, v in datasets.CRITEO_MAX.items()})
+    model = mm.DCNModel(schema, depth=3, deep_block=mm.MLPBlock([32, 16]))
+    _set_tables(model.body.input_block.embeddings, z)
+    cross = replay.unpack_layers(z, "cross")
+    d = cross[0]["kernel"].shape[0]
+    for l, w in zip(model.body.cross.cross_layers, cross):
+        l.build(d, device)
+        l.dense.set_weights(w["kernel"], w["bias"])
+    _set_mlp(model.body.deep, replay.unpack_layers(z, "deep"))
+    h = replay.unpack_layers(z, "head")[0]
+    model.prediction.to_call.set_weights(h["kernel"], h["bias"])
+    batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
+    np.testing.assert_allclose(model(batch).cpu().numpy(), z["expected"], rtol=2e-4, atol=2e-6)
+
+
+def test_golden_two_tower_model(device):
+    z = replay.load(G / "oracle_two_tower_ml1m_small.npz")
+    spec = json.loads(str(z["spec"]))
+    schema = datasets.movielens_1m_schema()
+    model = mm.TwoTowerModel(schema, query_tower=mm.MLPBlock([32, 16]), item_tower=mm.MLPBlock([32, 16]),
+                             embedding_options=mm.EmbeddingOptions(embedding_dim_default=16),
+                             logits_temperature=spec["temperature"])
+    _set_tables(model.body.query.inputs.embeddings, z)
+    _set_tables(model.body.item.inputs.embeddings, z)
+    _set_mlp(model.body.query.mlp, replay.unpack_layers(z, "query"))
+    _set_mlp(model.body.item.mlp, replay.unpack_layers(z, "item"))
+    batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
+    pred = model(batch, training=True)
+    np.testing.assert_allclose(pred.outputs.cpu().numpy(), z["expected"], rtol=2e-4, atol=2e-5)
