@@ -159,6 +159,30 @@ int mm_dense_fp32(const float* x, int64_t B, int K, int64_t x_stride, const floa
                   float* out, int64_t out_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K4/K7  Tensor-core dense layer (tcgen05.mma kind::f16, TMA-fed, TMEM accumulators).
+ * fp32 operands are carried as split-bf16 pairs (hi, lo): x ~ hi + lo with
+ * hi = bf16(x), lo = bf16(x - hi).  passes = 3 computes hi*hi + hi*lo + lo*hi in one fp32
+ * TMEM accumulator (|err| ~ 2^-16 relative: fp32-grade, holds the 1e-3 logit tolerance);
+ * passes = 1 is plain bf16.
+ *   a_split : (M, 2*Kp) bf16, row = [hi(0..Kp) | lo(0..Kp)], Kp = K padded to 64
+ *   w_split : (Np, 2*Kp) bf16, K-major transpose of the Keras kernel, same split, Np = N
+ *             padded to 16 — produced once by mm_split_weights
+ *   out_f32 : (M, N) fp32 (nullable);  out_split : (M, 2*Np_next) bf16 for the next layer
+ *             (nullable; its padding columns are written as zeros)
+ *   x0/xres : fp32 (M, N) operands of the cross epilogue (nullable, both or none)
+ * ------------------------------------------------------------------------------------- */
+/* padded operand sizes used by the tensor-core path: Kp = ceil64(K); Np = ceil16(N) (N<=256) or ceil128(N) */
+int mm_tc_padded_k(int K);
+int mm_tc_padded_n(int N);
+int mm_split_rows(const float* x, int64_t M, int K, int64_t x_stride, void* out_split, int Kp,
+                  void* stream);
+int mm_split_weights(const float* W, int K, int N, void* w_split, int Kp, int Np, void* stream);
+int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_split, int N, int Np,
+                const float* bias, int act, int passes, const float* x0, const float* xres,
+                int64_t x_stride, float* out_f32, int64_t out_stride, void* out_split,
+                int out_Kp, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * K8/K9  Two-tower scoring.
  * mm_rowwise_dot: inference scorer  s[b] = sum_d q[b,d]*i[b,d]
  *   (blocks/retrieval/base.py:278-281; outputs/contrastive.py:305-307).

@@ -64,6 +64,12 @@ SIGNATURES = {
     "mm_dot_interaction": (_i, [_vp, _i64, _i, _i, _i64, _vp, _i, _i64, _i, _vp, _i64, _vp]),
     "mm_dlrm_gather_interact": (_i, [_tables, _i, _i, _i64, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "mm_dense_fp32": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64, _vp]),
+    "mm_tc_padded_k": (_i, [_i]),
+    "mm_tc_padded_n": (_i, [_i]),
+    "mm_split_rows": (_i, [_vp, _i64, _i, _i64, _vp, _i, _vp]),
+    "mm_split_weights": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
+    "mm_dense_tc": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _i64, _vp, _i64,
+                         _vp, _i, _vp]),
     "mm_rowwise_dot": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
     "mm_inbatch_scores": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _f,
                                _vp, _i64, _vp]),

@@ -31,6 +31,43 @@ def dense_engine() -> str:
     return _DENSE_ENGINE[0]
 
 
+def _use_tc() -> bool:
+    return _DENSE_ENGINE[0] in ("auto", "tc")
+
+
+def run_dense_chain(x: torch.Tensor, layers: "List[_Dense]") -> torch.Tensor:
+    """A chain of Dense layers on one input matrix.
+
+    tensor-core engine ("auto"/"tc"): x is split once into bf16 (hi, lo); every layer is one
+    tcgen05 launch whose epilogue (bias + activation) directly emits the NEXT layer's split-bf16
+    operand, so intermediate activations never exist in fp32 in HBM; the last layer writes fp32.
+    "fp32" engine: exact CUDA-core kernels (parity anchor)."""
+    width = x.shape[1]
+    for l in layers:
+        l.build(width, x.device)
+        width = l.units
+    if not _use_tc():
+        for l in layers:
+            x = l(x)
+        return x
+    B = x.shape[0]
+    a = ops.split_rows(x)
+    K = x.shape[1]
+    out = None
+    for i, l in enumerate(layers):
+        last = i == len(layers) - 1
+        if K != l.input_dim:
+            raise ValueError(f"{l.name}: input width {K} != kernel rows {l.input_dim}")
+        nxt = None
+        if last:
+            out = torch.empty((B, l.units), dtype=torch.float32, device=x.device)
+        else:
+            nxt = l.split_buffer(B, x.device)
+        ops.dense_tc(a, K, l.split_kernel(), l.units, l.bias, l.activation, passes=3, out_f32=out, out_split=nxt)
+        a, K = nxt, l.units
+    return out
+
+
 class _Dense(Block):
     """Keras Dense as wrapped by blocks/mlp.py:210-300: dict inputs are concat-aggregated in
     sorted-key order first (:275-277), then act(x @ kernel + bias) with kernel (in, units)."""
@@ -49,6 +86,25 @@ class _Dense(Block):
         self.kernel: Optional[torch.Tensor] = None
         self.bias: Optional[torch.Tensor] = None
         self.input_dim: Optional[int] = None
+        self._w_split: Optional[torch.Tensor] = None
+        self._split_bufs: Dict[int, torch.Tensor] = {}
+
+    def split_kernel(self) -> torch.Tensor:
+        """(Np, 2*Kp) split-bf16 K-major copy of the kernel for the tensor-core path (built once)."""
+        if self._w_split is None:
+            self._w_split = ops.split_weights(self.kernel)
+        return self._w_split
+
+    def split_buffer(self, B: int, device) -> torch.Tensor:
+        """Cached (B, 2*Kp(units)) bf16 buffer receiving this layer's output as the next layer's
+        operand; its padding columns are zeroed once and never written again."""
+        buf = self._split_bufs.get(B)
+        if buf is None or buf.device != device:
+            if len(self._split_bufs) > 4:
+                self._split_bufs.clear()
+            buf = torch.zeros((B, 2 * ops.tc_padded_k(self.units)), dtype=torch.bfloat16, device=device)
+            self._split_bufs[B] = buf
+        return buf
 
     def build(self, input_dim: Optional[int] = None, device=None) -> "_Dense":
         if self.kernel is None:
@@ -70,6 +126,7 @@ class _Dense(Block):
             raise ValueError(f"{self.name}: kernel has {self.kernel.shape[1]} columns, expected {self.units}")
         self.bias = None if bias is None else torch.as_tensor(bias, dtype=torch.float32).to(dev).contiguous()
         self.use_bias = bias is not None
+        self._w_split = None
         self.built = True
 
     def weights(self):
@@ -86,6 +143,12 @@ class _Dense(Block):
         if x.shape[1] != self.input_dim:
             raise ValueError(f"{self.name}: input width {x.shape[1]} != kernel rows {self.input_dim}")
         out = torch.empty((x.shape[0], self.units), dtype=torch.float32, device=x.device)
+        if x0 is None and not _use_tc():
+            return ops.dense_fp32(x, self.kernel, self.bias, self.activation, out)
+        if x0 is None:
+            ops.dense_tc(ops.split_rows(x), self.input_dim, self.split_kernel(), self.units, self.bias, self.activation,
+                         out_f32=out)
+            return out
         return ops.dense_fp32(x, self.kernel, self.bias, self.activation, out, x0=x0)
 
 
@@ -117,9 +180,7 @@ class MLP(SequentialBlock):
             if self.filter_names is not None:
                 x = {k: v for k, v in x.items() if k in self.filter_names}
             x = concat_sorted(x)
-        for l in self.dense_layers:
-            x = l(x)
-        return x
+        return run_dense_chain(x, self.dense_layers)
 
     def oracle_layers(self):
         return [{"kernel": l.kernel.cpu().numpy(), "bias": None if l.bias is None else l.bias.cpu().numpy(),
@@ -261,8 +322,27 @@ class CrossBlockSeq(SequentialBlock):
             x = self.inputs(x)
         if isinstance(x, dict):
             x = concat_sorted(x)
-        for l in self.cross_layers:
+        layers = self.cross_layers
+        if _use_tc() and all(l.low_rank_dim is None for l in layers):
+            return self._call_tc(x, layers)
+        for l in layers:
             x = l(x)
+        return x
+
+    def _call_tc(self, x0: torch.Tensor, layers) -> torch.Tensor:
+        """x_{l+1} = x0 * (x_l W_l + b_l) + x_l with every layer one tcgen05 launch: the epilogue reads
+        x0 and x_l (fp32) and writes x_{l+1} both as fp32 (next residual) and split-bf16 (next operand)."""
+        B, d = x0.shape
+        for l in layers:
+            l.build(d, x0.device)
+        a = ops.split_rows(x0)
+        x = x0
+        for i, l in enumerate(layers):
+            last = i == len(layers) - 1
+            out = torch.empty((B, d), dtype=torch.float32, device=x0.device)
+            nxt = None if last else l.dense.split_buffer(B, x0.device)
+            ops.dense_tc(a, d, l.dense.split_kernel(), d, l.dense.bias, "linear", out_f32=out, out_split=nxt, x0=x0, xres=x)
+            a, x = nxt, out
         return x
 
     def oracle_layers(self):

@@ -1,0 +1,512 @@
+// Tensor-core dense layer for sm_100a: tcgen05.mma (kind::f16, bf16 operands, fp32 TMEM
+// accumulators) fed by TMA, warp-specialised persistent CTAs.
+//
+//   out = act(x @ W + bias)            (Keras Dense, merlin/models/tf/blocks/mlp.py:275-280)
+//   out = x0 * (x @ W + bias) + x      (DCN-v2 cross, blocks/cross.py:196-198)
+//
+// fp32 parity on bf16 tensor cores: every fp32 operand is carried as a split-bf16 pair
+// x = hi + lo (hi = bf16(x), lo = bf16(x - hi)); passes = 3 accumulates hi*lo + lo*hi + hi*hi
+// into ONE fp32 TMEM accumulator (relative error ~2^-16: fp32-grade, well inside the 1e-3 logit
+// tolerance of the north star); passes = 1 is plain bf16.
+//
+// Layout in HBM:  a_split (M, 2*Kp) bf16 = [hi(0..Kp) | lo(0..Kp)]      K-major rows
+//                 w_split (Np, 2*Kp) bf16 = transpose of the Keras kernel, same split
+// Kp = K rounded up to 64 (one 128-byte swizzle row per k-block), Np = N rounded up to 16
+// (<= 256) or to 128 (> 256).  Padding is zero, so it contributes nothing.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue
+// (TMEM -> registers -> bias/activation/cross -> global).  A pipeline stage holds the four
+// 64-wide k-block tiles {A_hi, A_lo, B_hi, B_lo}; the accumulator is double-buffered in TMEM so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "mm_common.cuh"
+
+namespace mm {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // bf16 elements = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+
+struct Params {
+  long long M;
+  int N, Np, Kp, BN, n_tiles_n, passes, act, stages;
+  const float* bias;
+  const float* x0;
+  const float* xres;
+  long long x_stride;
+  float* out_f32;
+  long long out_stride;
+  __nv_bfloat16* out_split;
+  int out_Kp;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 8000000000ll) {
+      printf("mm_dense_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart.
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+//  version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64)).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;   // SBO
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// ---------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A_hi | A_lo | B_hi | B_lo] (1024-B aligned tiles), then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t B_TILE_BYTES = (uint32_t)p.BN * BLOCK_K * 2;
+  const uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [stages]
+  uint64_t* empty_bar = bars + p.stages;           // [stages]
+  uint64_t* tmem_full = bars + 2 * p.stages;       // [2]
+  uint64_t* tmem_empty = bars + 2 * p.stages + 2;  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const long long tiles = m_tiles * p.n_tiles_n;
+  const int KB = p.Kp / BLOCK_K;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(tmem_full + a), 1);
+      mbar_init(smem_u32(tmem_empty + a), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp, .sync.aligned)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (p.passes == 3) ? STAGE_BYTES : (A_TILE_BYTES + B_TILE_BYTES);
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (int)(tile / p.n_tiles_n) * BLOCK_M;
+        const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+          mbar_expect_tx(fb, tx);
+          tma_load_2d(smem_u32(st), &tmA, fb, kb * BLOCK_K, m0);
+          tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &tmB, fb, kb * BLOCK_K, n0);
+          if (p.passes == 3) {
+            tma_load_2d(smem_u32(st + A_TILE_BYTES), &tmA, fb, p.Kp + kb * BLOCK_K, m0);
+            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + B_TILE_BYTES), &tmB, fb, p.Kp + kb * BLOCK_K, n0);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_M, p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tmem_empty + acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
+          const uint32_t b_hi = st + 2 * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+          if (p.passes == 3) {
+            // small cross terms first, the dominant hi*hi product last
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_bf16(d_tmem, make_desc_sw128(a_hi + k * 32), make_desc_sw128(b_lo + k * 32), idesc, accumulate);
+              accumulate = 1;
+            }
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(d_tmem, make_desc_sw128(a_lo + k * 32), make_desc_sw128(b_hi + k * 32), idesc, 1);
+          }
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_bf16(d_tmem, make_desc_sw128(a_hi + k * 32), make_desc_sw128(b_hi + k * 32), idesc, accumulate);
+            accumulate = 1;
+          }
+          tcgen05_commit(smem_u32(empty_bar + stage));  // frees the smem stage when the MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tcgen05_commit(smem_u32(tmem_full + acc));  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long long m0 = (tile / p.n_tiles_n) * BLOCK_M;
+      const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
+      const long long row = m0 + q * 32 + lane;
+      mbar_wait(smem_u32(tmem_full + acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        const int ncols = min(32, p.BN - c0);  // BN is a multiple of 16
+        if (ncols == 32) tmem_ld_32x32b_x32(t_row + c0, r);
+        else tmem_ld_32x32b_x16(t_row + c0, r);
+        tmem_ld_wait();
+        if (c0 + 32 >= p.BN) {  // last TMEM read of this accumulator: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(tmem_empty + acc));
+        }
+        if (row < p.M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            float x = __uint_as_float(r[j]);
+            if (j < ncols && n < p.N) {
+              if (p.bias) x += __ldg(p.bias + n);
+              if (p.x0) x = __fadd_rn(__fmul_rn(__ldg(p.x0 + row * p.x_stride + n), x), __ldg(p.xres + row * p.x_stride + n));
+              else x = apply_act(x, p.act);
+            } else {
+              x = 0.0f;  // padding columns are exact zeros for the next layer
+            }
+            v[j] = x;
+          }
+          if (p.out_f32) {
+            float* o = p.out_f32 + row * p.out_stride + n0 + c0;
+            const bool vec = ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int n = n0 + c0 + j;
+              if (j >= ncols) break;
+              if (vec && n + 3 < p.N) {
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < p.N) o[j + e] = v[j + e];
+              }
+            }
+          }
+          if (p.out_split) {
+            // next layer's A operand: [hi | lo] halves, columns n0+c0 .. +ncols (< out_Kp by construction)
+            __nv_bfloat16* oh = p.out_split + row * (2ll * p.out_Kp) + n0 + c0;
+            __nv_bfloat16* ol = oh + p.out_Kp;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j >= ncols || n0 + c0 + j >= p.out_Kp) break;
+              __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) split_bf16(v[j + e], h[e], l[e]);
+              *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(h);
+              *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(l);
+            }
+          }
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// fp32 rows -> split-bf16 rows [hi | lo], zero padded to Kp
+__global__ void split_rows_kernel(const float* __restrict__ x, long long M, int K, long long x_stride,
+                                  __nv_bfloat16* __restrict__ out, int Kp) {
+  const long long total = M * (Kp / 8);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long m = e / (Kp / 8);
+    const int k0 = (int)(e % (Kp / 8)) * 8;
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = (k0 + j < K) ? x[m * x_stride + k0 + j] : 0.0f;
+      split_bf16(v, h[j], l[j]);
+    }
+    __nv_bfloat16* o = out + m * (2ll * Kp) + k0;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(o + Kp) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// Keras kernel (K, N) fp32 -> (Np, 2*Kp) bf16, transposed (K-major), split, zero padded
+__global__ void split_weights_kernel(const float* __restrict__ W, int K, int N, __nv_bfloat16* __restrict__ out,
+                                     int Kp, int Np) {
+  const long long total = (long long)Np * Kp;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(e / Kp), k = (int)(e % Kp);
+    const float v = (n < N && k < K) ? W[(long long)k * N + n] : 0.0f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    out[(long long)n * 2 * Kp + k] = h;
+    out[(long long)n * 2 * Kp + Kp + k] = l;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major (rows, cols) matrix, box = (64 cols, box_rows), SWIZZLE_128B
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  MM_REQUIRE(fn != nullptr, MM_ERR_DRIVER, "mm_dense_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MM_REQUIRE(r == CUDA_SUCCESS, MM_ERR_DRIVER, "mm_dense_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return MM_OK;
+}
+
+}  // namespace tc
+}  // namespace mm
+
+extern "C" {
+
+int mm_tc_padded_k(int K) { return ((K + 63) / 64) * 64; }
+int mm_tc_padded_n(int N) { return N <= 256 ? ((N + 15) / 16) * 16 : ((N + 127) / 128) * 128; }
+
+int mm_split_rows(const float* x, int64_t M, int K, int64_t x_stride, void* out_split, int Kp, void* stream) {
+  MM_REQUIRE(x && out_split && M >= 0 && K > 0 && x_stride >= K, MM_ERR_ARG, "mm_split_rows: null pointer or bad K/stride");
+  MM_REQUIRE(Kp >= K && Kp % 64 == 0, MM_ERR_ARG, "mm_split_rows: Kp must be a multiple of 64 and >= K");
+  MM_REQUIRE(((uintptr_t)out_split % 16) == 0, MM_ERR_ALIGN, "mm_split_rows: out_split must be 16-B aligned");
+  if (M == 0) return MM_OK;
+  const long long total = M * (Kp / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)mm::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  mm::tc::split_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, M, K, x_stride,
+                                                                               (__nv_bfloat16*)out_split, Kp);
+  return mm::check_launch("mm_split_rows");
+}
+
+int mm_split_weights(const float* W, int K, int N, void* w_split, int Kp, int Np, void* stream) {
+  MM_REQUIRE(W && w_split && K > 0 && N > 0, MM_ERR_ARG, "mm_split_weights: null pointer or non-positive K/N");
+  MM_REQUIRE(Kp == mm_tc_padded_k(K) && Np == mm_tc_padded_n(N), MM_ERR_ARG,
+             "mm_split_weights: Kp/Np must be mm_tc_padded_k(K)=%d / mm_tc_padded_n(N)=%d", mm_tc_padded_k(K),
+             mm_tc_padded_n(N));
+  const long long total = (long long)Np * Kp;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)mm::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  mm::tc::split_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, K, N, (__nv_bfloat16*)w_split, Kp, Np);
+  return mm::check_launch("mm_split_weights");
+}
+
+int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_split, int N, int Np,
+                const float* bias, int act, int passes, const float* x0, const float* xres,
+                int64_t x_stride, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
+                void* stream) {
+  using namespace mm::tc;
+  MM_REQUIRE(a_split && w_split && M >= 0 && K > 0 && N > 0, MM_ERR_ARG, "mm_dense_tc: null operand or non-positive K/N");
+  MM_REQUIRE(Kp == mm_tc_padded_k(K) && Np == mm_tc_padded_n(N), MM_ERR_ARG,
+             "mm_dense_tc: Kp/Np must be the padded sizes (%d / %d)", mm_tc_padded_k(K), mm_tc_padded_n(N));
+  MM_REQUIRE(passes == 1 || passes == 3, MM_ERR_ARG, "mm_dense_tc: passes must be 1 (bf16) or 3 (split-bf16)");
+  MM_REQUIRE(act >= MM_ACT_LINEAR && act <= MM_ACT_GELU, MM_ERR_ARG, "mm_dense_tc: unknown activation %d", act);
+  MM_REQUIRE((x0 == nullptr) == (xres == nullptr), MM_ERR_ARG, "mm_dense_tc: x0 and xres go together");
+  MM_REQUIRE(!x0 || x_stride >= N, MM_ERR_ARG, "mm_dense_tc: x_stride < N for the cross epilogue");
+  MM_REQUIRE(out_f32 || out_split, MM_ERR_ARG, "mm_dense_tc: no output requested");
+  MM_REQUIRE(!out_f32 || out_stride >= N, MM_ERR_ARG, "mm_dense_tc: out_stride < N");
+  MM_REQUIRE(!out_split || (out_Kp == mm_tc_padded_k(N) && ((uintptr_t)out_split % 16) == 0), MM_ERR_ARG,
+             "mm_dense_tc: out_Kp must be mm_tc_padded_k(N)=%d and out_split 16-B aligned", mm_tc_padded_k(N));
+  MM_REQUIRE(((uintptr_t)a_split % 16) == 0 && ((uintptr_t)w_split % 16) == 0, MM_ERR_ALIGN,
+             "mm_dense_tc: operands must be 16-B aligned");
+  MM_REQUIRE(M < (1ll << 31), MM_ERR_UNSUPPORTED, "mm_dense_tc: M too large for 32-bit TMA coordinates");
+  if (M == 0) return MM_OK;
+
+  Params p;
+  p.M = M;
+  p.N = N;
+  p.Np = Np;
+  p.Kp = Kp;
+  p.BN = Np <= 256 ? Np : 128;
+  p.n_tiles_n = Np / p.BN;
+  p.passes = passes;
+  p.act = act;
+  p.bias = bias;
+  p.x0 = x0;
+  p.xres = xres;
+  p.x_stride = x_stride;
+  p.out_f32 = out_f32;
+  p.out_stride = out_stride;
+  p.out_split = (__nv_bfloat16*)out_split;
+  p.out_Kp = out_Kp;
+  const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.BN * BLOCK_K * 2;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages > Kp / BLOCK_K * 2) stages = Kp / BLOCK_K * 2 > 2 ? Kp / BLOCK_K * 2 : 2;
+  MM_REQUIRE(stages >= 2, MM_ERR_UNSUPPORTED, "mm_dense_tc: tile does not fit two pipeline stages");
+  p.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, a_split, (uint64_t)M, (uint64_t)2 * Kp, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&tmB, w_split, (uint64_t)Np, (uint64_t)2 * Kp, (uint32_t)p.BN);
+  if (rc) return rc;
+
+  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    mm::set_error("mm_dense_tc: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
+    return (int)e;
+  }
+  const long long tiles = ((M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles_n;
+  const int sms = mm::sm_count();
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  dense_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  return mm::check_launch("mm_dense_tc");
+}
+
+}  // extern "C"

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .blocks import MLP, CrossBlock, CrossBlockSeq, DLRM, DLRMBlock, MLPBlock, _Dense
+from .blocks import MLP, CrossBlock, CrossBlockSeq, DLRM, DLRMBlock, MLPBlock, _Dense, run_dense_chain
 from .core import Block, Prediction, TabularData, default_device, to_device, unique_name
 from .inputs import EmbeddingOptions, EmbeddingsBlock, InputBlockV2
 from .retrieval import ItemRetrievalTask, TwoTowerBlock
@@ -157,6 +157,14 @@ class RankingModel(Model):
         self._check_inputs(inputs)
         if not self.built:
             self.build(next(iter(inputs.values())).device)
+        if isinstance(self.body, DLRM) and self.body.top_block is not None:
+            # top MLP + output layer as ONE dense chain (no fp32 round trip between them)
+            bottom = self.body.bottom_forward(inputs)
+            x = self.body.interaction_forward(inputs, bottom)
+            return run_dense_chain(x, self.body.top_block.dense_layers + [self.prediction.to_call])
+        if isinstance(self.body, DCNBody) and self.body.stacked:
+            x = self.body.cross(self.body.input_block(inputs))
+            return run_dense_chain(x, self.body.deep.dense_layers + [self.prediction.to_call])
         x = self.body(inputs, training=training)
         return self.prediction(x)
 

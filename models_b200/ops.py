@@ -275,3 +275,68 @@ def l2_normalize(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     _cabi.check(_lib().mm_l2_normalize(x.data_ptr(), x.shape[0], x.shape[1], _row_stride(x, "x"), out.data_ptr(),
                                        _row_stride(out, "out"), _stream()), "mm_l2_normalize")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core dense path (tcgen05 split-bf16)
+# ---------------------------------------------------------------------------------------------
+def tc_padded_k(K: int) -> int:
+    return int(_lib().mm_tc_padded_k(int(K)))
+
+
+def tc_padded_n(N: int) -> int:
+    return int(_lib().mm_tc_padded_n(int(N)))
+
+
+def split_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 (M, K) -> split-bf16 (M, 2*Kp) = [hi | lo], zero padded (mm_split_rows)."""
+    _dev(x, "x", torch.float32)
+    M, K = x.shape
+    Kp = tc_padded_k(K)
+    if out is None:
+        out = torch.empty((M, 2 * Kp), dtype=torch.bfloat16, device=x.device)
+    _cabi.check(_lib().mm_split_rows(x.data_ptr(), M, K, _row_stride(x, "x"), out.data_ptr(), Kp, _stream()), "mm_split_rows")
+    return out
+
+
+def split_weights(W: torch.Tensor) -> torch.Tensor:
+    """Keras kernel (K, N) fp32 -> (Np, 2*Kp) bf16 K-major split (mm_split_weights); one-time."""
+    _dev(W, "W", torch.float32)
+    if W.dim() != 2 or not W.is_contiguous():
+        raise ValueError("W must be a contiguous (K, N) matrix")
+    K, N = W.shape
+    Kp, Np = tc_padded_k(K), tc_padded_n(N)
+    out = torch.empty((Np, 2 * Kp), dtype=torch.bfloat16, device=W.device)
+    _cabi.check(_lib().mm_split_weights(W.data_ptr(), K, N, out.data_ptr(), Kp, Np, _stream()), "mm_split_weights")
+    return out
+
+
+def dense_tc(a_split: torch.Tensor, K: int, w_split: torch.Tensor, N: int, bias: Optional[torch.Tensor],
+             act: Optional[str], passes: int = 3, out_f32: Optional[torch.Tensor] = None,
+             out_split: Optional[torch.Tensor] = None, x0: Optional[torch.Tensor] = None,
+             xres: Optional[torch.Tensor] = None) -> None:
+    """One tensor-core dense layer (mm_dense_tc); see include/mm_b200.h."""
+    _dev(a_split, "a_split", torch.bfloat16), _dev(w_split, "w_split", torch.bfloat16)
+    if act not in ACTIVATIONS:
+        raise ValueError(f"unsupported activation {act!r}")
+    M = a_split.shape[0]
+    Kp, Np = tc_padded_k(K), tc_padded_n(N)
+    if tuple(a_split.shape) != (M, 2 * Kp) or not a_split.is_contiguous():
+        raise ValueError(f"a_split must be contiguous (M, {2 * Kp}), got {tuple(a_split.shape)}")
+    if tuple(w_split.shape) != (Np, 2 * Kp) or not w_split.is_contiguous():
+        raise ValueError(f"w_split must be contiguous ({Np}, {2 * Kp}), got {tuple(w_split.shape)}")
+    out_Kp = 0
+    if out_split is not None:
+        out_Kp = tc_padded_k(N)
+        if tuple(out_split.shape) != (M, 2 * out_Kp) or not out_split.is_contiguous() or out_split.dtype != torch.bfloat16:
+            raise ValueError(f"out_split must be contiguous bf16 (M, {2 * out_Kp})")
+    xs = 0
+    if x0 is not None:
+        if xres is None or x0.stride(0) != xres.stride(0):
+            raise ValueError("x0 and xres must both be given with equal row strides")
+        xs = _row_stride(x0, "x0")
+    _cabi.check(
+        _lib().mm_dense_tc(a_split.data_ptr(), M, K, Kp, w_split.data_ptr(), N, Np, _ptr(bias), ACTIVATIONS[act],
+                           passes, _ptr(x0), _ptr(xres), xs, _ptr(out_f32),
+                           0 if out_f32 is None else _row_stride(out_f32, "out_f32"), _ptr(out_split), out_Kp, _stream()),
+        "mm_dense_tc")
