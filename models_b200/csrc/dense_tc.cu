@@ -31,6 +31,8 @@ constexpr int BLOCK_K = 64;   // bf16 elements = 128 bytes = one SWIZZLE_128B ro
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr uint32_t EPI_STAGE_BYTES = 32 * 80 * 2;         // per epilogue warp: max(32x36 fp32, 2 x 32x80 B)
+static_assert(EPI_STAGE_BYTES >= 32 * 36 * 4, "transpose tile too small");
 
 struct Params {
   long long M;
@@ -70,10 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > 8000000000ll) {
-      printf("mm_dense_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 8000000000ll) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -153,6 +152,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * p.stages;       // [2]
   uint64_t* tmem_empty = bars + 2 * p.stages + 2;  // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);                       // [Np], zero padded
+  uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(bias_s + p.Np);                         // 4 x EPI_STAGE_BYTES (16-B aligned: Np % 16 == 0)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -180,6 +181,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.Np; i += blockDim.x) bias_s[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -262,13 +264,21 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
+    // TMEM -> registers (thread = one accumulator row, 32 columns per step) -> bias/act/cross ->
+    // per-warp shared-memory transpose tile -> coalesced 16-byte global stores (a warp store
+    // covers whole 64/128-byte row segments instead of 32 scattered 16-byte pieces).
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* stg = stage_tiles + (size_t)(warp - 2) * EPI_STAGE_BYTES;
+    float* stg_f = reinterpret_cast<float*>(stg);
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool vec_f32 = p.out_f32 && ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+    const bool vec_x = p.x0 && ((p.x_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x0) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(p.xres) & 15) == 0);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const long long m0 = (tile / p.n_tiles_n) * BLOCK_M;
       const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
-      const long long row = m0 + q * 32 + lane;
+      const long long row0 = m0 + q * 32;  // first row of this warp
       mbar_wait(smem_u32(tmem_full + acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -283,48 +293,106 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(tmem_empty + acc));
         }
-        if (row < p.M) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            float x = __uint_as_float(r[j]);
-            if (j < ncols && n < p.N) {
-              if (p.bias) x += __ldg(p.bias + n);
-              if (p.x0) x = __fadd_rn(__fmul_rn(__ldg(p.x0 + row * p.x_stride + n), x), __ldg(p.xres + row * p.x_stride + n));
-              else x = apply_act(x, p.act);
-            } else {
-              x = 0.0f;  // padding columns are exact zeros for the next layer
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[n0 + c0 + j];  // bias_s is zero padded
+        if (p.x0) {
+          // cross epilogue: x0 * (xW + b) + x ; x0 / x tiles come in through the transpose tile (coalesced)
+#pragma unroll 1
+          for (int which = 0; which < 2; ++which) {
+            const float* src = which == 0 ? p.x0 : p.xres;
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), cv = (lane & 7) * 4;
+              const long long grow = row0 + rr;
+              const int n = n0 + c0 + cv;
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (grow < p.M && cv < ncols) {
+                const float* g = src + grow * p.x_stride + n;
+                if (vec_x && n + 3 < p.N) t = *reinterpret_cast<const float4*>(g);
+                else {
+                  if (n < p.N) t.x = g[0];
+                  if (n + 1 < p.N) t.y = g[1];
+                  if (n + 2 < p.N) t.z = g[2];
+                  if (n + 3 < p.N) t.w = g[3];
+                }
+              }
+              *reinterpret_cast<float4*>(stg_f + rr * 36 + cv) = t;
             }
-            v[j] = x;
-          }
-          if (p.out_f32) {
-            float* o = p.out_f32 + row * p.out_stride + n0 + c0;
-            const bool vec = ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const int n = n0 + c0 + j;
-              if (j >= ncols) break;
-              if (vec && n + 3 < p.N) {
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              const float4 t = *reinterpret_cast<const float4*>(stg_f + lane * 36 + j);
+              if (which == 0) {
+                v[j] = __fmul_rn(t.x, v[j]); v[j + 1] = __fmul_rn(t.y, v[j + 1]);
+                v[j + 2] = __fmul_rn(t.z, v[j + 2]); v[j + 3] = __fmul_rn(t.w, v[j + 3]);
               } else {
-                for (int e = 0; e < 4; ++e)
-                  if (n + e < p.N) o[j + e] = v[j + e];
+                v[j] = __fadd_rn(v[j], t.x); v[j + 1] = __fadd_rn(v[j + 1], t.y);
+                v[j + 2] = __fadd_rn(v[j + 2], t.z); v[j + 3] = __fadd_rn(v[j + 3], t.w);
               }
             }
           }
-          if (p.out_split) {
-            // next layer's A operand: [hi | lo] halves, columns n0+c0 .. +ncols (< out_Kp by construction)
-            __nv_bfloat16* oh = p.out_split + row * (2ll * p.out_Kp) + n0 + c0;
-            __nv_bfloat16* ol = oh + p.out_Kp;
+        } else if (p.act == MM_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j >= ncols || n0 + c0 + j >= p.out_Kp) break;
-              __align__(16) __nv_bfloat16 h[8], l[8];
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (p.act != MM_ACT_LINEAR) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) split_bf16(v[j + e], h[e], l[e]);
-              *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(h);
-              *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(l);
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) v[j] = apply_act_slow(v[j], p.act);  // warp-uniform: skip padding columns
+        }
+        // padding columns (n >= N) must be exact zeros for the next layer's operand
+        if (n0 + c0 + 32 > p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j >= p.N) v[j] = 0.0f;
+        }
+        if (p.out_f32) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stg_f + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), cv = (lane & 7) * 4;
+            const long long grow = row0 + rr;
+            const int n = n0 + c0 + cv;
+            if (grow < p.M && cv < ncols && n < p.N) {
+              const float4 t = *reinterpret_cast<const float4*>(stg_f + rr * 36 + cv);
+              float* g = p.out_f32 + grow * p.out_stride + n;
+              if (vec_f32 && n + 3 < p.N) *reinterpret_cast<float4*>(g) = t;
+              else {
+                g[0] = t.x;
+                if (n + 1 < p.N) g[1] = t.y;
+                if (n + 2 < p.N) g[2] = t.z;
+                if (n + 3 < p.N) g[3] = t.w;
+              }
+            }
+          }
+        }
+        if (p.out_split && n0 + c0 < p.out_Kp) {
+          // [hi | lo] bf16 rows of the next layer's A operand; tile rows are 80 B apart (bank spread)
+          __syncwarp();
+          uint8_t* th = stg;             // hi: 32 rows x 64 B (+16 pad)
+          uint8_t* tl = stg + 32 * 80;   // lo
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16(v[j + e], h[e], l[e]);
+            *reinterpret_cast<uint4*>(th + lane * 80 + j * 2) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(tl + lane * 80 + j * 2) = *reinterpret_cast<const uint4*>(l);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), cv = (lane & 3) * 8;  // 8 bf16 = 16 B per lane
+            const long long grow = row0 + rr;
+            if (grow < p.M && cv < ncols && n0 + c0 + cv < p.out_Kp) {
+              __nv_bfloat16* oh = p.out_split + grow * (2ll * p.out_Kp) + n0 + c0 + cv;
+              *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(th + rr * 80 + cv * 2);
+              *reinterpret_cast<uint4*>(oh + p.out_Kp) = *reinterpret_cast<const uint4*>(tl + rr * 80 + cv * 2);
             }
           }
         }
@@ -484,12 +552,13 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
   p.out_split = (__nv_bfloat16*)out_split;
   p.out_Kp = out_Kp;
   const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.BN * BLOCK_K * 2;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t epi_bytes = (size_t)Np * sizeof(float) + 4 * (size_t)EPI_STAGE_BYTES;
+  int stages = (int)((224 * 1024 - 2048 - epi_bytes) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages > Kp / BLOCK_K * 2) stages = Kp / BLOCK_K * 2 > 2 ? Kp / BLOCK_K * 2 : 2;
   MM_REQUIRE(stages >= 2, MM_ERR_UNSUPPORTED, "mm_dense_tc: tile does not fit two pipeline stages");
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + epi_bytes;
 
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a_split, (uint64_t)M, (uint64_t)2 * Kp, BLOCK_M);
@@ -497,10 +566,14 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
   rc = make_map(&tmB, w_split, (uint64_t)Np, (uint64_t)2 * Kp, (uint32_t)p.BN);
   if (rc) return rc;
 
-  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    mm::set_error("mm_dense_tc: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
-    return (int)e;
+  static size_t smem_set = 0;  // raise the dynamic-smem limit once (monotone), not per launch
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      mm::set_error("mm_dense_tc: cudaFuncSetAttribute(227 KB smem) failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    smem_set = 227 * 1024;
   }
   const long long tiles = ((M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles_n;
   const int sms = mm::sm_count();

@@ -190,10 +190,14 @@ static int launch_interact(const float* x, int64_t x_stride, const GatherParams&
   MM_REQUIRE(smem <= 200 * 1024, MM_ERR_UNSUPPORTED,
              "%s: F=%d D=%d needs %zu B of shared memory per sample (> 200 KB)", who, F, D, smem);
   auto kern = interact_kernel<MODE, IdxT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_error("%s: cudaFuncSetAttribute(%zu B smem) failed: %s", who, smem, cudaGetErrorString(e));
-    return (int)e;
+  static size_t smem_set = 0;  // per template instantiation
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute(200 KB smem) failed: %s", who, cudaGetErrorString(e));
+      return (int)e;
+    }
+    smem_set = 200 * 1024;
   }
   long long tiles = (B + G - 1) / G;
   const long long cap = (long long)sm_count() * 4 * 8;

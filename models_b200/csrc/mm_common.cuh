@@ -48,9 +48,11 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // Keras activations (tf.keras.activations.*); exact (non-fast-math) forms.
-__device__ __forceinline__ float apply_act(float v, int act) {
+// linear / relu are inlined; the transcendental ones live in ONE out-of-line function so that
+// unrolled epilogues do not replicate ~3 KB of libm code per element (that blew the instruction
+// cache: 110 KB of SASS and ~600 cycles per element in the first tensor-core epilogue).
+static __device__ __noinline__ float apply_act_slow(float v, int act) {
   switch (act) {
-    case MM_ACT_RELU: return fmaxf(v, 0.0f);
     case MM_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
     case MM_ACT_TANH: return tanhf(v);
     case MM_ACT_SELU: {
@@ -61,6 +63,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case MM_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     default: return v;
   }
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == MM_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == MM_ACT_LINEAR) return v;
+  return apply_act_slow(v, act);
 }
 
 // per-launch table list, passed by value in kernel parameter space (2 KB)
