@@ -134,19 +134,24 @@ int mm_l2_normalize(const float* x, int64_t B, int D, int64_t x_stride, float* o
  * (blocks/interaction.py:102,107-112) and the shortcut concat (blocks/dlrm.py:126-130).
  *   out[b, 0:P]      = prefix[b, 0:P]                  (P = 0 / prefix NULL: no prefix)
  *   out[b, P + p(i,j)] = sum_d x[b,i,d] * x[b,j,d]      i<j (or i<=j if self_interaction),
- * pairs enumerated row-major over the upper triangle.  Dots accumulate in fp32, d ascending.
+ * pairs enumerated row-major over the upper triangle.  Dots accumulate in fp32.
+ * Output: either fp32 `out` (B, >= P+pairs) or `out_split`, the split-bf16 operand (B, 2*out_Kp)
+ * = [hi | lo] of the next tensor-core dense layer (out_Kp = mm_tc_padded_k(P+pairs), padding
+ * columns written as zeros) — exactly one of the two must be non-null.
+ * Tensor-core path (mma.sync bf16, 3-pass split, one warp per sample, cp.async.bulk row staging)
+ * when F <= 32, D % 16 == 0, P in {0, D}, no self interaction; CUDA-core path otherwise.
  * ------------------------------------------------------------------------------------- */
 int mm_dot_interaction(const float* x, int64_t B, int F, int D, int64_t x_stride,
                        const float* prefix, int P, int64_t prefix_stride, int self_interaction,
-                       float* out, int64_t out_stride, void* stream);
+                       float* out, int64_t out_stride, void* out_split, int out_Kp, void* stream);
 
 /* Fused K1+K5+K6+K3 for DLRM: gather T rows per sample straight into shared memory, append
  * the bottom-MLP vector at slot `bottom_slot`, write [bottom | interactions]; the (B,F,D)
  * stack never touches HBM.  tables[t].out_col is interpreted as slot(t)*D.  All dims == D. */
 int mm_dlrm_gather_interact(const mm_gather_table* tables_host, int n_tables, int idx_dtype,
                             int64_t B, int D, const float* bottom, int64_t bottom_stride,
-                            int bottom_slot, float* out, int64_t out_stride, int32_t* oob_count,
-                            void* stream);
+                            int bottom_slot, float* out, int64_t out_stride, void* out_split,
+                            int out_Kp, int32_t* oob_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4  Dense layer, exact fp32 on CUDA cores:  out = act(x @ W + bias).

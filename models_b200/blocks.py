@@ -35,24 +35,30 @@ def _use_tc() -> bool:
     return _DENSE_ENGINE[0] in ("auto", "tc")
 
 
-def run_dense_chain(x: torch.Tensor, layers: "List[_Dense]") -> torch.Tensor:
+def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: Optional[torch.Tensor] = None,
+                    K: Optional[int] = None) -> torch.Tensor:
     """A chain of Dense layers on one input matrix.
 
     tensor-core engine ("auto"/"tc"): x is split once into bf16 (hi, lo); every layer is one
     tcgen05 launch whose epilogue (bias + activation) directly emits the NEXT layer's split-bf16
     operand, so intermediate activations never exist in fp32 in HBM; the last layer writes fp32.
     "fp32" engine: exact CUDA-core kernels (parity anchor)."""
-    width = x.shape[1]
+    if a_split is not None:  # producer (interaction kernel) already emitted the split-bf16 operand
+        device, B, a = a_split.device, a_split.shape[0], a_split
+    else:
+        device, B, K = x.device, x.shape[0], x.shape[1]
+    width = K
     for l in layers:
-        l.build(width, x.device)
+        l.build(width, device)
         width = l.units
     if not _use_tc():
+        if x is None:
+            raise ValueError("the fp32 dense engine needs an fp32 input")
         for l in layers:
             x = l(x)
         return x
-    B = x.shape[0]
-    a = ops.split_rows(x)
-    K = x.shape[1]
+    if a_split is None:
+        a = ops.split_rows(x)
     out = None
     for i, l in enumerate(layers):
         last = i == len(layers) - 1
@@ -60,9 +66,9 @@ def run_dense_chain(x: torch.Tensor, layers: "List[_Dense]") -> torch.Tensor:
             raise ValueError(f"{l.name}: input width {K} != kernel rows {l.input_dim}")
         nxt = None
         if last:
-            out = torch.empty((B, l.units), dtype=torch.float32, device=x.device)
+            out = torch.empty((B, l.units), dtype=torch.float32, device=device)
         else:
-            nxt = l.split_buffer(B, x.device)
+            nxt = l.split_buffer(B, device)
         ops.dense_tc(a, K, l.split_kernel(), l.units, l.bias, l.activation, passes=3, out_f32=out, out_split=nxt)
         a, K = nxt, l.units
     return out
@@ -410,13 +416,19 @@ class DLRM(Block):
             out.update({f"top_block/{k}": v for k, v in self.top_block.weights().items()})
         return out
 
+    def can_emit_split(self) -> bool:
+        """True when the tensor-core interaction kernel applies (F <= 32, D % 16 == 0)."""
+        F = len(self.embeddings.feature_names) + (1 if self.bottom_block is not None else 0)
+        return 2 <= F <= 32 and self.embedding_dim % 16 == 0 and self.embedding_dim <= 256
+
     def bottom_forward(self, inputs: TabularData) -> Optional[torch.Tensor]:
         if self.bottom_block is None:
             return None
         return self.bottom_block(self.continuous(inputs))
 
-    def interaction_forward(self, inputs: TabularData, bottom: Optional[torch.Tensor]) -> torch.Tensor:
-        """[bottom |] interactions, (B, P + F(F-1)/2)."""
+    def interaction_forward(self, inputs: TabularData, bottom: Optional[torch.Tensor], as_split: bool = False) -> torch.Tensor:
+        """[bottom |] interactions, (B, P + F(F-1)/2) fp32 — or, with as_split, the split-bf16 operand
+        (B, 2*Kp) of the top MLP's first tensor-core layer, written directly by the kernel."""
         self.build(next(iter(inputs.values())).device)
         D = self.embedding_dim
         slots = self.slots()
@@ -425,7 +437,11 @@ class DLRM(Block):
         dev = next(iter(inputs.values())).device
         with_prefix = bottom is not None and self.top_block is not None
         P = D if with_prefix else 0
-        out = torch.empty((B, P + F * (F - 1) // 2), dtype=torch.float32, device=dev)
+        width = P + F * (F - 1) // 2
+        if as_split:
+            out = torch.empty((B, 2 * ops.tc_padded_k(width)), dtype=torch.bfloat16, device=dev)
+        else:
+            out = torch.empty((B, width), dtype=torch.float32, device=dev)
         emb = self.embeddings
         feats = emb.feature_names
         from .core import get_feature

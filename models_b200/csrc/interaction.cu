@@ -10,6 +10,13 @@
 
 namespace mm {
 
+namespace imma {  // interaction_mma.cu: tensor-core fast path (F <= 32, D % 16 == 0)
+template <int MODE, typename IdxT>
+int launch(const float* x, int64_t x_stride, const GatherParams& gp, const float* prefix, int64_t prefix_stride,
+           int P, int bottom_slot, int64_t B, int F, int D, float* out_f32, int64_t out_stride, void* out_split,
+           int out_Kp, int32_t* oob, cudaStream_t st, const char* who);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
@@ -213,20 +220,30 @@ extern "C" {
 
 int mm_dot_interaction(const float* x, int64_t B, int F, int D, int64_t x_stride,
                        const float* prefix, int P, int64_t prefix_stride, int self_interaction,
-                       float* out, int64_t out_stride, void* stream) {
-  MM_REQUIRE(x && out && B >= 0 && F >= 1 && D >= 4, MM_ERR_ARG,
+                       float* out, int64_t out_stride, void* out_split, int out_Kp, void* stream) {
+  MM_REQUIRE(x && (out || out_split) && B >= 0 && F >= 1 && D >= 4, MM_ERR_ARG,
              "mm_dot_interaction: null pointer, B<0, F<1 or D<4");
+  MM_REQUIRE(!(out && out_split), MM_ERR_ARG, "mm_dot_interaction: give either out or out_split");
   MM_REQUIRE(D % 4 == 0 && x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0, MM_ERR_ALIGN,
              "mm_dot_interaction: D and x_stride must be multiples of 4 floats and x 16-B aligned");
   MM_REQUIRE(x_stride >= (int64_t)F * D, MM_ERR_ARG, "mm_dot_interaction: x_stride < F*D");
   MM_REQUIRE((P == 0) || (prefix != nullptr && prefix_stride >= P), MM_ERR_ARG,
              "mm_dot_interaction: P>0 requires a prefix pointer with stride >= P");
   const int npairs = self_interaction ? F * (F + 1) / 2 : F * (F - 1) / 2;
-  MM_REQUIRE(out_stride >= P + npairs, MM_ERR_ARG, "mm_dot_interaction: out_stride %lld < %d",
+  MM_REQUIRE(!out || out_stride >= P + npairs, MM_ERR_ARG, "mm_dot_interaction: out_stride %lld < %d",
              (long long)out_stride, P + npairs);
+  MM_REQUIRE(!out_split || (out_Kp % 64 == 0 && out_Kp >= P + npairs && ((uintptr_t)out_split % 16) == 0), MM_ERR_ARG,
+             "mm_dot_interaction: out_Kp must be a multiple of 64 >= %d and out_split 16-B aligned", P + npairs);
   if (B == 0) return MM_OK;
   mm::GatherParams p;
   memset(&p, 0, sizeof(p));
+  if (!self_interaction) {
+    const int rc = mm::imma::launch<0, int32_t>(x, x_stride, p, prefix, prefix_stride, P, -1, B, F, D, out, out_stride,
+                                                out_split, out_Kp, nullptr, (cudaStream_t)stream, "mm_dot_interaction");
+    if (rc != MM_ERR_UNSUPPORTED) return rc;
+  }
+  MM_REQUIRE(out != nullptr, MM_ERR_UNSUPPORTED,
+             "mm_dot_interaction: split-bf16 output needs the tensor-core path (F<=32, D%%16==0, P in {0,D})");
   return mm::launch_interact<0, int32_t>(x, x_stride, p, prefix, prefix_stride, P, -1, B, F, D,
                                          self_interaction ? 1 : 0, out, out_stride, nullptr,
                                          (cudaStream_t)stream, "mm_dot_interaction");
@@ -234,10 +251,11 @@ int mm_dot_interaction(const float* x, int64_t B, int F, int D, int64_t x_stride
 
 int mm_dlrm_gather_interact(const mm_gather_table* tables_host, int n_tables, int idx_dtype,
                             int64_t B, int D, const float* bottom, int64_t bottom_stride,
-                            int bottom_slot, float* out, int64_t out_stride, int32_t* oob_count,
-                            void* stream) {
-  MM_REQUIRE(tables_host && n_tables > 0 && n_tables <= MM_MAX_TABLES && out && B >= 0, MM_ERR_ARG,
+                            int bottom_slot, float* out, int64_t out_stride, void* out_split,
+                            int out_Kp, int32_t* oob_count, void* stream) {
+  MM_REQUIRE(tables_host && n_tables > 0 && n_tables <= MM_MAX_TABLES && (out || out_split) && B >= 0, MM_ERR_ARG,
              "mm_dlrm_gather_interact: bad table list / null out / B<0");
+  MM_REQUIRE(!(out && out_split), MM_ERR_ARG, "mm_dlrm_gather_interact: give either out or out_split");
   MM_REQUIRE(D >= 4 && D % 4 == 0, MM_ERR_ALIGN, "mm_dlrm_gather_interact: D must be a multiple of 4");
   MM_REQUIRE(idx_dtype == MM_I32 || idx_dtype == MM_I64, MM_ERR_ARG,
              "mm_dlrm_gather_interact: bad idx_dtype");
@@ -258,14 +276,27 @@ int mm_dlrm_gather_interact(const mm_gather_table* tables_host, int n_tables, in
     seen |= 1ull << (tb.out_col / D);
   }
   const int P = bottom ? D : 0;
-  MM_REQUIRE(out_stride >= P + F * (F - 1) / 2, MM_ERR_ARG,
+  MM_REQUIRE(!out || out_stride >= P + F * (F - 1) / 2, MM_ERR_ARG,
              "mm_dlrm_gather_interact: out_stride too small");
+  MM_REQUIRE(!out_split || (out_Kp % 64 == 0 && out_Kp >= P + F * (F - 1) / 2 && ((uintptr_t)out_split % 16) == 0),
+             MM_ERR_ARG, "mm_dlrm_gather_interact: out_Kp must be a multiple of 64 >= the row width, out_split 16-B aligned");
   if (B == 0) return MM_OK;
   mm::GatherParams p;
   memset(&p, 0, sizeof(p));
   p.n_tables = n_tables;
   for (int t = 0; t < n_tables; ++t) p.t[t] = tables_host[t];
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int bs = bottom ? bottom_slot : -1;
+    const int rc = idx_dtype == MM_I32
+                       ? mm::imma::launch<1, int32_t>(nullptr, 0, p, bottom, bottom_stride, P, bs, B, F, D, out, out_stride,
+                                                      out_split, out_Kp, oob_count, st, "mm_dlrm_gather_interact")
+                       : mm::imma::launch<1, int64_t>(nullptr, 0, p, bottom, bottom_stride, P, bs, B, F, D, out, out_stride,
+                                                      out_split, out_Kp, oob_count, st, "mm_dlrm_gather_interact");
+    if (rc != MM_ERR_UNSUPPORTED) return rc;
+  }
+  MM_REQUIRE(out != nullptr, MM_ERR_UNSUPPORTED,
+             "mm_dlrm_gather_interact: split-bf16 output needs the tensor-core path (F<=32, D%%16==0)");
   return idx_dtype == MM_I32
              ? mm::launch_interact<1, int32_t>(nullptr, 0, p, bottom, bottom_stride, P,
                                                bottom ? bottom_slot : -1, B, F, D, 0, out,

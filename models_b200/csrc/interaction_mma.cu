@@ -1,0 +1,364 @@
+// DLRM pairwise interaction on tensor cores, one warp per sample.
+//
+// The per-sample Gram matrix X X^T (X = F x D, F <= 32) is far too small for tcgen05 (M >= 64 per
+// instruction would waste > 4x on block-diagonal padding), so it runs on the warp-level
+// mma.sync.m16n8k16 bf16 path with the same 3-pass split as the dense layers (hi*lo + lo*hi + hi*hi,
+// fp32 accumulate) — the kernel stays HBM-bound instead of shared-memory-bandwidth bound like the
+// CUDA-core version (interaction.cu, 3x3 register blocking: 0.31 ms vs the 0.086 ms HBM floor).
+//
+// Data movement: every row (256 B for D = 64) is ONE cp.async.bulk (TMA engine, UBLKCP) from the
+// embedding table — or the stacked (B,F,D) tensor — into a padded shared-memory tile, completion
+// tracked by a per-buffer mbarrier; each warp keeps NBUF-1 samples in flight while it computes one.
+// Because B = X^T, the B fragments of n-tile nt ARE registers of the A fragment of m-tile nt/2, so X
+// is read from shared memory once per k-step.  The output row [prefix | upper triangle] is assembled
+// in shared memory and written coalesced, either as fp32 or directly as the split-bf16 operand
+// (M, 2*Kp) of the top MLP's first tensor-core layer.
+//
+// Replaces: StackFeatures + DotProductInteraction + shortcut concat
+// (merlin/models/tf/core/aggregation.py:101-108, blocks/interaction.py:86-116, blocks/dlrm.py:126-130).
+#include <cuda_bf16.h>
+
+#include <cstring>
+
+#include "mm_common.cuh"
+
+namespace mm {
+namespace imma {
+
+constexpr int NBUF = 3;
+constexpr int MAX_WARPS = 12;
+
+struct Params {
+  // MODE 0: stacked input
+  const float* x;
+  long long x_stride;
+  // prefix / bottom vector (P == 0 or P == D)
+  const float* prefix;
+  long long prefix_stride;
+  int P;
+  int bottom_slot;  // MODE 1: slot of the bottom vector inside the stack (-1: none)
+  long long B;
+  int F, D, T;
+  int rows;  // rows staged per sample (F, or F+1 when MODE 0 carries a separate prefix row)
+  float* out_f32;
+  long long out_stride;
+  __nv_bfloat16* out_split;
+  int out_Kp;
+  int* oob_count;
+  int n_warps;
+  unsigned per_warp_bytes, in_bytes, bar_offset;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 8000000000ll) __trap();  // protocol bug: trap instead of hanging the GPU
+  }
+}
+// one row: global -> shared through the bulk-copy (TMA) engine
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x, y) -> packed bf16x2 hi (x in the low half) and the bf16x2 of the residuals
+__device__ __forceinline__ void split_pair(float2 v, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(v.x - xh, v.y - yh);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+template <int MODE, typename IdxT>
+__global__ void __launch_bounds__(32 * MAX_WARPS, 1)
+interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int F = p.F, D = p.D, DS = D + 8, KS = D >> 4;
+  uint8_t* wbase = smem_raw + (size_t)warp * p.per_warp_bytes;
+  uint8_t* ostage = wbase + (size_t)NBUF * p.in_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + p.bar_offset) + warp * NBUF;
+  const int npairs = F * (F - 1) / 2;
+  const int OW = p.P + npairs;
+
+  // ---- one-time per warp: barriers, zeroed output staging, output offsets of this lane's accumulators
+  if (lane == 0) {
+    for (int i = 0; i < NBUF; ++i) mbar_init(smem_u32(bars + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    const int stage_words = (int)((p.per_warp_bytes - NBUF * p.in_bytes) >> 2);
+    for (int i = lane; i < stage_words; i += 32) reinterpret_cast<uint32_t*>(ostage)[i] = 0u;
+  }
+  // accumulator tiles: (mt, nt) in {(0,0),(0,1),(0,2),(0,3),(1,2),(1,3)}; c0..c3 = (g,2t),(g,2t+1),(g+8,2t),(g+8,2t+1)
+  int off[6][4];
+#pragma unroll
+  for (int ti = 0; ti < 6; ++ti) {
+    const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = 16 * mt + g + ((c & 2) ? 8 : 0), j = 8 * nt + 2 * t + (c & 1);
+      off[ti][c] = (i < j && j < F) ? p.P + i * (2 * F - i - 1) / 2 + (j - i - 1) : -1;
+    }
+  }
+  int ro[2][2];  // shared-memory row offsets (floats) of this lane's fragment rows, clamped to staged rows
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) ro[mt][h] = min(16 * mt + g + 8 * h, F - 1) * DS;
+  __syncwarp();
+
+  const long long gw = (long long)blockIdx.x * p.n_warps + warp;
+  const long long wstride = (long long)gridDim.x * p.n_warps;
+  const long long n_mine = gw < p.B ? (p.B - gw + wstride - 1) / wstride : 0;
+
+  // lane -> staged row: MODE 1: lanes < T tables, lane T bottom; MODE 0: lanes < F rows, lane F prefix
+  const bool row_lane = lane < p.rows;
+  int my_slot = lane;
+  const float* my_w = nullptr;
+  long long my_rows = 0;
+  const IdxT* my_idx_ptr = nullptr;
+  if (MODE == 1 && lane < p.T) {
+    my_slot = gp.t[lane].out_col / D;
+    my_w = gp.t[lane].weights;
+    my_rows = gp.t[lane].rows;
+    my_idx_ptr = reinterpret_cast<const IdxT*>(gp.t[lane].indices);
+  } else if (MODE == 1 && lane == p.T) {
+    my_slot = p.bottom_slot;
+  }
+
+  auto load_index = [&](long long it) -> long long {
+    if (MODE == 1 && lane < p.T && it < n_mine) return (long long)my_idx_ptr[gw + it * wstride];
+    return 0;
+  };
+  auto issue = [&](long long it, long long idx) {
+    if (it >= n_mine) return;
+    const long long s = gw + it * wstride;
+    const int buf = (int)(it % NBUF);
+    float* xs = reinterpret_cast<float*>(wbase + (size_t)buf * p.in_bytes);
+    const uint32_t bar = smem_u32(bars + buf);
+    const float* src = nullptr;
+    bool valid = false;
+    if (row_lane) {
+      if (MODE == 1) {
+        if (lane < p.T) {
+          valid = idx >= 0 && idx < my_rows;
+          if (!valid && p.oob_count) atomicAdd(p.oob_count, 1);
+          src = my_w + idx * D;
+        } else {
+          valid = true;
+          src = p.prefix + s * p.prefix_stride;
+        }
+      } else {
+        valid = true;
+        src = lane < F ? p.x + s * p.x_stride + (long long)lane * D : p.prefix + s * p.prefix_stride;
+      }
+    }
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(vmask) * (uint32_t)(D * 4));
+    __syncwarp();
+    if (row_lane) {
+      float* dst = xs + my_slot * DS;
+      if (valid) bulk_copy_g2s(smem_u32(dst), src, (uint32_t)(D * 4), bar);
+      else
+        for (int d = 0; d < D; d += 4) *reinterpret_cast<float4*>(dst + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  // ---- software pipeline: NBUF-1 samples in flight; indices fetched one iteration ahead of their rows
+  long long idx_pref = load_index(0);
+  for (int i = 0; i < NBUF - 1; ++i) {
+    const long long idx_cur = idx_pref;
+    idx_pref = load_index(i + 1);
+    issue(i, idx_cur);
+  }
+  for (long long it = 0; it < n_mine; ++it) {
+    {
+      const long long idx_cur = idx_pref;
+      idx_pref = load_index(it + NBUF);
+      issue(it + NBUF - 1, idx_cur);  // refills the buffer consumed in the previous iteration
+    }
+    const long long s = gw + it * wstride;
+    const int buf = (int)(it % NBUF);
+    const float* xs = reinterpret_cast<const float*>(wbase + (size_t)buf * p.in_bytes);
+    mbar_wait(smem_u32(bars + buf), (uint32_t)((it / NBUF) & 1));
+
+    float acc[6][4];
+#pragma unroll
+    for (int ti = 0; ti < 6; ++ti)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[ti][c] = 0.0f;
+
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int k0 = 16 * ks + 2 * t;
+        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][0] + k0), ah[mt][0], al[mt][0]);
+        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][1] + k0), ah[mt][1], al[mt][1]);
+        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][0] + k0 + 8), ah[mt][2], al[mt][2]);
+        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][1] + k0 + 8), ah[mt][3], al[mt][3]);
+      }
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti) {
+        const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+        // B fragment of n-tile nt = registers {nt&1, 2+(nt&1)} of the A fragment of m-tile nt>>1
+        const uint32_t bh0 = ah[nt >> 1][nt & 1], bh1 = ah[nt >> 1][2 + (nt & 1)];
+        const uint32_t bl0 = al[nt >> 1][nt & 1], bl1 = al[nt >> 1][2 + (nt & 1)];
+        mma_bf16_16816(acc[ti], ah[mt], bl0, bl1);
+        mma_bf16_16816(acc[ti], al[mt], bh0, bh1);
+        mma_bf16_16816(acc[ti], ah[mt], bh0, bh1);
+      }
+    }
+
+    // ---- assemble the output row in shared memory
+    if (p.out_split) {
+      __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(ostage);
+      __nv_bfloat16* ol = oh + p.out_Kp;
+      if (p.P > 0) {
+        const float* pr = xs + (MODE == 1 ? p.bottom_slot : F) * DS;
+        for (int e = lane; e < p.P; e += 32) {
+          const float v = pr[e];
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          oh[e] = h;
+          ol[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+      }
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (off[ti][c] >= 0) {
+            const float v = acc[ti][c];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            oh[off[ti][c]] = h;
+            ol[off[ti][c]] = __float2bfloat16_rn(v - __bfloat162float(h));
+          }
+    } else {
+      float* os = reinterpret_cast<float*>(ostage);
+      if (p.P > 0) {
+        const float* pr = xs + (MODE == 1 ? p.bottom_slot : F) * DS;
+        for (int e = lane; e < p.P; e += 32) os[e] = pr[e];
+      }
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (off[ti][c] >= 0) os[off[ti][c]] = acc[ti][c];
+    }
+    __syncwarp();  // staging complete; also: every lane is done reading xs[buf]
+
+    // ---- coalesced row store
+    if (p.out_split) {
+      const uint4* src = reinterpret_cast<const uint4*>(ostage);
+      uint4* dst = reinterpret_cast<uint4*>(p.out_split + s * (2ll * p.out_Kp));
+      const int n16 = p.out_Kp >> 2;  // 2*Kp bf16 = Kp/4 x 16 B
+      for (int e = lane; e < n16; e += 32) dst[e] = src[e];
+    }
+    if (p.out_f32) {
+      const float* os = reinterpret_cast<const float*>(ostage);
+      float* dst = p.out_f32 + s * p.out_stride;
+      if (!p.out_split) {
+        if (((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0)) {
+          const int n4 = OW >> 2;
+          for (int e = lane; e < n4; e += 32)
+            reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(os)[e];
+          for (int e = (n4 << 2) + lane; e < OW; e += 32) dst[e] = os[e];
+        } else {
+          for (int e = lane; e < OW; e += 32) dst[e] = os[e];
+        }
+      }
+    }
+    __syncwarp();  // staging may be overwritten by the next sample
+  }
+}
+
+// Returns MM_ERR_UNSUPPORTED (without touching the error text) when the fast path does not apply.
+template <int MODE, typename IdxT>
+int launch(const float* x, int64_t x_stride, const GatherParams& gp, const float* prefix, int64_t prefix_stride,
+           int P, int bottom_slot, int64_t B, int F, int D, float* out_f32, int64_t out_stride, void* out_split,
+           int out_Kp, int32_t* oob, cudaStream_t st, const char* who) {
+  if (F < 2 || F > 32 || D % 16 != 0 || D < 16 || D > 256) return MM_ERR_UNSUPPORTED;
+  if (P != 0 && P != D) return MM_ERR_UNSUPPORTED;
+  if (out_f32 && out_split) return MM_ERR_UNSUPPORTED;
+  const int rows = (MODE == 0 && P > 0) ? F + 1 : F;
+  if (rows > 32) return MM_ERR_UNSUPPORTED;
+  if (MODE == 1 && gp.n_tables + (bottom_slot >= 0 ? 1 : 0) != F) return MM_ERR_UNSUPPORTED;
+  if (MODE == 0 && (((uintptr_t)x & 15) || (x_stride & 3))) return MM_ERR_UNSUPPORTED;
+  if (P > 0 && (((uintptr_t)prefix & 15) || (prefix_stride & 3))) return MM_ERR_UNSUPPORTED;
+  const int OW = P + F * (F - 1) / 2;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x;
+  p.x_stride = x_stride;
+  p.prefix = prefix;
+  p.prefix_stride = prefix_stride;
+  p.P = P;
+  p.bottom_slot = bottom_slot;
+  p.B = B;
+  p.F = F;
+  p.D = D;
+  p.T = MODE == 1 ? gp.n_tables : 0;
+  p.rows = rows;
+  p.out_f32 = out_f32;
+  p.out_stride = out_stride;
+  p.out_split = (__nv_bfloat16*)out_split;
+  p.out_Kp = out_Kp;
+  p.oob_count = oob;
+  p.in_bytes = (unsigned)(rows * (D + 8) * 4);
+  const unsigned stage = out_split ? (unsigned)(2 * out_Kp * 2) : (unsigned)(((OW + 3) & ~3) * 4);
+  p.per_warp_bytes = (NBUF * p.in_bytes + stage + 127u) & ~127u;
+  int warps = (int)((200u * 1024u) / p.per_warp_bytes);
+  if (warps > MAX_WARPS) warps = MAX_WARPS;
+  if (warps < 2) return MM_ERR_UNSUPPORTED;
+  p.n_warps = warps;
+  p.bar_offset = (unsigned)warps * p.per_warp_bytes;
+  const size_t smem = (size_t)p.bar_offset + (size_t)warps * NBUF * sizeof(uint64_t);
+  auto kern = interact_mma_kernel<MODE, IdxT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  long long want = (B + warps - 1) / warps;
+  const long long sms = sm_count();
+  const unsigned grid = (unsigned)(want < sms ? want : sms);
+  kern<<<grid, 32 * warps, smem, st>>>(gp, p);
+  return check_launch(who);
+}
+
+template int launch<0, int32_t>(const float*, int64_t, const GatherParams&, const float*, int64_t, int, int, int64_t,
+                                int, int, float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*);
+template int launch<1, int32_t>(const float*, int64_t, const GatherParams&, const float*, int64_t, int, int, int64_t,
+                                int, int, float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*);
+template int launch<1, int64_t>(const float*, int64_t, const GatherParams&, const float*, int64_t, int, int, int64_t,
+                                int, int, float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*);
+
+}  // namespace imma
+}  // namespace mm

@@ -13,7 +13,8 @@ import numpy as np
 import torch
 
 from . import ops
-from .blocks import MLP, CrossBlock, CrossBlockSeq, DLRM, DLRMBlock, MLPBlock, _Dense, run_dense_chain
+from .blocks import (MLP, CrossBlock, CrossBlockSeq, DLRM, DLRMBlock, MLPBlock, _Dense, dense_engine,
+                     run_dense_chain)
 from .core import Block, Prediction, TabularData, default_device, to_device, unique_name
 from .inputs import EmbeddingOptions, EmbeddingsBlock, InputBlockV2
 from .retrieval import ItemRetrievalTask, TwoTowerBlock
@@ -160,8 +161,12 @@ class RankingModel(Model):
         if isinstance(self.body, DLRM) and self.body.top_block is not None:
             # top MLP + output layer as ONE dense chain (no fp32 round trip between them)
             bottom = self.body.bottom_forward(inputs)
+            layers = self.body.top_block.dense_layers + [self.prediction.to_call]
+            if dense_engine() != "fp32" and self.body.can_emit_split():
+                a = self.body.interaction_forward(inputs, bottom, as_split=True)
+                return run_dense_chain(None, layers, a_split=a, K=self.body.output_width_before_top())
             x = self.body.interaction_forward(inputs, bottom)
-            return run_dense_chain(x, self.body.top_block.dense_layers + [self.prediction.to_call])
+            return run_dense_chain(x, layers)
         if isinstance(self.body, DCNBody) and self.body.stacked:
             x = self.body.cross(self.body.input_block(inputs))
             return run_dense_chain(x, self.body.deep.dense_layers + [self.prediction.to_call])

@@ -139,31 +139,45 @@ def gather_seq(weight, ids, combiner: str, out: torch.Tensor, out_col: int = 0,
     return out
 
 
+def _split_out_args(out: torch.Tensor):
+    """(fp32 ptr, fp32 stride, split ptr, out_Kp) for an output that is either fp32 (B, W) or the
+    split-bf16 operand (B, 2*Kp) of a following tensor-core layer."""
+    if out.dtype == torch.bfloat16:
+        if out.dim() != 2 or not out.is_contiguous() or out.shape[1] % 128 != 0:
+            raise ValueError("a split-bf16 output must be contiguous (B, 2*Kp) with Kp a multiple of 64")
+        return None, 0, out.data_ptr(), out.shape[1] // 2
+    _dev(out, "out", torch.float32)
+    return out.data_ptr(), _row_stride(out, "out"), None, 0
+
+
 def dot_interaction(x: torch.Tensor, out: torch.Tensor, prefix: Optional[torch.Tensor] = None,
                     self_interaction: bool = False) -> torch.Tensor:
-    """x (B,F,D) -> out[:, :P] = prefix, out[:, P:] = upper-triangle pairwise dots."""
-    _dev(x, "x", torch.float32), _dev(out, "out", torch.float32)
+    """x (B,F,D) -> out[:, :P] = prefix, out[:, P:] = upper-triangle pairwise dots.
+    `out` fp32 (B, >=P+pairs) or bf16 (B, 2*Kp) = split operand of the next tensor-core layer."""
+    _dev(x, "x", torch.float32), _dev(out, "out")
     if x.dim() != 3 or not x.is_contiguous():
         raise ValueError("x must be a contiguous (B, F, D) tensor")
     B, F, D = x.shape
     P = 0 if prefix is None else prefix.shape[1]
+    o32, ostride, osplit, okp = _split_out_args(out)
     _cabi.check(
         _lib().mm_dot_interaction(x.data_ptr(), B, F, D, F * D, _ptr(prefix), P,
                                   0 if prefix is None else _row_stride(_dev(prefix, "prefix", torch.float32), "prefix"),
-                                  int(self_interaction), out.data_ptr(), _row_stride(out, "out"), _stream()),
+                                  int(self_interaction), o32, ostride, osplit, okp, _stream()),
         "mm_dot_interaction")
     return out
 
 
 def dlrm_gather_interact(weights, indices, slots, D: int, bottom: Optional[torch.Tensor], bottom_slot: int,
                          out: torch.Tensor, oob: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _dev(out, "out", torch.float32)
+    _dev(out, "out")
     B = out.shape[0]
     arr, n, dt = _table_array(weights, indices, [s * D for s in slots], B)
+    o32, ostride, osplit, okp = _split_out_args(out)
     _cabi.check(
         _lib().mm_dlrm_gather_interact(arr, n, dt, B, D, _ptr(bottom),
                                        0 if bottom is None else _row_stride(_dev(bottom, "bottom", torch.float32), "bottom"),
-                                       bottom_slot, out.data_ptr(), _row_stride(out, "out"), _ptr(oob), _stream()),
+                                       bottom_slot, o32, ostride, osplit, okp, _ptr(oob), _stream()),
         "mm_dlrm_gather_interact")
     return out
 

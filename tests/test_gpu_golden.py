@@ -31,8 +31,9 @@ def test_reference_torch_dlrm_interaction(device):
     assert np.array_equal(stack.cpu().numpy().reshape(B, F, D), z["stacked"])
     out = torch.empty((B, D + F * (F - 1) // 2), dtype=torch.float32, device=device)
     ops.dot_interaction(stack.view(B, F, D), out, prefix=dev(z["in_continuous"], device))
-    np.testing.assert_allclose(out.cpu().numpy(), z["block_out"], rtol=RTOL, atol=ATOL)
-    np.testing.assert_allclose(out.cpu().numpy()[:, D:], z["interactions"], rtol=RTOL, atol=ATOL)
+    # tensor-core interaction (3-pass split-bf16): |err| ~ 2^-16 * sum|x_k y_k| -> absolute, not relative
+    np.testing.assert_allclose(out.cpu().numpy(), z["block_out"], rtol=RTOL, atol=2e-4)
+    np.testing.assert_allclose(out.cpu().numpy()[:, D:], z["interactions"], rtol=RTOL, atol=2e-4)
 
 
 def test_reference_torch_concat(device):
