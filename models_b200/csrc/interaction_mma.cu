@@ -6,9 +6,12 @@
 // fp32 accumulate) — the kernel stays HBM-bound instead of shared-memory-bandwidth bound like the
 // CUDA-core version (interaction.cu, 3x3 register blocking: 0.31 ms vs the 0.086 ms HBM floor).
 //
-// Data movement: every row (256 B for D = 64) is ONE cp.async.bulk (TMA engine, UBLKCP) from the
-// embedding table — or the stacked (B,F,D) tensor — into a padded shared-memory tile, completion
-// tracked by a per-buffer mbarrier; each warp keeps NBUF-1 samples in flight while it computes one.
+// Data movement: rows go from the embedding tables — or the stacked (B,F,D) tensor — straight
+// into a padded shared-memory tile with 16-byte cp.async (LDGSTS: no register staging, zero-fill
+// for out-of-range ids), one commit group per sample; each warp keeps NBUF-1 samples in flight
+// while it computes one.  (A first version issued one cp.async.bulk per row: UBLKCP takes uniform
+// registers, so the compiler serialised the 27 per-lane copies through an ELECT/R2UR loop that
+// cost ~20 % of the issue slots — see profiles/r01_notes.md.)
 // Because B = X^T, the B fragments of n-tile nt ARE registers of the A fragment of m-tile nt/2, so X
 // is read from shared memory once per k-step.  The output row [prefix | upper triangle] is assembled
 // in shared memory and written coalesced, either as fp32 or directly as the split-bf16 operand
@@ -18,6 +21,7 @@
 // (merlin/models/tf/core/aggregation.py:101-108, blocks/interaction.py:86-116, blocks/dlrm.py:126-130).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "mm_common.cuh"
@@ -25,7 +29,6 @@
 namespace mm {
 namespace imma {
 
-constexpr int NBUF = 3;
 constexpr int MAX_WARPS = 12;
 
 struct Params {
@@ -46,38 +49,22 @@ struct Params {
   int out_Kp;
   int* oob_count;
   int n_warps;
-  unsigned per_warp_bytes, in_bytes, bar_offset;
+  unsigned per_warp_bytes, in_bytes;
+  int log2V, log2D;  // V = D/4 float4 per row
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+// 16-byte global -> shared copy; src_bytes = 0 zero-fills the destination (out-of-range id)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 8000000000ll) __trap();  // protocol bug: trap instead of hanging the GPU
-  }
-}
-// one row: global -> shared through the bulk-copy (TMA) engine
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -90,24 +77,21 @@ __device__ __forceinline__ void split_pair(float2 v, uint32_t& hi, uint32_t& lo)
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
-template <int MODE, typename IdxT>
+template <int MODE, typename IdxT, int KD /* compile-time D (0 = runtime) */, int NBUF /* sample buffers per warp */>
 __global__ void __launch_bounds__(32 * MAX_WARPS, 1)
 interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int F = p.F, D = p.D, DS = D + 8, KS = D >> 4;
+  // rows are stored unpadded (D floats) with the 16-byte chunk index XOR-swizzled by ((row & 3) << 1):
+  // the 8-byte fragment loads of 4 consecutive rows then hit 8 distinct chunks (conflict-free)
+  const int F = p.F, D = KD > 0 ? KD : p.D, DS = D, KS = D >> 4;
   uint8_t* wbase = smem_raw + (size_t)warp * p.per_warp_bytes;
   uint8_t* ostage = wbase + (size_t)NBUF * p.in_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + p.bar_offset) + warp * NBUF;
   const int npairs = F * (F - 1) / 2;
   const int OW = p.P + npairs;
 
-  // ---- one-time per warp: barriers, zeroed output staging, output offsets of this lane's accumulators
-  if (lane == 0) {
-    for (int i = 0; i < NBUF; ++i) mbar_init(smem_u32(bars + i), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  // ---- one-time per warp: zeroed output staging, output offsets of this lane's accumulators
   {
     const int stage_words = (int)((p.per_warp_bytes - NBUF * p.in_bytes) >> 2);
     for (int i = lane; i < stage_words; i += 32) reinterpret_cast<uint32_t*>(ostage)[i] = 0u;
@@ -128,82 +112,85 @@ interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int h = 0; h < 2; ++h) ro[mt][h] = min(16 * mt + g + 8 * h, F - 1) * DS;
+  int sw[2][2];  // chunk swizzle of those rows
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) sw[mt][h] = ((min(16 * mt + g + 8 * h, F - 1) & 3) << 1) & ((D >> 2) - 1);
   __syncwarp();
 
   const long long gw = (long long)blockIdx.x * p.n_warps + warp;
   const long long wstride = (long long)gridDim.x * p.n_warps;
   const long long n_mine = gw < p.B ? (p.B - gw + wstride - 1) / wstride : 0;
 
-  // lane -> staged row: MODE 1: lanes < T tables, lane T bottom; MODE 0: lanes < F rows, lane F prefix
-  const bool row_lane = lane < p.rows;
-  int my_slot = lane;
-  const float* my_w = nullptr;
-  long long my_rows = 0;
-  const IdxT* my_idx_ptr = nullptr;
-  if (MODE == 1 && lane < p.T) {
-    my_slot = gp.t[lane].out_col / D;
-    my_w = gp.t[lane].weights;
-    my_rows = gp.t[lane].rows;
-    my_idx_ptr = reinterpret_cast<const IdxT*>(gp.t[lane].indices);
-  } else if (MODE == 1 && lane == p.T) {
-    my_slot = p.bottom_slot;
-  }
+  // lane r < T holds the id of table r for the sample being issued (MODE 1)
+  const IdxT* my_idx_ptr = (MODE == 1 && lane < p.T) ? reinterpret_cast<const IdxT*>(gp.t[lane].indices) : nullptr;
+  const long long my_rows = (MODE == 1 && lane < p.T) ? gp.t[lane].rows : 0;
+  const int V = D >> 2;
 
-  auto load_index = [&](long long it) -> long long {
-    if (MODE == 1 && lane < p.T && it < n_mine) return (long long)my_idx_ptr[gw + it * wstride];
-    return 0;
+  // raw (un-widened) index prefetch: the value is not touched until the next iteration, so the
+  // global-load latency is hidden behind a whole sample of compute
+  auto load_index = [&](long long it) -> IdxT {
+    if (MODE == 1 && lane < p.T && it < n_mine) return my_idx_ptr[gw + it * wstride];
+    return (IdxT)0;
   };
-  auto issue = [&](long long it, long long idx) {
-    if (it >= n_mine) return;
-    const long long s = gw + it * wstride;
-    const int buf = (int)(it % NBUF);
-    float* xs = reinterpret_cast<float*>(wbase + (size_t)buf * p.in_bytes);
-    const uint32_t bar = smem_u32(bars + buf);
-    const float* src = nullptr;
-    bool valid = false;
-    if (row_lane) {
-      if (MODE == 1) {
-        if (lane < p.T) {
-          valid = idx >= 0 && idx < my_rows;
-          if (!valid && p.oob_count) atomicAdd(p.oob_count, 1);
-          src = my_w + idx * D;
+  auto issue = [&](long long it, IdxT idx_raw) {
+    if (it < n_mine) {
+      const long long s = gw + it * wstride;
+      const int buf = (int)(it % NBUF);
+      const uint32_t xs_u32 = smem_u32(wbase + (size_t)buf * p.in_bytes);
+      int idx32 = -1;  // row index within the table (tables have < 2^31 rows), -1 = zero row
+      if (MODE == 1 && lane < p.T) {
+        const long long idx = (long long)idx_raw;
+        if (idx >= 0 && idx < my_rows) idx32 = (int)idx;
+        else if (p.oob_count) atomicAdd(p.oob_count, 1);
+      }
+      const int total = p.rows << p.log2V;
+      for (int e0 = 0; e0 < total; e0 += 32) {  // warp-uniform trip count (shuffles inside)
+        const int e = e0 + lane;
+        const bool act = e < total;
+        const int r = act ? e >> p.log2V : 0, v = e & (V - 1);
+        const float* src;
+        uint32_t bytes = 16;
+        int slot = r;
+        if (MODE == 1) {
+          const int ridx = __shfl_sync(0xffffffffu, idx32, r);
+          if (r < p.T) {
+            slot = gp.t[r].out_col >> p.log2D;
+            src = gp.t[r].weights + ((long long)(ridx < 0 ? 0 : ridx) << p.log2D) + v * 4;
+            if (ridx < 0) bytes = 0;
+          } else {
+            slot = p.bottom_slot;
+            src = p.prefix + s * p.prefix_stride + v * 4;
+          }
         } else {
-          valid = true;
-          src = p.prefix + s * p.prefix_stride;
+          src = r < F ? p.x + s * p.x_stride + ((long long)r << p.log2D) + v * 4
+                      : p.prefix + s * p.prefix_stride + v * 4;
         }
-      } else {
-        valid = true;
-        src = lane < F ? p.x + s * p.x_stride + (long long)lane * D : p.prefix + s * p.prefix_stride;
+        if (act) cp_async16_zfill(xs_u32 + (uint32_t)((slot * DS + ((v ^ (((slot & 3) << 1) & (V - 1))) << 2)) * 4), src, bytes);
       }
     }
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(vmask) * (uint32_t)(D * 4));
-    __syncwarp();
-    if (row_lane) {
-      float* dst = xs + my_slot * DS;
-      if (valid) bulk_copy_g2s(smem_u32(dst), src, (uint32_t)(D * 4), bar);
-      else
-        for (int d = 0; d < D; d += 4) *reinterpret_cast<float4*>(dst + d) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    cp_async_commit();  // one group per sample (empty past the end keeps the group count in step)
   };
 
   // ---- software pipeline: NBUF-1 samples in flight; indices fetched one iteration ahead of their rows
-  long long idx_pref = load_index(0);
+  IdxT idx_pref = load_index(0);
   for (int i = 0; i < NBUF - 1; ++i) {
-    const long long idx_cur = idx_pref;
+    const IdxT idx_cur = idx_pref;
     idx_pref = load_index(i + 1);
     issue(i, idx_cur);
   }
   for (long long it = 0; it < n_mine; ++it) {
     {
-      const long long idx_cur = idx_pref;
+      const IdxT idx_cur = idx_pref;
       idx_pref = load_index(it + NBUF);
       issue(it + NBUF - 1, idx_cur);  // refills the buffer consumed in the previous iteration
     }
     const long long s = gw + it * wstride;
     const int buf = (int)(it % NBUF);
     const float* xs = reinterpret_cast<const float*>(wbase + (size_t)buf * p.in_bytes);
-    mbar_wait(smem_u32(bars + buf), (uint32_t)((it / NBUF) & 1));
+    cp_async_wait<NBUF - 1>();  // this sample's group (the oldest of NBUF pending) has landed
+    __syncwarp();
 
     float acc[6][4];
 #pragma unroll
@@ -211,25 +198,34 @@ interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[ti][c] = 0.0f;
 
+#pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       uint32_t ah[2][4], al[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        const int k0 = 16 * ks + 2 * t;
-        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][0] + k0), ah[mt][0], al[mt][0]);
-        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][1] + k0), ah[mt][1], al[mt][1]);
-        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][0] + k0 + 8), ah[mt][2], al[mt][2]);
-        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][1] + k0 + 8), ah[mt][3], al[mt][3]);
+        // logical column k0 = 16ks + 2t (+8): chunk c = k0/4, swizzled by the row's (r & 3) << 1
+        const int c0 = 4 * ks + (t >> 1), w = (t & 1) * 2;
+        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][0] + (((c0) ^ sw[mt][0]) << 2) + w), ah[mt][0], al[mt][0]);
+        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][1] + (((c0) ^ sw[mt][1]) << 2) + w), ah[mt][1], al[mt][1]);
+        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][0] + (((c0 + 2) ^ sw[mt][0]) << 2) + w), ah[mt][2], al[mt][2]);
+        split_pair(*reinterpret_cast<const float2*>(xs + ro[mt][1] + (((c0 + 2) ^ sw[mt][1]) << 2) + w), ah[mt][3], al[mt][3]);
+      }
+      // B fragment of n-tile nt = registers {nt&1, 2+(nt&1)} of the A fragment of m-tile nt>>1.
+      // Pass-major order: six independent accumulators between dependent MMAs.
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti) {
+        const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+        mma_bf16_16816(acc[ti], ah[mt], al[nt >> 1][nt & 1], al[nt >> 1][2 + (nt & 1)]);
       }
 #pragma unroll
       for (int ti = 0; ti < 6; ++ti) {
         const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-        // B fragment of n-tile nt = registers {nt&1, 2+(nt&1)} of the A fragment of m-tile nt>>1
-        const uint32_t bh0 = ah[nt >> 1][nt & 1], bh1 = ah[nt >> 1][2 + (nt & 1)];
-        const uint32_t bl0 = al[nt >> 1][nt & 1], bl1 = al[nt >> 1][2 + (nt & 1)];
-        mma_bf16_16816(acc[ti], ah[mt], bl0, bl1);
-        mma_bf16_16816(acc[ti], al[mt], bh0, bh1);
-        mma_bf16_16816(acc[ti], ah[mt], bh0, bh1);
+        mma_bf16_16816(acc[ti], al[mt], ah[nt >> 1][nt & 1], ah[nt >> 1][2 + (nt & 1)]);
+      }
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti) {
+        const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+        mma_bf16_16816(acc[ti], ah[mt], ah[nt >> 1][nt & 1], ah[nt >> 1][2 + (nt & 1)]);
       }
     }
 
@@ -238,9 +234,10 @@ interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
       __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(ostage);
       __nv_bfloat16* ol = oh + p.out_Kp;
       if (p.P > 0) {
-        const float* pr = xs + (MODE == 1 ? p.bottom_slot : F) * DS;
+        const int prow = MODE == 1 ? p.bottom_slot : F;
+        const float* pr = xs + prow * DS;
         for (int e = lane; e < p.P; e += 32) {
-          const float v = pr[e];
+          const float v = pr[((((e >> 2) ^ (((prow & 3) << 1) & ((D >> 2) - 1)))) << 2) + (e & 3)];
           const __nv_bfloat16 h = __float2bfloat16_rn(v);
           oh[e] = h;
           ol[e] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -259,8 +256,9 @@ interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
     } else {
       float* os = reinterpret_cast<float*>(ostage);
       if (p.P > 0) {
-        const float* pr = xs + (MODE == 1 ? p.bottom_slot : F) * DS;
-        for (int e = lane; e < p.P; e += 32) os[e] = pr[e];
+        const int prow = MODE == 1 ? p.bottom_slot : F;
+        const float* pr = xs + prow * DS;
+        for (int e = lane; e < p.P; e += 32) os[e] = pr[((((e >> 2) ^ (((prow & 3) << 1) & ((D >> 2) - 1)))) << 2) + (e & 3)];
       }
 #pragma unroll
       for (int ti = 0; ti < 6; ++ti)
@@ -300,7 +298,7 @@ template <int MODE, typename IdxT>
 int launch(const float* x, int64_t x_stride, const GatherParams& gp, const float* prefix, int64_t prefix_stride,
            int P, int bottom_slot, int64_t B, int F, int D, float* out_f32, int64_t out_stride, void* out_split,
            int out_Kp, int32_t* oob, cudaStream_t st, const char* who) {
-  if (F < 2 || F > 32 || D % 16 != 0 || D < 16 || D > 256) return MM_ERR_UNSUPPORTED;
+  if (F < 2 || F > 32 || (D != 16 && D != 32 && D != 64 && D != 128)) return MM_ERR_UNSUPPORTED;
   if (P != 0 && P != D) return MM_ERR_UNSUPPORTED;
   if (out_f32 && out_split) return MM_ERR_UNSUPPORTED;
   const int rows = (MODE == 0 && P > 0) ? F + 1 : F;
@@ -309,6 +307,14 @@ int launch(const float* x, int64_t x_stride, const GatherParams& gp, const float
   if (MODE == 0 && (((uintptr_t)x & 15) || (x_stride & 3))) return MM_ERR_UNSUPPORTED;
   if (P > 0 && (((uintptr_t)prefix & 15) || (prefix_stride & 3))) return MM_ERR_UNSUPPORTED;
   const int OW = P + F * (F - 1) / 2;
+  // buffers per warp: gathers of random rows want 2 samples in flight behind the one being computed;
+  // MM_IMMA_NBUF overrides for tuning
+  static int nbuf_env = -1;
+  if (nbuf_env < 0) {
+    const char* e = getenv("MM_IMMA_NBUF");
+    nbuf_env = e ? atoi(e) : 0;
+  }
+  const int NBUF = (nbuf_env == 2 || nbuf_env == 3) ? nbuf_env : 2;
   Params p;
   memset(&p, 0, sizeof(p));
   p.x = x;
@@ -327,24 +333,26 @@ int launch(const float* x, int64_t x_stride, const GatherParams& gp, const float
   p.out_split = (__nv_bfloat16*)out_split;
   p.out_Kp = out_Kp;
   p.oob_count = oob;
-  p.in_bytes = (unsigned)(rows * (D + 8) * 4);
+  p.in_bytes = (unsigned)(rows * D * 4);
   const unsigned stage = out_split ? (unsigned)(2 * out_Kp * 2) : (unsigned)(((OW + 3) & ~3) * 4);
   p.per_warp_bytes = (NBUF * p.in_bytes + stage + 127u) & ~127u;
-  int warps = (int)((200u * 1024u) / p.per_warp_bytes);
+  int warps = (int)((226u * 1024u) / p.per_warp_bytes);
   if (warps > MAX_WARPS) warps = MAX_WARPS;
   if (warps < 2) return MM_ERR_UNSUPPORTED;
   p.n_warps = warps;
-  p.bar_offset = (unsigned)warps * p.per_warp_bytes;
-  const size_t smem = (size_t)p.bar_offset + (size_t)warps * NBUF * sizeof(uint64_t);
-  auto kern = interact_mma_kernel<MODE, IdxT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  p.log2D = D == 16 ? 4 : D == 32 ? 5 : D == 64 ? 6 : 7;
+  p.log2V = p.log2D - 2;
+  const size_t smem = (size_t)warps * p.per_warp_bytes;
+  auto kern = D == 64 ? (NBUF == 3 ? interact_mma_kernel<MODE, IdxT, 64, 3> : interact_mma_kernel<MODE, IdxT, 64, 2>)
+                      : (NBUF == 3 ? interact_mma_kernel<MODE, IdxT, 0, 3> : interact_mma_kernel<MODE, IdxT, 0, 2>);
+  static bool attr_set[2][2] = {{false, false}, {false, false}};
+  if (!attr_set[D == 64][NBUF == 3]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(e));
       return (int)e;
     }
-    attr_set = true;
+    attr_set[D == 64][NBUF == 3] = true;
   }
   long long want = (B + warps - 1) / warps;
   const long long sms = sm_count();
