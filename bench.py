@@ -202,6 +202,9 @@ def main():
     model.build(dev)
     n_bufs = 4
     hosts = host_batches(datasets, schema, B, n_bufs, seed0=1234 + 1000 * rank)
+    # packed pinned host batches (one allocation each) and their device-resident copies
+    hbs = [mm.HostBatch.like(h, model.input_columns()) for h in hosts]
+    packed_dev = [hb.buffer.to(dev) for hb in hbs]
     devs = [{k: torch.from_numpy(v).to(dev) for k, v in h.items()} for h in hosts]
     torch.cuda.synchronize()
 
@@ -212,55 +215,74 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    # events around the dominant kernel (gather+interaction fused), recorded in-stream
-    kev = []
+    # the public serving call: forward captured into a CUDA graph over static buffers
+    cf = model.compile(hbs[0])
+    ref_out = model(devs[0])
+    cf.load_device(packed_dev[0])
+    assert torch.equal(ref_out, cf.replay()), "graph replay diverges from model.__call__"
 
     def step(i):
-        feats = devs[i % n_bufs]
-        bottom = model.body.bottom_forward(feats)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        x = model.body.interaction_forward(feats, bottom)
-        e1.record()
-        kev.append((e0, e1))
-        return run_dense_chain(x, model.body.top_block.dense_layers + [model.prediction.to_call])
-
-    # correctness guard: the staged step above must equal the public call
-    ref_out = model(devs[0])
-    assert torch.equal(ref_out, step(0)), "bench step diverges from model.__call__"
-    kev.clear()
+        cf.load_device(packed_dev[i % n_bufs])  # device-to-device refresh of the static input buffer
+        return cf.replay()
 
     for i in range(args.warmup):
         step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = ops.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev.clear()
     t0.record()
     for i in range(args.steps):
         out = step(i)
     t1.record()
     barrier()
-    launches = ops.launch_count() - l0
     clocks = sampler.stop()
+    launches = cf.launches_per_replay * args.steps
     elapsed_ms = t0.elapsed_time(t1)
+
+    # ---- roofline of the dominant kernel: launched back to back on the same rotating inputs with a
+    # CUDA-event pair around every launch (the host runs ahead of the GPU, so each pair brackets
+    # exactly one kernel execution; graph nodes cannot be bracketed individually)
+    body = model.body
+    slots = body.slots()
+    feats_names = body.embeddings.feature_names
+    tables = [body.embeddings.feature_to_table[f].table for f in feats_names]
+    slot_list = [slots[f] for f in feats_names]
+    bottoms = [body.bottom_forward(d) for d in devs]
+    width = body.output_width_before_top()
+    a_out = torch.empty((B, 2 * ops.tc_padded_k(width)), dtype=torch.bfloat16, device=dev)
+    idx_lists = [[d[f] for f in feats_names] for d in devs]
+
+    def dominant(i):
+        ops.dlrm_gather_interact(tables, idx_lists[i % n_bufs], slot_list, 64, bottoms[i % n_bufs],
+                                 slots["bottom_block"], a_out)
+
+    for i in range(args.warmup):
+        dominant(i)
+    torch.cuda.synchronize()
+    kev = []
+    for i in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dominant(i)
+        e1.record()
+        kev.append((e0, e1))
+    torch.cuda.synchronize()
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
 
-    # ---- e2e: public host-buffer call; pinned H2D + forward + D2H per step inside the region
+    # ---- e2e: public host-buffer call; ONE pinned H2D + graph + D2H per step inside the region
     for i in range(3):
-        model.forward_host(hosts[i % n_bufs])
+        cf(hbs[i % n_bufs])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(5, min(args.steps, 20))
+    e2e_steps = max(5, args.steps)
     e0.record()
     for i in range(e2e_steps):
-        res = model.forward_host(hosts[i % n_bufs])
+        res = cf(hbs[i % n_bufs])
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    h2d = int(sum(v.nbytes for v in hosts[0].values()))
+    h2d = int(hbs[0].payload_bytes())
     d2h = int(res.numel() * res.element_size())
 
     if world > 1:
@@ -295,13 +317,15 @@ def main():
                 "batch_per_gpu": B, "global_batch": B * world, "index_dtype": "int32", "table_rows": 45621194,
                 "table_gb": 11.68, "parallelism": f"replicas x{world} (no data-path collective)",
                 "l2": f"inputs larger than L2: 11.7 GB of tables, {n_bufs} rotating input batches, no flush",
+                "runtime": "CUDA graph replay (model.compile); input refresh = one D2D copy of the packed batch per step",
                 "dense_engine": mm.dense_engine(),
             },
             "clocks": clocks,
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "interact_kernel<gather-fused> (mm_dlrm_gather_interact)",
+            "roofline": {"bound": "hbm", "kernel": "interact_mma_kernel<gather-fused> (mm_dlrm_gather_interact)",
+                         "timing": "CUDA events around each of K back-to-back launches on the same rotating inputs (graph nodes cannot be bracketed)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": fused_b * B,
                          "kernel_ms": kern_ms, "traffic": None},

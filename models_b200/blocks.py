@@ -449,14 +449,13 @@ class DLRM(Block):
 
         all_onehot = all(emb.feature_to_table[f].lookup_kind(get_feature(inputs, f)) == "onehot" for f in feats)
         if self.fused and all_onehot and with_prefix == (bottom is not None):
-            oob = torch.zeros(1, dtype=torch.int32, device=dev) if emb.check_indices else None
+            oob = emb.counter(dev)
             idx = [_as_index(get_feature(inputs, f)).reshape(-1) for f in feats]
             if len({i.dtype for i in idx}) > 1:
                 idx = [i.to(torch.int64) for i in idx]
             ops.dlrm_gather_interact([emb.feature_to_table[f].table for f in feats], idx, [slots[f] for f in feats], D,
                                      bottom, slots.get("bottom_block", -1), out, oob)
-            if oob is not None:
-                _raise_on_oob(oob, ",".join(emb.tables))
+            emb.finish_check(oob)
             return out
         # staged path: one fused gather into the (B,F,D) stack, then the interaction kernel
         stack = torch.empty((B, F * D), dtype=torch.float32, device=dev)

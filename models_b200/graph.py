@@ -1,0 +1,141 @@
+"""Host-side runtime for the hot path: packed pinned host batches and CUDA-graph replay.
+
+At B = 65 536 a DLRM forward is ~0.3 ms of GPU work spread over ~10 kernels; launching them one
+by one from Python (argument checks, ctypes, tensor-map encodes, allocator calls) costs more host
+time than that.  `CompiledForward` captures the whole forward once into a CUDA graph over static
+device buffers and replays it: one H2D copy of a packed pinned batch, one graph launch, one D2H copy
+of the predictions.  This is the reference-facing "call a user makes" for serving: host buffers in,
+host predictions out (`Model.compile(example_batch)`), and what bench.py reports as `e2e`.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .core import Prediction, default_device
+
+_ALIGN = 256
+
+
+class HostBatch:
+    """All input columns of one batch inside ONE pinned host allocation (so the H2D transfer is a
+    single cudaMemcpyAsync), exposed as per-column NumPy / torch views."""
+
+    def __init__(self, spec: Dict[str, tuple]):
+        """spec: name -> (shape tuple, numpy dtype)."""
+        self.spec = {k: (tuple(int(x) for x in shp), np.dtype(dt)) for k, (shp, dt) in spec.items()}
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for name, (shp, dt) in self.spec.items():
+            self.offsets[name] = off
+            nbytes = int(np.prod(shp, dtype=np.int64)) * dt.itemsize
+            off += (nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.nbytes = off
+        self.buffer = torch.empty(max(off, _ALIGN), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        self.columns: Dict[str, torch.Tensor] = {name: _view(self.buffer, self.offsets[name], shp, dt)
+                                                 for name, (shp, dt) in self.spec.items()}
+
+    @classmethod
+    def like(cls, batch: Dict[str, np.ndarray], names=None) -> "HostBatch":
+        names = list(batch) if names is None else list(names)
+        hb = cls({k: (np.asarray(batch[k]).shape, np.asarray(batch[k]).dtype) for k in names})
+        hb.fill(batch)
+        return hb
+
+    def fill(self, batch: Dict[str, np.ndarray]) -> "HostBatch":
+        for name, (shp, dt) in self.spec.items():
+            src = np.asarray(batch[name])
+            if src.shape != shp or src.dtype != dt:
+                raise ValueError(f"column {name!r}: expected {shp} {dt}, got {src.shape} {src.dtype}")
+            self.columns[name].numpy()[...] = src
+        return self
+
+    def payload_bytes(self) -> int:
+        return sum(int(np.prod(shp, dtype=np.int64)) * dt.itemsize for shp, dt in self.spec.values())
+
+
+def _view(buf: torch.Tensor, off: int, shape, dt: np.dtype) -> torch.Tensor:
+    n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    tdt = torch.from_numpy(np.empty(0, dtype=dt)).dtype
+    return buf[off: off + n].view(tdt).view(*shape) if n else torch.empty(shape, dtype=tdt, device=buf.device)
+
+
+class CompiledForward:
+    """A model forward captured into a CUDA graph over static device buffers."""
+
+    def __init__(self, model, example: HostBatch, device=None, **call_kwargs):
+        self.model = model
+        self.device = device or default_device()
+        self.spec = example.spec
+        self.offsets = example.offsets
+        self.call_kwargs = call_kwargs
+        self.dev_buffer = torch.empty(example.buffer.numel(), dtype=torch.uint8, device=self.device)
+        self.inputs = {name: _view(self.dev_buffer, example.offsets[name], shp, dt) for name, (shp, dt) in self.spec.items()}
+        self.dev_buffer.copy_(example.buffer, non_blocking=True)
+        self._oob = model.index_error_counter(self.device)
+        model.defer_index_check(True)
+        try:
+            # warm-up on a side stream (builds weights, split kernels, zeroed operand buffers, smem
+            # attributes) — nothing lazy may remain for the capture
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._run()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            from . import ops
+
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(self.graph):
+                out = self._run()
+            self.launches_per_replay = ops.launch_count() - n0  # kernels of libmm_b200.so inside the graph
+            self.output = out
+        finally:
+            model.defer_index_check(False)
+        self.output_host = torch.empty(self.output.shape, dtype=self.output.dtype, pin_memory=True)
+        self._oob_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        self.check_indices(sync=True)
+
+    def _run(self) -> torch.Tensor:
+        out = self.model(self.inputs, **self.call_kwargs)
+        return out.outputs if isinstance(out, Prediction) else out
+
+    def check_indices(self, sync: bool = False) -> None:
+        if self._oob is None:
+            return
+        if sync:
+            n = int(self._oob.item())
+        else:
+            n = int(self._oob_host.item())
+        if n:
+            self._oob.zero_()
+            raise IndexError(f"{n} indices out of range for the embedding tables "
+                             "(TF raises InvalidArgumentError: indices[...] is not in [0, rows))")
+
+    # ---- device-resident inputs: copy into the static buffer and replay ---------------------------
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.output
+
+    def load_device(self, packed: torch.Tensor) -> None:
+        """Device-to-device refresh of the static input buffer (packed layout of `HostBatch`)."""
+        self.dev_buffer.copy_(packed, non_blocking=True)
+
+    # ---- host in / host out ---------------------------------------------------------------------------
+    def __call__(self, batch: HostBatch) -> torch.Tensor:
+        """One H2D copy of the packed pinned batch, one graph launch, one D2H copy; returns the pinned
+        host predictions (valid until the next call)."""
+        if batch.spec != self.spec:
+            raise ValueError("batch layout differs from the one this forward was compiled for")
+        self.dev_buffer.copy_(batch.buffer, non_blocking=True)
+        self.graph.replay()
+        self.output_host.copy_(self.output, non_blocking=True)
+        if self._oob is not None:
+            self._oob_host.copy_(self._oob, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.check_indices()
+        return self.output_host

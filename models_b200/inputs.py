@@ -170,6 +170,7 @@ def _as_index(t: torch.Tensor) -> torch.Tensor:
 def _raise_on_oob(oob: torch.Tensor, what: str) -> None:
     n = int(oob.item())
     if n:
+        oob.zero_()
         raise IndexError(f"{n} indices out of range for embedding table(s) {what} "
                          "(TF raises InvalidArgumentError: indices[...] is not in [0, rows))")
 
@@ -188,6 +189,19 @@ class EmbeddingsBlock(Block):
             for f in t.features:
                 self.feature_to_table[f] = t
         self.check_indices = check_indices
+        self.oob_counter: Optional[torch.Tensor] = None  # persistent device int32[1]
+        self.defer_check = False  # CUDA-graph capture: the owner checks the counter after replay
+
+    def counter(self, device) -> Optional[torch.Tensor]:
+        if not self.check_indices:
+            return None
+        if self.oob_counter is None or self.oob_counter.device != device:
+            self.oob_counter = torch.zeros(1, dtype=torch.int32, device=device)
+        return self.oob_counter
+
+    def finish_check(self, oob: Optional[torch.Tensor]) -> None:
+        if oob is not None and not self.defer_check:
+            _raise_on_oob(oob, ",".join(self.tables))
 
     @property
     def feature_names(self) -> List[str]:
@@ -212,7 +226,7 @@ class EmbeddingsBlock(Block):
         """Every feature of this block into out[:, out_cols[f] : +dim_f]; one-hot features share one
         launch (chunks of 64 tables), bag / sequence features one launch each."""
         self.build(out.device)
-        oob = torch.zeros(1, dtype=torch.int32, device=out.device) if self.check_indices else None
+        oob = self.counter(out.device)
         one_w, one_i, one_c = [], [], []
         for fname, table in self.feature_to_table.items():
             if not has_feature(inputs, fname):
@@ -228,8 +242,7 @@ class EmbeddingsBlock(Block):
             if len({i.dtype for i in one_i}) > 1:
                 one_i = [i.to(torch.int64) for i in one_i]
             ops.gather_multi(one_w, one_i, one_c, out, oob)
-        if oob is not None:
-            _raise_on_oob(oob, ",".join(self.tables))
+        self.finish_check(oob)
 
     def call(self, inputs: TabularData, **kwargs) -> TabularData:
         """dict feature -> (B, dim_f) views of one (B, sum dim) buffer (iteration order = schema order)."""

@@ -120,6 +120,51 @@ class Model(Block):
         x = self.body(inputs, training=training, testing=testing)
         return self.prediction(x, features=inputs, targets=targets, training=training, testing=testing)
 
+    # -- CUDA-graph runtime (models_b200/graph.py) ---------------------------------------------
+    def embedding_blocks(self) -> List[EmbeddingsBlock]:
+        """Every EmbeddingsBlock of the model (they share one out-of-range index counter)."""
+        found: List[EmbeddingsBlock] = []
+
+        def walk(o, depth=0):
+            if isinstance(o, EmbeddingsBlock):
+                if o not in found:
+                    found.append(o)
+                return
+            if depth > 6 or not isinstance(o, Block):
+                return
+            for v in vars(o).values():
+                if isinstance(v, Block):
+                    walk(v, depth + 1)
+                elif isinstance(v, (list, tuple)):
+                    for e in v:
+                        walk(e, depth + 1)
+
+        walk(self)
+        return found
+
+    def index_error_counter(self, device) -> Optional[torch.Tensor]:
+        blocks = [b for b in self.embedding_blocks() if b.check_indices]
+        if not blocks:
+            return None
+        c = blocks[0].counter(device)
+        for b in blocks[1:]:
+            b.oob_counter = c
+        return c
+
+    def defer_index_check(self, flag: bool) -> None:
+        for b in self.embedding_blocks():
+            b.defer_check = bool(flag)
+
+    def compile(self, example: Union[Dict[str, np.ndarray], "HostBatch"], **call_kwargs) -> "CompiledForward":
+        """Capture this model's forward for `example`'s batch layout into a CUDA graph; the result
+        maps a packed pinned HostBatch to pinned host predictions with one H2D, one graph launch and
+        one D2H (see models_b200/graph.py)."""
+        from .graph import CompiledForward, HostBatch
+
+        if not isinstance(example, HostBatch):
+            example = HostBatch.like(example, self.input_columns())
+        return CompiledForward(self, example, **call_kwargs)
+
     # -- host-buffer entry point (the e2e path of bench.py) -----------------------------------
     def forward_host(self, batch: Dict[str, np.ndarray], stream: Optional[torch.cuda.Stream] = None, **kwargs):
         """Host numpy batch -> pinned staging -> H2D -> forward -> D2H of the predictions."""

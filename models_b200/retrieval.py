@@ -148,6 +148,22 @@ def log_uniform_sampling_probs(max_id: int, min_id: int = 0, max_num_samples: in
 # ------------------------------------------------------------------------------------------------
 # scorer (v1) and contrastive output (v2)
 # ------------------------------------------------------------------------------------------------
+_TARGET_ROWS: Dict[tuple, torch.Tensor] = {}
+
+
+def _target_row(width: int, device) -> torch.Tensor:
+    """[1, 0, 0, ...] (cached per width/device; built without host scalars so it is graph-capturable)."""
+    key = (width, str(device))
+    row = _TARGET_ROWS.get(key)
+    if row is None:
+        row = torch.zeros(width, dtype=torch.float32, device=device)
+        row[:1].fill_(1.0)
+        if len(_TARGET_ROWS) > 16:
+            _TARGET_ROWS.clear()
+        _TARGET_ROWS[key] = row
+    return row
+
+
 def _score(query, pos_item, neg_items, pos_ids, neg_ids, downscore, false_neg_score, temperature,
            pos_prob=None, neg_prob=None) -> Prediction:
     B, N = query.shape[0], neg_items.shape[0]
@@ -157,9 +173,7 @@ def _score(query, pos_item, neg_items, pos_ids, neg_ids, downscore, false_neg_sc
                        neg_prob=neg_prob, temperature=temperature)
     # targets: one-hot on column 0 (retrieval/base.py:413-422) as a broadcast view — the reference
     # materialises a second (B, 1+N) tensor; nothing downstream needs it resident
-    row = torch.zeros(1 + N, dtype=torch.float32, device=query.device)
-    row[0] = 1.0
-    return Prediction(out, row.unsqueeze(0).expand(B, 1 + N), negative_candidate_ids=neg_ids)
+    return Prediction(out, _target_row(1 + N, query.device).unsqueeze(0).expand(B, 1 + N), negative_candidate_ids=neg_ids)
 
 
 class ItemRetrievalScorer(Block):

@@ -181,3 +181,39 @@ def test_forward_host_roundtrip(device):
     a = model.forward_host(feats).numpy()
     b = model(H.device_batch(feats, device)).cpu().numpy()
     assert np.array_equal(a, b)
+
+
+def test_compiled_forward_matches_eager_and_checks_indices(device):
+    """Model.compile: CUDA-graph replay over static buffers, packed pinned host batch in, pinned
+    host predictions out; out-of-range ids are still reported (deferred check after the replay)."""
+    mm.set_seed(31)
+    schema = small_criteo(500)
+    model = mm.DLRMModel(schema, embedding_dim=64, bottom_block=mm.MLPBlock([32, 64]), top_block=mm.MLPBlock([64, 16]))
+    b0, _ = datasets.split_targets(schema, datasets.generate_batch(schema, 700, seed=1, index_law="uniform"))
+    b1, _ = datasets.split_targets(schema, datasets.generate_batch(schema, 700, seed=2, index_law="uniform"))
+    cf = model.compile(b0)
+    assert cf.launches_per_replay >= 5
+    for b in (b0, b1, b0):
+        hb = mm.HostBatch.like(b, model.input_columns())
+        got = cf(hb).clone().numpy()
+        want = model(H.device_batch(b, device)).cpu().numpy()
+        assert np.array_equal(got, want)
+    bad = {k: v.copy() for k, v in b1.items()}
+    bad["C5"][3] = 10 ** 6
+    with pytest.raises(IndexError, match="out of range"):
+        cf(mm.HostBatch.like(bad, model.input_columns()))
+    # the counter was reset: a good batch works again
+    assert np.array_equal(cf(mm.HostBatch.like(b0, model.input_columns())).numpy(), model(H.device_batch(b0, device)).cpu().numpy())
+    with pytest.raises(ValueError, match="layout"):
+        cf(mm.HostBatch.like({k: v[:10] for k, v in b0.items()}, model.input_columns()))
+
+
+def test_compiled_two_tower_training_logits(device):
+    mm.set_seed(32)
+    schema = datasets.movielens_1m_schema()
+    model = mm.TwoTowerModel(schema, query_tower=mm.MLPBlock([64, 32]))
+    b, _ = datasets.split_targets(schema, datasets.generate_batch(schema, 256, seed=5))
+    cf = model.compile(b, training=True)
+    got = cf(mm.HostBatch.like(b, model.input_columns())).clone().numpy()
+    want = model(H.device_batch(b, device), training=True).outputs.cpu().numpy()
+    assert got.shape == (256, 257) and np.array_equal(got, want)
