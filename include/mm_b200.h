@@ -176,7 +176,7 @@ int mm_dense_fp32(const float* x, int64_t B, int K, int64_t x_stride, const floa
  *             (nullable; its padding columns are written as zeros)
  *   x0/xres : fp32 (M, N) operands of the cross epilogue (nullable, both or none)
  * ------------------------------------------------------------------------------------- */
-/* padded operand sizes used by the tensor-core path: Kp = ceil64(K); Np = ceil16(N) (N<=256) or ceil128(N) */
+/* padded operand sizes used by the tensor-core path: Kp = ceil64(K); Np = ceil16(N) (N<=128) or ceil128(N) */
 int mm_tc_padded_k(int K);
 int mm_tc_padded_n(int N);
 int mm_split_rows(const float* x, int64_t M, int K, int64_t x_stride, void* out_split, int Kp,
@@ -205,6 +205,17 @@ int mm_inbatch_scores(const float* q, const float* pos, const float* neg, int64_
                       int D, const void* pos_ids, const void* neg_ids, int id_dtype, int downscore,
                       float false_neg_score, const float* pos_prob, const float* neg_prob,
                       float temperature, float* out, int64_t out_stride, void* stream);
+/* Tensor-core version of the same logits, in two calls:
+ *   mm_positive_scores   : column 0   (row-wise dot, logQ, temperature)
+ *   mm_inbatch_scores_tc : columns 1..N — tcgen05 GEMM Q.N^T on split-bf16 operands
+ *                          (q_split (B, 2*Kp) and neg_split (N, 2*Kp), both from mm_split_rows,
+ *                          Kp = mm_tc_padded_k(D)) with mask / logQ / temperature in the epilogue. */
+int mm_positive_scores(const float* q, const float* pos, int64_t B, int D, const float* pos_prob,
+                       float temperature, float* out, int64_t out_stride, void* stream);
+int mm_inbatch_scores_tc(const void* q_split, const void* neg_split, int64_t B, int64_t N, int D,
+                         const void* pos_ids, const void* neg_ids, int id_dtype, int downscore,
+                         float false_neg_score, const float* neg_prob, float temperature, float* out,
+                         int64_t out_stride, void* stream);
 
 #ifdef __cplusplus
 }

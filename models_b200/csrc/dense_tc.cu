@@ -12,7 +12,7 @@
 // Layout in HBM:  a_split (M, 2*Kp) bf16 = [hi(0..Kp) | lo(0..Kp)]      K-major rows
 //                 w_split (Np, 2*Kp) bf16 = transpose of the Keras kernel, same split
 // Kp = K rounded up to 64 (one 128-byte swizzle row per k-block), Np = N rounded up to 16
-// (<= 256) or to 128 (> 256).  Padding is zero, so it contributes nothing.
+// (<= 128) or to 128 (> 128).  Padding is zero, so it contributes nothing.
 //
 // CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue
 // (TMEM -> registers -> bias/activation/cross -> global).  A pipeline stage holds the four
@@ -29,7 +29,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // bf16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;              // two per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr uint32_t EPI_STAGE_BYTES = 32 * 80 * 2;         // per epilogue warp: max(32x36 fp32, 2 x 32x80 B)
 static_assert(EPI_STAGE_BYTES >= 32 * 36 * 4, "transpose tile too small");
@@ -45,6 +46,14 @@ struct Params {
   long long out_stride;
   __nv_bfloat16* out_split;
   int out_Kp;
+  // scorer epilogue (mm_inbatch_scores_tc): logits[m, n] = mask(pos_id[m] == neg_id[n]) ? fns : acc - log(p_n + 1e-16),
+  // all divided by `temperature`; `bias` then holds the negative sampling probabilities p_n (or null)
+  int score_mode;
+  int id_is64;
+  const void* pos_ids;
+  const void* neg_ids;
+  float fns;
+  float temperature;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -152,8 +161,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * p.stages;       // [2]
   uint64_t* tmem_empty = bars + 2 * p.stages + 2;  // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * p.stages + 6);                       // [Np], zero padded
-  uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(bias_s + p.Np);                         // 4 x EPI_STAGE_BYTES (16-B aligned: Np % 16 == 0)
+  long long* ids_s = reinterpret_cast<long long*>(bars + 2 * p.stages + 6);                // [256] negative ids of the tile (scorer)
+  float* bias_s = reinterpret_cast<float*>(ids_s + 256);                                   // [256] bias of the tile, zero padded
+  uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(bias_s + 256);                         // kEpiWarps x EPI_STAGE_BYTES
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -171,7 +181,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(tmem_full + a), 1);
-      mbar_init(smem_u32(tmem_empty + a), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(tmem_empty + a), kEpiWarps);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -181,7 +191,6 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.Np; i += blockDim.x) bias_s[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -263,11 +272,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
     // TMEM -> registers (thread = one accumulator row, 32 columns per step) -> bias/act/cross ->
     // per-warp shared-memory transpose tile -> coalesced 16-byte global stores (a warp store
     // covers whole 64/128-byte row segments instead of 32 scattered 16-byte pieces).
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which interleaved set of 32-column chunks
     uint8_t* stg = stage_tiles + (size_t)(warp - 2) * EPI_STAGE_BYTES;
     float* stg_f = reinterpret_cast<float*>(stg);
     int acc = 0;
@@ -279,23 +289,47 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const long long m0 = (tile / p.n_tiles_n) * BLOCK_M;
       const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
       const long long row0 = m0 + q * 32;  // first row of this warp
+      // per-tile column data: bias (or -log sampling prob) and, for the scorer, the negative ids
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // previous tile's readers are done
+      for (int i = threadIdx.x - 64; i < p.BN; i += 32 * kEpiWarps) {
+        const int n = n0 + i;
+        float b = 0.0f;
+        if (p.bias && n < p.N) b = p.score_mode ? -logf(p.bias[n] + 1e-16f) : p.bias[n];
+        bias_s[i] = b;
+        if (p.score_mode && p.neg_ids)
+          ids_s[i] = n < p.N ? (p.id_is64 ? reinterpret_cast<const long long*>(p.neg_ids)[n]
+                                          : (long long)reinterpret_cast<const int*>(p.neg_ids)[n])
+                             : -0x7fffffffffffffffll;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      long long my_pid = 0;
+      if (p.score_mode && p.pos_ids && row0 + lane < p.M)
+        my_pid = p.id_is64 ? reinterpret_cast<const long long*>(p.pos_ids)[row0 + lane]
+                           : (long long)reinterpret_cast<const int*>(p.pos_ids)[row0 + lane];
       mbar_wait(smem_u32(tmem_full + acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      const int n_chunks = (p.BN + 31) >> 5;
+      if (half >= n_chunks) {  // nothing to read for this warp (BN <= 32): release the accumulator right away
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tmem_empty + acc));
+      }
+      for (int ch = half; ch < n_chunks; ch += 2) {
+        const int c0 = ch << 5;
         uint32_t r[32];
         const int ncols = min(32, p.BN - c0);  // BN is a multiple of 16
         if (ncols == 32) tmem_ld_32x32b_x32(t_row + c0, r);
         else tmem_ld_32x32b_x16(t_row + c0, r);
         tmem_ld_wait();
-        if (c0 + 32 >= p.BN) {  // last TMEM read of this accumulator: hand it back to the MMA warp
+        if (ch + 2 >= n_chunks) {  // this warp's last TMEM read of the accumulator: hand it back
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(tmem_empty + acc));
         }
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[n0 + c0 + j];  // bias_s is zero padded
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c0 + j];  // bias_s is zero padded
         if (p.x0) {
           // cross epilogue: x0 * (xW + b) + x ; x0 / x tiles come in through the transpose tile (coalesced)
 #pragma unroll 1
@@ -333,6 +367,17 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
+        } else if (p.score_mode) {
+          // false-negative mask (utils/tf_utils.py:140-150) then LogitsTemperatureScaler (x / T)
+          if (p.pos_ids != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ids_s[c0 + j] == my_pid) v[j] = p.fns;
+          }
+          if (p.temperature != 1.0f) {  // x / 1 == x exactly: skip the IEEE division in the common case
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdiv_rn(v[j], p.temperature);
+          }
         } else if (p.act == MM_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -353,21 +398,30 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(stg_f + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           __syncwarp();
+          if (vec_f32) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + (lane >> 3), cv = (lane & 7) * 4;
-            const long long grow = row0 + rr;
-            const int n = n0 + c0 + cv;
-            if (grow < p.M && cv < ncols && n < p.N) {
-              const float4 t = *reinterpret_cast<const float4*>(stg_f + rr * 36 + cv);
-              float* g = p.out_f32 + grow * p.out_stride + n;
-              if (vec_f32 && n + 3 < p.N) *reinterpret_cast<float4*>(g) = t;
-              else {
-                g[0] = t.x;
-                if (n + 1 < p.N) g[1] = t.y;
-                if (n + 2 < p.N) g[2] = t.z;
-                if (n + 3 < p.N) g[3] = t.w;
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), cv = (lane & 7) * 4;
+              const long long grow = row0 + rr;
+              const int n = n0 + c0 + cv;
+              if (grow < p.M && cv < ncols && n < p.N) {
+                const float4 t = *reinterpret_cast<const float4*>(stg_f + rr * 36 + cv);
+                float* g = p.out_f32 + grow * p.out_stride + n;
+                if (n + 3 < p.N) *reinterpret_cast<float4*>(g) = t;
+                else {
+                  g[0] = t.x;
+                  if (n + 1 < p.N) g[1] = t.y;
+                  if (n + 2 < p.N) g[2] = t.z;
+                }
               }
+            }
+          } else {
+            // rows only 4-byte aligned (e.g. the (B, 1+N) logits at column 1): a warp store covers 32
+            // consecutive floats of one row
+            const int n = n0 + c0 + lane;
+            if (lane < ncols && n < p.N) {
+              const int rmax = (int)min((long long)32, p.M - row0);
+              for (int rr = 0; rr < rmax; ++rr) p.out_f32[(row0 + rr) * p.out_stride + n] = stg_f[rr * 36 + lane];
             }
           }
         }
@@ -484,7 +538,7 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 extern "C" {
 
 int mm_tc_padded_k(int K) { return ((K + 63) / 64) * 64; }
-int mm_tc_padded_n(int N) { return N <= 256 ? ((N + 15) / 16) * 16 : ((N + 127) / 128) * 128; }
+int mm_tc_padded_n(int N) { return N <= 128 ? ((N + 15) / 16) * 16 : ((N + 127) / 128) * 128; }
 
 int mm_split_rows(const float* x, int64_t M, int K, int64_t x_stride, void* out_split, int Kp, void* stream) {
   MM_REQUIRE(x && out_split && M >= 0 && K > 0 && x_stride >= K, MM_ERR_ARG, "mm_split_rows: null pointer or bad K/stride");
@@ -513,10 +567,11 @@ int mm_split_weights(const float* W, int K, int N, void* w_split, int Kp, int Np
   return mm::check_launch("mm_split_weights");
 }
 
-int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_split, int N, int Np,
-                const float* bias, int act, int passes, const float* x0, const float* xres,
-                int64_t x_stride, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
-                void* stream) {
+static int dense_tc_launch(const void* a_split, int64_t M, int K, int Kp, const void* w_split, int N, int Np,
+                           const float* bias, int act, int passes, const float* x0, const float* xres,
+                           int64_t x_stride, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
+                           int score_mode, const void* pos_ids, const void* neg_ids, int id_is64, float fns,
+                           float temperature, int64_t b_rows, void* stream) {
   using namespace mm::tc;
   MM_REQUIRE(a_split && w_split && M >= 0 && K > 0 && N > 0, MM_ERR_ARG, "mm_dense_tc: null operand or non-positive K/N");
   MM_REQUIRE(Kp == mm_tc_padded_k(K) && Np == mm_tc_padded_n(N), MM_ERR_ARG,
@@ -524,6 +579,7 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
   MM_REQUIRE(passes == 1 || passes == 3, MM_ERR_ARG, "mm_dense_tc: passes must be 1 (bf16) or 3 (split-bf16)");
   MM_REQUIRE(act >= MM_ACT_LINEAR && act <= MM_ACT_GELU, MM_ERR_ARG, "mm_dense_tc: unknown activation %d", act);
   MM_REQUIRE((x0 == nullptr) == (xres == nullptr), MM_ERR_ARG, "mm_dense_tc: x0 and xres go together");
+  MM_REQUIRE(!score_mode || (!x0 && !out_split), MM_ERR_ARG, "mm_dense_tc: scorer epilogue excludes cross / split outputs");
   MM_REQUIRE(!x0 || x_stride >= N, MM_ERR_ARG, "mm_dense_tc: x_stride < N for the cross epilogue");
   MM_REQUIRE(out_f32 || out_split, MM_ERR_ARG, "mm_dense_tc: no output requested");
   MM_REQUIRE(!out_f32 || out_stride >= N, MM_ERR_ARG, "mm_dense_tc: out_stride < N");
@@ -539,7 +595,7 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
   p.N = N;
   p.Np = Np;
   p.Kp = Kp;
-  p.BN = Np <= 256 ? Np : 128;
+  p.BN = Np <= 128 ? Np : 128;
   p.n_tiles_n = Np / p.BN;
   p.passes = passes;
   p.act = act;
@@ -551,8 +607,14 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
   p.out_stride = out_stride;
   p.out_split = (__nv_bfloat16*)out_split;
   p.out_Kp = out_Kp;
+  p.score_mode = score_mode;
+  p.id_is64 = id_is64;
+  p.pos_ids = pos_ids;
+  p.neg_ids = neg_ids;
+  p.fns = fns;
+  p.temperature = temperature;
   const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.BN * BLOCK_K * 2;
-  const size_t epi_bytes = (size_t)Np * sizeof(float) + 4 * (size_t)EPI_STAGE_BYTES;
+  const size_t epi_bytes = 256 * sizeof(long long) + 256 * sizeof(float) + (size_t)kEpiWarps * EPI_STAGE_BYTES;
   int stages = (int)((224 * 1024 - 2048 - epi_bytes) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages > Kp / BLOCK_K * 2) stages = Kp / BLOCK_K * 2 > 2 ? Kp / BLOCK_K * 2 : 2;
@@ -563,7 +625,7 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a_split, (uint64_t)M, (uint64_t)2 * Kp, BLOCK_M);
   if (rc) return rc;
-  rc = make_map(&tmB, w_split, (uint64_t)Np, (uint64_t)2 * Kp, (uint32_t)p.BN);
+  rc = make_map(&tmB, w_split, (uint64_t)b_rows, (uint64_t)2 * Kp, (uint32_t)p.BN);  // rows past b_rows read as zeros
   if (rc) return rc;
 
   static size_t smem_set = 0;  // raise the dynamic-smem limit once (monotone), not per launch
@@ -581,5 +643,30 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
   dense_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return mm::check_launch("mm_dense_tc");
 }
+
+int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_split, int N, int Np,
+                const float* bias, int act, int passes, const float* x0, const float* xres,
+                int64_t x_stride, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
+                void* stream) {
+  return dense_tc_launch(a_split, M, K, Kp, w_split, N, Np, bias, act, passes, x0, xres, x_stride, out_f32, out_stride,
+                         out_split, out_Kp, 0, nullptr, nullptr, 0, 0.0f, 1.0f, Np, stream);
+}
+
+int mm_inbatch_scores_tc(const void* q_split, const void* neg_split, int64_t B, int64_t N, int D,
+                         const void* pos_ids, const void* neg_ids, int id_dtype, int downscore,
+                         float false_neg_score, const float* neg_prob, float temperature, float* out,
+                         int64_t out_stride, void* stream) {
+  MM_REQUIRE(q_split && neg_split && out && B >= 0 && N > 0 && D > 0, MM_ERR_ARG, "mm_inbatch_scores_tc: null pointer or bad size");
+  MM_REQUIRE(N < (1ll << 31) && out_stride >= N + 1, MM_ERR_ARG, "mm_inbatch_scores_tc: N too large or out_stride < 1+N");
+  MM_REQUIRE(!downscore || (pos_ids && neg_ids), MM_ERR_ARG, "mm_inbatch_scores_tc: downscore needs positive and negative ids");
+  MM_REQUIRE(id_dtype == MM_I32 || id_dtype == MM_I64, MM_ERR_ARG, "mm_inbatch_scores_tc: bad id dtype");
+  MM_REQUIRE(temperature != 0.0f, MM_ERR_ARG, "mm_inbatch_scores_tc: temperature must be non-zero");
+  // negatives play the role of the weight matrix: (N, D) K-major rows; columns 1.. of `out`
+  return dense_tc_launch(q_split, B, D, mm_tc_padded_k(D), neg_split, (int)N, mm_tc_padded_n((int)N), neg_prob,
+                         MM_ACT_LINEAR, 3, nullptr, nullptr, 0, out + 1, out_stride, nullptr, 0, 1,
+                         downscore ? pos_ids : nullptr, downscore ? neg_ids : nullptr, id_dtype == MM_I64,
+                         false_neg_score, temperature, N, stream);
+}
+
 
 }  // extern "C"

@@ -108,6 +108,20 @@ int mm_rowwise_dot(const float* q, const float* items, int64_t B, int D, int64_t
   return mm::check_launch("mm_rowwise_dot");
 }
 
+int mm_positive_scores(const float* q, const float* pos, int64_t B, int D, const float* pos_prob,
+                       float temperature, float* out, int64_t out_stride, void* stream) {
+  MM_REQUIRE(q && pos && out && B >= 0 && D > 0 && out_stride >= 1, MM_ERR_ARG, "mm_positive_scores: null pointer or D<=0");
+  MM_REQUIRE(temperature != 0.0f, MM_ERR_ARG, "mm_positive_scores: temperature must be non-zero");
+  if (B == 0) return MM_OK;
+  const int threads = 256;
+  long long blocks = (B * 32 + threads - 1) / threads;
+  const long long cap = (long long)mm::sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  mm::rowwise_dot_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(q, pos, B, D, D, D, pos_prob, temperature,
+                                                                                out, out_stride);
+  return mm::check_launch("mm_positive_scores");
+}
+
 int mm_inbatch_scores(const float* q, const float* pos, const float* neg, int64_t B, int64_t N,
                       int D, const void* pos_ids, const void* neg_ids, int id_dtype, int downscore,
                       float false_neg_score, const float* pos_prob, const float* neg_prob,

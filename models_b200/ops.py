@@ -213,11 +213,16 @@ def rowwise_dot(q: torch.Tensor, items: torch.Tensor, out: torch.Tensor) -> torc
 
 def inbatch_scores(q, pos, neg, out, pos_ids=None, neg_ids=None, downscore=True,
                    false_neg_score: float = -655.04, pos_prob=None, neg_prob=None,
-                   temperature: float = 1.0) -> torch.Tensor:
-    for n_, t_ in (("q", q), ("pos", pos), ("neg", neg), ("out", out)):
+                   temperature: float = 1.0, tensor_cores: bool = True) -> torch.Tensor:
+    """out (B, 1+N) = [q.pos | masked(q @ neg^T)] / T  (include/mm_b200.h: mm_inbatch_scores[_tc]).
+    tensor_cores=True: tcgen05 split-bf16 GEMM (fp32-grade); False: exact fp32 CUDA-core kernel."""
+    for n_, t_ in (("q", q), ("pos", pos), ("neg", neg)):
         _dev(t_, n_, torch.float32)
         if not t_.is_contiguous():
             raise ValueError(f"{n_} must be contiguous")
+    _dev(out, "out", torch.float32)
+    if out.dim() != 2 or out.stride(1) != 1 or out.shape[1] != neg.shape[0] + 1:
+        raise ValueError("out must be (B, 1+N) with unit inner stride")
     B, D = q.shape
     N = neg.shape[0]
     id_dt = MM_I64
@@ -228,6 +233,17 @@ def inbatch_scores(q, pos, neg, out, pos_ids=None, neg_ids=None, downscore=True,
         # reference: positive ids are cast to the negative ids' dtype (utils/tf_utils.py:136)
         pos_ids = pos_ids.reshape(-1).to(neg_ids.dtype).contiguous()
         id_dt = _idx_dtype(neg_ids, "neg_ids")
+    if tensor_cores and N > 0 and B > 0:
+        _cabi.check(_lib().mm_positive_scores(q.data_ptr(), pos.data_ptr(), B, D, _ptr(pos_prob), float(temperature),
+                                              out.data_ptr(), out.stride(0), _stream()), "mm_positive_scores")
+        qs = split_rows(q)
+        ns = qs if neg.data_ptr() == q.data_ptr() else split_rows(neg)
+        _cabi.check(
+            _lib().mm_inbatch_scores_tc(qs.data_ptr(), ns.data_ptr(), B, N, D, _ptr(pos_ids), _ptr(neg_ids), id_dt,
+                                        int(bool(downscore)), float(false_neg_score), _ptr(neg_prob),
+                                        float(temperature), out.data_ptr(), out.stride(0), _stream()),
+            "mm_inbatch_scores_tc")
+        return out
     _cabi.check(
         _lib().mm_inbatch_scores(q.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, N, D, _ptr(pos_ids),
                                  _ptr(neg_ids), id_dt, int(bool(downscore)), float(false_neg_score),

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .blocks import MLP
+from .blocks import MLP, dense_engine
 from .core import Block, Prediction, TabularData, unique_name
 from .inputs import EmbeddingOptions, InputBlock
 from .schema import Schema, Tags
@@ -167,10 +167,14 @@ def _target_row(width: int, device) -> torch.Tensor:
 def _score(query, pos_item, neg_items, pos_ids, neg_ids, downscore, false_neg_score, temperature,
            pos_prob=None, neg_prob=None) -> Prediction:
     B, N = query.shape[0], neg_items.shape[0]
-    out = torch.empty((B, 1 + N), dtype=torch.float32, device=query.device)
+    # (B, 1+N) logits as a view into a (B, 4+Nr) buffer starting at physical column 3: the negatives
+    # (logical columns 1..N) then start 16-byte aligned in every row, so the GEMM epilogue can use
+    # 128-bit stores; Nr = N rounded up to 4 keeps the row stride a multiple of 16 bytes
+    Nr = (N + 3) // 4 * 4
+    out = torch.empty((B, 4 + Nr), dtype=torch.float32, device=query.device)[:, 3:4 + N]
     ops.inbatch_scores(query.contiguous(), pos_item.contiguous(), neg_items.contiguous(), out, pos_ids=pos_ids,
                        neg_ids=neg_ids, downscore=downscore, false_neg_score=false_neg_score, pos_prob=pos_prob,
-                       neg_prob=neg_prob, temperature=temperature)
+                       neg_prob=neg_prob, temperature=temperature, tensor_cores=dense_engine() != "fp32")
     # targets: one-hot on column 0 (retrieval/base.py:413-422) as a broadcast view — the reference
     # materialises a second (B, 1+N) tensor; nothing downstream needs it resident
     return Prediction(out, _target_row(1 + N, query.device).unsqueeze(0).expand(B, 1 + N), negative_candidate_ids=neg_ids)

@@ -161,7 +161,7 @@ def test_contrastive_output_v2(device):
     assert tuple(inf.shape) == (B, 1)
     pred = out({"query": dq, "candidate": dc}, candidate_ids=dids, training=True)
     ref, _ = oracle.contrastive_logits(q, c, c, ids, ids, True, oracle.MIN_FLOAT)
-    np.testing.assert_allclose(pred.outputs.cpu().numpy(), ref, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(pred.outputs.cpu().numpy(), ref, rtol=2e-4, atol=5e-4)
     # logQ correction with the log-uniform sampling probabilities (popularity.py:141-165)
     probs = mm.log_uniform_sampling_probs(max_id=39, min_id=0, max_num_samples=B, unique=True)
     assert np.allclose(probs, oracle.log_uniform_probs(39, 0, True, B))
@@ -169,7 +169,7 @@ def test_contrastive_output_v2(device):
     pred_q = out_q({"query": dq, "candidate": dc}, candidate_ids=dids, training=True,
                    sampling_probs=torch.from_numpy(probs).to(device))
     ref_q, _ = oracle.contrastive_logits(q, c, c, ids, ids, True, oracle.MIN_FLOAT, pos_prob=probs[ids], neg_prob=probs[ids])
-    np.testing.assert_allclose(pred_q.outputs.cpu().numpy(), ref_q, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(pred_q.outputs.cpu().numpy(), ref_q, rtol=2e-4, atol=5e-4)
 
 
 def test_forward_host_roundtrip(device):

@@ -113,9 +113,11 @@ def main():
         q = torch.randn((Bq, Dq), device=dev)
         it = torch.randn((Bq, Dq), device=dev)
         ids = torch.randint(0, 10_000_000, (Bq,), device=dev, dtype=torch.int64)
-        o = torch.empty((Bq, Bq + 1), device=dev)
-        m, mn = timeit(lambda i: ops.inbatch_scores(q, it, it, o, pos_ids=ids, neg_ids=ids), max(5, args.iters // 2))
-        report("mm_inbatch_scores 16384x16384 D=64", m, mn, bytes_=Bq * (Bq + 1) * 4, flops=2.0 * Bq * Bq * Dq)
+        o = torch.empty((Bq, Bq + 4), device=dev)[:, 3:]  # negatives 16-B aligned (as retrieval._score allocates)
+        for tc in (False, True):
+            m, mn = timeit(lambda i: ops.inbatch_scores(q, it, it, o, pos_ids=ids, neg_ids=ids, tensor_cores=tc), max(5, args.iters // 2))
+            report(f"mm_inbatch_scores 16384x16384 D=64 ({'tcgen05 split-bf16 incl. operand split' if tc else 'fp32 SIMT'})", m, mn,
+                   bytes_=Bq * (Bq + 1) * 4, flops=2.0 * Bq * Bq * Dq)
 
 
 if __name__ == "__main__":
