@@ -217,6 +217,29 @@ int mm_inbatch_scores_tc(const void* q_split, const void* neg_split, int64_t B, 
                          float false_neg_score, const float* neg_prob, float temperature, float* out,
                          int64_t out_stride, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K13  Row-sharded tables over the GPUs of one NVLink domain: row r of every table lives on
+ * rank r % world at local row r / world (the reference's counterpart is SOK's distributed
+ * variable, distributed/embedding.py:75-84,144-148).  Owner-computes push = gather + all-to-all
+ * in ONE kernel: each rank scans the GLOBAL index list (B_global = world * B_local samples,
+ * replicated by an all-gather of 4 B/feature/sample) and, for the rows it owns, copies the row
+ * from its local shard straight into the destination rank's (B_local, out_stride) stack through
+ * peer-mapped memory (dst_ptrs_host[r] = that buffer as mapped in this process; NVLink stores).
+ *   tables_host[t].weights = local shard (local_rows, D);  .rows = GLOBAL row count;
+ *   .indices = global (B_global,) index array of feature t;  .out_col = slot*D.
+ * Out-of-range ids write a zero row (by the rank idx mod world) and bump *oob_count.
+ * A cross-rank barrier must follow before the stacks are read (torch.distributed / symmetric
+ * memory barrier on the same stream).
+ * mm_init_uniform_hash_rows initialises a shard so that local row l equals global row
+ * row0 + l*row_step of the table mm_init_uniform_hash would produce.
+ * ------------------------------------------------------------------------------------- */
+int mm_shard_gather_push(const mm_gather_table* tables_host, int n_tables, int idx_dtype,
+                         int64_t B_global, int64_t B_local, int D, int rank, int world,
+                         void* const* dst_ptrs_host, int64_t out_stride, int32_t* oob_count,
+                         void* stream);
+int mm_init_uniform_hash_rows(float* w, int64_t local_rows, int D, uint64_t seed, float lo, float hi,
+                              int64_t row0, int64_t row_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ from .retrieval import (ContrastiveOutput, InBatchSampler, InBatchSamplerV2, Ite
 from .models import (BinaryClassificationTask, BinaryOutput, DCNModel, DLRMModel, Model,  # noqa: F401
                      RetrievalModel, TwoTowerModel)
 from .graph import CompiledForward, HostBatch  # noqa: F401
+from .sharded import ShardedEmbeddings, shard_model  # noqa: F401
 from . import datasets, ops  # noqa: F401
 
 __version__ = "0.1.0"

@@ -387,6 +387,7 @@ class DLRM(Block):
         self.top_block = top_block
         self.embedding_dim = embedding_dim
         self.fused = fused
+        self.sharded = None  # models_b200.sharded.ShardedEmbeddings when the tables are row-sharded
 
     # stack order = sorted over {feature names} U {"bottom_block"} (core/aggregation.py:104-108)
     def slots(self) -> Dict[str, int]:
@@ -396,7 +397,10 @@ class DLRM(Block):
         return {k: i for i, k in enumerate(sorted(keys))}
 
     def build(self, device=None):
-        self.embeddings.build(device)
+        if self.sharded is not None:
+            self.sharded.build(device)  # local shards only: full tables are never materialised
+        else:
+            self.embeddings.build(device)
         if self.bottom_block is not None:
             self.bottom_block.build_from_width(len(self.continuous.features), device)
         if self.top_block is not None:
@@ -447,6 +451,15 @@ class DLRM(Block):
         from .core import get_feature
         from .inputs import _as_index, _raise_on_oob
 
+        if self.sharded is not None:
+            # row-sharded tables: index all-gather + owner-computes NVLink push + barrier rebuild the
+            # (B,F,D) stack of the local samples; the interaction then reads it like the staged path
+            oob = emb.counter(dev)
+            stack = self.sharded.lookup_stack(inputs, slots, F, oob)
+            emb.finish_check(oob)
+            if bottom is not None:
+                ops.concat_columns([bottom], stack, [slots["bottom_block"] * D])
+            return ops.dot_interaction(stack.view(B, F, D), out, prefix=bottom if with_prefix else None)
         all_onehot = all(emb.feature_to_table[f].lookup_kind(get_feature(inputs, f)) == "onehot" for f in feats)
         if self.fused and all_onehot and with_prefix == (bottom is not None):
             oob = emb.counter(dev)

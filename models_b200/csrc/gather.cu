@@ -164,6 +164,88 @@ __global__ void gather_seq_kernel(const float* __restrict__ w, long long rows, i
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row-sharded tables over `world` GPUs of one NVLink domain (row r lives on rank r % world at local
+// row r / world).  Owner-computes push: every rank scans the GLOBAL index list (replicated by an
+// all-gather, 104 B/sample), and for the rows it owns copies the 256-byte row from its local shard
+// straight into the destination rank's (B_local, F, D) stack through peer-mapped memory — the
+// gather and the all-to-all are one kernel, no pack/unpack buffers, no size exchange.
+// Reference counterpart: sok.lookup_sparse on a distributed sok.Variable
+// (merlin/models/tf/distributed/embedding.py:75-84,144-148).
+// ---------------------------------------------------------------------------------------------
+struct ShardDst {
+  float* ptr[16];
+};
+
+template <typename IdxT, int VPR>
+__global__ void __launch_bounds__(256)
+shard_gather_push_kernel(const __grid_constant__ GatherParams p, const __grid_constant__ ShardDst dst, long long B_global,
+                         long long B_local, int rank, int world, long long out_stride, int* __restrict__ oob_count) {
+  constexpr int RPS = 32 / VPR;  // rows copied per warp step
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / VPR, v = lane % VPR;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long chunks = (B_global + 31) >> 5;
+  const long long tasks = chunks * p.n_tables;
+  for (long long task = warp0; task < tasks; task += n_warps) {
+    const int t = (int)(task % p.n_tables);
+    const long long g0 = (task / p.n_tables) << 5;
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(p.t[t].weights);
+    const long long rows = p.t[t].rows;  // GLOBAL row count of the table
+    const int col4 = p.t[t].out_col >> 2;
+    long long local = -2;  // -2: not mine, -1: mine but out of range (write zeros), >= 0: local row
+    if (g0 + lane < B_global) {
+      const long long idx = (long long)reinterpret_cast<const IdxT*>(p.t[t].indices)[g0 + lane];
+      const long long owner = ((idx % world) + world) % world;
+      if (owner == rank) {
+        if (idx >= 0 && idx < rows) local = idx / world;
+        else {
+          local = -1;
+          if (oob_count) atomicAdd(oob_count, 1);
+        }
+      }
+    }
+    unsigned mine = __ballot_sync(0xffffffffu, local != -2);
+    while (mine) {  // RPS owned samples per step
+      int src_lane = -1;
+      unsigned m = mine;
+      for (int k = 0; k <= sub && m; ++k) {
+        src_lane = __ffs(m) - 1;
+        m &= m - 1;
+        if (k < sub) src_lane = -1;
+      }
+      // drop the RPS lowest set bits
+      for (int k = 0; k < RPS && mine; ++k) mine &= mine - 1;
+      const long long l = __shfl_sync(0xffffffffu, local, src_lane < 0 ? 0 : src_lane);
+      if (src_lane >= 0) {
+        const long long g = g0 + src_lane;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l >= 0) val = ldg_stream(w4 + l * VPR + v);
+        float4* o = reinterpret_cast<float4*>(dst.ptr[g / B_local]) + (g % B_local) * (out_stride >> 2) + col4 + v;
+        *o = val;  // peer (NVLink) or local store
+      }
+    }
+  }
+}
+
+// deterministic initialiser of a row shard: local row l holds global row row0 + l*row_step
+__global__ void init_uniform_hash_rows_kernel(float* __restrict__ w, long long local_rows, int D, unsigned long long seed,
+                                              float lo, float span, long long row0, long long row_step) {
+  const long long n = local_rows * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long l = i / D, d = i % D;
+    const unsigned long long e = (unsigned long long)((row0 + l * row_step) * D + d);
+    unsigned long long z = seed + (e + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    const float u = (float)(unsigned int)(z >> 40) * (1.0f / 16777216.0f);
+    w[i] = __fadd_rn(lo, __fmul_rn(span, u));
+  }
+}
+
 static int validate_tables(const mm_gather_table* tb, int n, const char* who) {
   MM_REQUIRE(tb != nullptr && n > 0 && n <= MM_MAX_TABLES, MM_ERR_ARG,
              "%s: n_tables=%d outside 1..%d or null table list", who, n, MM_MAX_TABLES);
@@ -294,6 +376,73 @@ int mm_gather_seq(const float* weights, int64_t rows, int dim, const void* ids, 
     mm::gather_seq_kernel<int64_t><<<(unsigned)blocks, threads, 0, st>>>(
         weights, rows, dim, (const int64_t*)ids, B, L, combiner, out, out_stride, out_col, oob_count);
   return mm::check_launch("mm_gather_seq");
+}
+
+
+int mm_shard_gather_push(const mm_gather_table* tables_host, int n_tables, int idx_dtype, int64_t B_global,
+                         int64_t B_local, int D, int rank, int world, void* const* dst_ptrs_host,
+                         int64_t out_stride, int32_t* oob_count, void* stream) {
+  int rc = mm::validate_tables(tables_host, n_tables, "mm_shard_gather_push");
+  if (rc) return rc;
+  MM_REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world && dst_ptrs_host, MM_ERR_ARG,
+             "mm_shard_gather_push: world must be 1..16, 0 <= rank < world, dst_ptrs non-null");
+  MM_REQUIRE(B_local > 0 && B_global == B_local * world, MM_ERR_ARG, "mm_shard_gather_push: B_global must equal B_local * world");
+  MM_REQUIRE(idx_dtype == MM_I32 || idx_dtype == MM_I64, MM_ERR_ARG, "mm_shard_gather_push: bad idx_dtype");
+  const int vpr = D / 4;
+  MM_REQUIRE(D % 4 == 0 && vpr >= 1 && vpr <= 32 && (vpr & (vpr - 1)) == 0 && out_stride % 4 == 0, MM_ERR_UNSUPPORTED,
+             "mm_shard_gather_push: D/4 must be a power of two <= 32 and out_stride a multiple of 4");
+  mm::GatherParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_tables = n_tables;
+  for (int t = 0; t < n_tables; ++t) {
+    MM_REQUIRE(tables_host[t].dim == D && tables_host[t].out_col % 4 == 0 && (int64_t)tables_host[t].out_col + D <= out_stride &&
+                   ((uintptr_t)tables_host[t].weights % 16) == 0,
+               MM_ERR_ARG, "mm_shard_gather_push: table %d: dim != D, bad out_col or misaligned shard", t);
+    p.t[t] = tables_host[t];
+  }
+  mm::ShardDst dst;
+  memset(&dst, 0, sizeof(dst));
+  for (int r = 0; r < world; ++r) {
+    MM_REQUIRE(dst_ptrs_host[r] && ((uintptr_t)dst_ptrs_host[r] % 16) == 0, MM_ERR_ARG,
+               "mm_shard_gather_push: destination pointer of rank %d is null or misaligned", r);
+    dst.ptr[r] = (float*)dst_ptrs_host[r];
+  }
+  const int threads = 256;
+  long long warps = ((B_global + 31) / 32) * n_tables;
+  long long blocks = (warps * 32 + threads - 1) / threads;
+  const long long cap = (long long)mm::sm_count() * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MM_PUSH(IT, V)                                                                                              \
+  mm::shard_gather_push_kernel<IT, V><<<(unsigned)blocks, threads, 0, st>>>(p, dst, B_global, B_local, rank, world, \
+                                                                           out_stride, oob_count)
+#define MM_PUSH_V(IT)        \
+  switch (vpr) {             \
+    case 1: MM_PUSH(IT, 1); break;   \
+    case 2: MM_PUSH(IT, 2); break;   \
+    case 4: MM_PUSH(IT, 4); break;   \
+    case 8: MM_PUSH(IT, 8); break;   \
+    case 16: MM_PUSH(IT, 16); break; \
+    default: MM_PUSH(IT, 32); break; \
+  }
+  if (idx_dtype == MM_I32) { MM_PUSH_V(int32_t) } else { MM_PUSH_V(int64_t) }
+#undef MM_PUSH_V
+#undef MM_PUSH
+  return mm::check_launch("mm_shard_gather_push");
+}
+
+int mm_init_uniform_hash_rows(float* w, int64_t local_rows, int D, uint64_t seed, float lo, float hi,
+                              int64_t row0, int64_t row_step, void* stream) {
+  MM_REQUIRE(w && local_rows >= 0 && D > 0 && row0 >= 0 && row_step >= 1, MM_ERR_ARG,
+             "mm_init_uniform_hash_rows: null buffer or bad rows / D / row0 / row_step");
+  if (local_rows == 0) return MM_OK;
+  const long long n = local_rows * D;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)mm::sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  mm::init_uniform_hash_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      w, local_rows, D, (unsigned long long)seed, lo, hi - lo, row0, row_step);
+  return mm::check_launch("mm_init_uniform_hash_rows");
 }
 
 }  // extern "C"
