@@ -19,7 +19,7 @@ from .retrieval import (ContrastiveOutput, InBatchSampler, InBatchSamplerV2, Ite
                         ItemRetrievalTask, L2Norm, TwoTowerBlock, log_uniform_sampling_probs)
 from .models import (BinaryClassificationTask, BinaryOutput, DCNModel, DLRMModel, Model,  # noqa: F401
                      RetrievalModel, TwoTowerModel)
-from .graph import CompiledForward, HostBatch  # noqa: F401
+from .graph import CompiledForward, HostBatch, PipelinedForward  # noqa: F401
 from .sharded import ShardedEmbeddings, shard_model  # noqa: F401
 from . import datasets, ops  # noqa: F401
 

@@ -11,8 +11,8 @@ import torch
 
 from . import ops
 from ._cabi import ACTIVATIONS
-from .core import (Block, InitializerType, SequentialBlock, TabularData, batch_size_of, concat_sorted,
-                   create_variable, default_device, unique_name)
+from .core import (Block, InitializerType, SequentialBlock, TabularData, batch_size_of, buffer_namespace,
+                   concat_sorted, create_variable, default_device, unique_name)
 from .inputs import (ContinuousFeatures, EmbeddingOptions, Embeddings, EmbeddingsBlock, InputBlock, InputBlockV2,
                      infer_embedding_dim)
 from .schema import Schema, Tags
@@ -93,7 +93,7 @@ class _Dense(Block):
         self.bias: Optional[torch.Tensor] = None
         self.input_dim: Optional[int] = None
         self._w_split: Optional[torch.Tensor] = None
-        self._split_bufs: Dict[int, torch.Tensor] = {}
+        self._split_bufs: Dict[tuple, torch.Tensor] = {}
 
     def split_kernel(self) -> torch.Tensor:
         """(Np, 2*Kp) split-bf16 K-major copy of the kernel for the tensor-core path (built once)."""
@@ -104,12 +104,13 @@ class _Dense(Block):
     def split_buffer(self, B: int, device) -> torch.Tensor:
         """Cached (B, 2*Kp(units)) bf16 buffer receiving this layer's output as the next layer's
         operand; its padding columns are zeroed once and never written again."""
-        buf = self._split_bufs.get(B)
+        key = (B, buffer_namespace())
+        buf = self._split_bufs.get(key)
         if buf is None or buf.device != device:
-            if len(self._split_bufs) > 4:
-                self._split_bufs.clear()
+            if len(self._split_bufs) > 8:
+                self._split_bufs = {k: v for k, v in self._split_bufs.items() if k[1] != 0}  # keep graph-owned buffers
             buf = torch.zeros((B, 2 * ops.tc_padded_k(self.units)), dtype=torch.bfloat16, device=device)
-            self._split_bufs[B] = buf
+            self._split_bufs[key] = buf
         return buf
 
     def build(self, input_dim: Optional[int] = None, device=None) -> "_Dense":

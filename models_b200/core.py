@@ -37,6 +37,26 @@ def unique_name(base: str) -> str:
     return base if i == 0 else f"{base}_{i}"
 
 
+# Cached scratch buffers (e.g. the split-bf16 operand buffers of the dense layers) are keyed by a
+# namespace so that two CUDA graphs of the same model that may run concurrently never share scratch.
+_BUFFER_NS = [0]
+_NEXT_NS = itertools.count(1)
+
+
+def buffer_namespace() -> int:
+    return _BUFFER_NS[0]
+
+
+def new_buffer_namespace() -> int:
+    return next(_NEXT_NS)
+
+
+def set_buffer_namespace(ns: int) -> int:
+    old = _BUFFER_NS[0]
+    _BUFFER_NS[0] = int(ns)
+    return old
+
+
 def default_device() -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError(

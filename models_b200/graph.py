@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from .core import Prediction, default_device
+from .core import Prediction, default_device, new_buffer_namespace, set_buffer_namespace
 
 _ALIGN = 256
 
@@ -76,6 +76,8 @@ class CompiledForward:
         self.dev_buffer.copy_(example.buffer, non_blocking=True)
         self._oob = model.index_error_counter(self.device)
         model.defer_index_check(True)
+        self.namespace = new_buffer_namespace()  # private scratch buffers: graphs may run concurrently
+        old_ns = set_buffer_namespace(self.namespace)
         try:
             # warm-up on a side stream (builds weights, split kernels, zeroed operand buffers, smem
             # attributes) — nothing lazy may remain for the capture
@@ -96,6 +98,7 @@ class CompiledForward:
             self.output = out
         finally:
             model.defer_index_check(False)
+            set_buffer_namespace(old_ns)
         self.output_host = torch.empty(self.output.shape, dtype=self.output.dtype, pin_memory=True)
         self._oob_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
         self.check_indices(sync=True)
@@ -139,3 +142,44 @@ class CompiledForward:
         torch.cuda.current_stream().synchronize()
         self.check_indices()
         return self.output_host
+
+
+class PipelinedForward:
+    """`depth` CompiledForward instances on their own streams: while one batch computes, the next
+    one's pinned H2D copy is already in flight (PCIe and the SMs overlap).  submit() returns a
+    ticket, result(ticket) waits for that batch's pinned host predictions."""
+
+    def __init__(self, model, example: HostBatch, depth: int = 2, **call_kwargs):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.slots = [CompiledForward(model, example, **call_kwargs) for _ in range(depth)]
+        dev = self.slots[0].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.busy = [False] * depth
+        self.n = 0
+
+    def submit(self, batch: HostBatch) -> int:
+        k = self.n % len(self.slots)
+        if self.busy[k]:
+            raise RuntimeError("pipeline slot still holds an uncollected result: call result() first")
+        cf, st = self.slots[k], self.streams[k]
+        if batch.spec != cf.spec:
+            raise ValueError("batch layout differs from the one this forward was compiled for")
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            cf.dev_buffer.copy_(batch.buffer, non_blocking=True)
+            cf.graph.replay()
+            cf.output_host.copy_(cf.output, non_blocking=True)
+            if cf._oob is not None:
+                cf._oob_host.copy_(cf._oob, non_blocking=True)
+            self.done[k].record(st)
+        self.busy[k] = True
+        self.n += 1
+        return k
+
+    def result(self, ticket: int) -> torch.Tensor:
+        self.done[ticket].synchronize()
+        self.busy[ticket] = False
+        self.slots[ticket].check_indices()
+        return self.slots[ticket].output_host

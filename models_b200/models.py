@@ -165,6 +165,15 @@ class Model(Block):
             example = HostBatch.like(example, self.input_columns())
         return CompiledForward(self, example, **call_kwargs)
 
+    def pipeline(self, example: Union[Dict[str, np.ndarray], "HostBatch"], depth: int = 2, **call_kwargs) -> "PipelinedForward":
+        """`depth` graph instances on separate streams so that the H2D copy of batch i+1 overlaps the
+        forward of batch i (models_b200/graph.py)."""
+        from .graph import HostBatch, PipelinedForward
+
+        if not isinstance(example, HostBatch):
+            example = HostBatch.like(example, self.input_columns())
+        return PipelinedForward(self, example, depth=depth, **call_kwargs)
+
     # -- host-buffer entry point (the e2e path of bench.py) -----------------------------------
     def forward_host(self, batch: Dict[str, np.ndarray], stream: Optional[torch.cuda.Stream] = None, **kwargs):
         """Host numpy batch -> pinned staging -> H2D -> forward -> D2H of the predictions."""

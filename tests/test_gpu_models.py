@@ -217,3 +217,28 @@ def test_compiled_two_tower_training_logits(device):
     got = cf(mm.HostBatch.like(b, model.input_columns())).clone().numpy()
     want = model(H.device_batch(b, device), training=True).outputs.cpu().numpy()
     assert got.shape == (256, 257) and np.array_equal(got, want)
+
+
+def test_pipelined_forward_overlapping_batches(device):
+    mm.set_seed(33)
+    schema = small_criteo(400)
+    model = mm.DLRMModel(schema, embedding_dim=64, bottom_block=mm.MLPBlock([32, 64]), top_block=mm.MLPBlock([64, 16]))
+    batches = [datasets.split_targets(schema, datasets.generate_batch(schema, 600, seed=s, index_law="uniform"))[0]
+               for s in range(5)]
+    hbs = [mm.HostBatch.like(b, model.input_columns()) for b in batches]
+    pf = model.pipeline(batches[0], depth=2)
+    want = [model(H.device_batch(b, device)).cpu().numpy() for b in batches]
+    got, tickets = [], []
+    for hb in hbs:
+        tickets.append(pf.submit(hb))
+        if len(tickets) == 2:
+            got.append(pf.result(tickets.pop(0)).clone().numpy())
+    while tickets:
+        got.append(pf.result(tickets.pop(0)).clone().numpy())
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    t = pf.submit(hbs[0])
+    pf.submit(hbs[1])
+    with pytest.raises(RuntimeError, match="uncollected"):
+        pf.submit(hbs[2])
+    pf.result(t)
