@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dlrm", choices=["dlrm"])
+    ap.add_argument("--workload", default="dlrm", choices=["dlrm", "dlrm-sharded"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -197,6 +197,9 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.workload == "dlrm-sharded":
+        return sharded_arm(args, mm, datasets, ops, dev, rank, local_rank, world)
 
     schema, model = build_dlrm(mm, datasets)
     model.build(dev)
@@ -381,6 +384,70 @@ def pick_threads(run, cores):
             best, best_t = n, dt
     torch.set_num_threads(best)
     return best
+
+
+def sharded_arm(args, mm, datasets, ops, dev, rank, local_rank, world):
+    """BASELINE config 4: Criteo-TB-shape tables (204 M rows x 64 fp32 = 52 GB) row-sharded over the
+    ranks (row r on rank r % world), batch 65 536 per GPU, data-parallel MLPs.  One step = index
+    all-gather + owner-computes NVLink push (mm_shard_gather_push) + barrier + interaction + MLPs."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1, device_id=dev)
+    B = args.batch
+    schema = datasets.criteo_tb_schema()
+    model = mm.DLRMModel(schema, embedding_dim=64, bottom_block=mm.MLPBlock([128, 64]), top_block=mm.MLPBlock([128, 64, 32]),
+                         embedding_options=mm.EmbeddingOptions(embeddings_initializers={"hash_seed": 4321}))
+    mm.shard_model(model)
+    model.build(dev)
+    n_bufs = 3
+    devs = []
+    for i in range(n_bufs):
+        b, _ = datasets.split_targets(schema, datasets.generate_batch(schema, B, seed=4000 + 100 * rank + i, index_law="uniform"))
+        devs.append({k: torch.from_numpy(v).to(dev) for k, v in b.items()})
+    torch.cuda.synchronize()
+
+    def barrier():
+        dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        model(devs[i % n_bufs])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        out = model(devs[i % n_bufs])
+    t1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ops.launch_count() - l0
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    if rank == 0:
+        rows = sum(datasets.CRITEO_TB_ROWS)
+        nv_bytes = B * 26 * 64 * 4 * (world - 1) / world  # payload each GPU sends (and receives) per step
+        print(json.dumps({
+            "metric": "DLRM fwd samples/sec (Criteo-TB shape, row-sharded tables, batch 65536/GPU)",
+            "value": world * B * args.steps / (elapsed_ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic (uniform indices; hash-initialised shards)",
+            "config": {"workload": "mm.DLRMModel Criteo-TB-shape, tables row-sharded (row r on rank r % world), "
+                                   "index all-gather + owner-computes NVLink push + barrier",
+                       "batch_per_gpu": B, "global_batch": B * world, "table_rows": rows, "table_gb": rows * 256 / 1e9,
+                       "shard_gb_per_gpu": rows * 256 / 1e9 / world, "parallelism": f"tables row-sharded x{world}, MLPs dp{world}",
+                       "nvlink_payload_bytes_per_gpu_per_step": nv_bytes, "runtime": "eager (symmetric-memory barriers)"},
+            "clocks": clocks, "gpu_launches": int(lt.item()),
+        }))
+    dist.destroy_process_group()
+    return 0
 
 
 def time_cpu_baseline(model, feats_host, sample_rows, cores, budget_s=20.0):

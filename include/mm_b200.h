@@ -218,6 +218,24 @@ int mm_inbatch_scores_tc(const void* q_split, const void* neg_split, int64_t B, 
                          int64_t out_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K10  Query x catalog scoring without materialising (B, N_I):
+ *   logits[b,i] = q[b].E[i] (+ bias[i])   (outputs/classification.py:347-357 EmbeddingTablePrediction;
+ *   blocks/retrieval/base.py:431-438; outputs/topk.py:221-223 BruteForce; core/index.py:236-237)
+ * One tcgen05 GEMM pass over the catalog whose epilogue folds every logits tile into per-row
+ *   out_stats (B,3) = [max, log-sum-exp, logit[target]]   — the inputs of
+ *                     CategoricalCrossEntropy(from_logits=True) (losses/listwise.py:38-50); nullable
+ *   topk_scores/topk_ids (B,k): tf.math.top_k order (descending, ties -> lower id), k <= 32; k = 0: off
+ * q_split (B, 2*Kp) and e_split (I, 2*Kp) are split-bf16 operands from mm_split_rows
+ * (Kp = mm_tc_padded_k(D), D <= 128; the catalog is split once and reused).  `workspace` must hold
+ * mm_catalog_workspace_bytes(B, I, k) bytes (per-row partials of the item-range splits).
+ * ------------------------------------------------------------------------------------- */
+int64_t mm_catalog_workspace_bytes(int64_t B, int64_t I, int k);
+int mm_catalog_score(const void* q_split, int64_t B, int D, const void* e_split, int64_t I,
+                     const float* bias, const void* targets, int id_dtype, float* out_stats, int k,
+                     float* topk_scores, int64_t* topk_ids, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * K13  Row-sharded tables over the GPUs of one NVLink domain: row r of every table lives on
  * rank r % world at local row r / world (the reference's counterpart is SOK's distributed
  * variable, distributed/embedding.py:75-84,144-148).  Owner-computes push = gather + all-to-all

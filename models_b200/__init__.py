@@ -15,7 +15,7 @@ from .inputs import (ContinuousFeatures, EmbeddingOptions, Embeddings, Embedding
                      InputBlockV2, infer_embedding_dim)
 from .blocks import (CrossBlock, DLRMBlock, DotProductInteraction, MLPBlock, dense_engine,  # noqa: F401
                      set_dense_engine)
-from .retrieval import (ContrastiveOutput, InBatchSampler, InBatchSamplerV2, ItemRetrievalScorer,  # noqa: F401
+from .retrieval import (CategoricalOutput, ContrastiveOutput, InBatchSampler, InBatchSamplerV2, ItemRetrievalScorer,  # noqa: F401
                         ItemRetrievalTask, L2Norm, TwoTowerBlock, log_uniform_sampling_probs)
 from .models import (BinaryClassificationTask, BinaryOutput, DCNModel, DLRMModel, Model,  # noqa: F401
                      RetrievalModel, TwoTowerModel)

@@ -370,3 +370,29 @@ def dense_tc(a_split: torch.Tensor, K: int, w_split: torch.Tensor, N: int, bias:
                            passes, _ptr(x0), _ptr(xres), xs, _ptr(out_f32),
                            0 if out_f32 is None else _row_stride(out_f32, "out_f32"), _ptr(out_split), out_Kp, _stream()),
         "mm_dense_tc")
+
+
+def catalog_score(q: torch.Tensor, e_split: torch.Tensor, n_items: int, bias: Optional[torch.Tensor] = None,
+                  targets: Optional[torch.Tensor] = None, k: int = 0, want_stats: bool = True):
+    """Fused query x catalog scoring (mm_catalog_score): returns (stats (B,3) or None, scores (B,k) or
+    None, ids (B,k) or None).  q fp32 (B, D); e_split = split_rows(E) with E the (n_items, D) catalog."""
+    _dev(q, "q", torch.float32), _dev(e_split, "e_split", torch.bfloat16)
+    B, D = q.shape
+    Kp = tc_padded_k(D)
+    if tuple(e_split.shape) != (n_items, 2 * Kp) or not e_split.is_contiguous():
+        raise ValueError(f"e_split must be contiguous ({n_items}, {2 * Kp}) = split_rows(catalog)")
+    dev = q.device
+    stats = torch.empty((B, 3), dtype=torch.float32, device=dev) if want_stats else None
+    scores = torch.empty((B, k), dtype=torch.float32, device=dev) if k else None
+    ids = torch.empty((B, k), dtype=torch.int64, device=dev) if k else None
+    id_dt = MM_I64
+    if targets is not None:
+        targets = targets.reshape(-1).contiguous()
+        id_dt = _idx_dtype(targets, "targets")
+    nbytes = int(_lib().mm_catalog_workspace_bytes(B, n_items, k))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    _cabi.check(
+        _lib().mm_catalog_score(split_rows(q).data_ptr(), B, D, e_split.data_ptr(), n_items, _ptr(bias), _ptr(targets), id_dt,
+                                _ptr(stats), k, _ptr(scores), _ptr(ids), ws.data_ptr(), nbytes, _stream()),
+        "mm_catalog_score")
+    return stats, scores, ids

@@ -318,3 +318,75 @@ class ContrastiveOutput(Block):
             neg_prob = sampling_probs[nid.long()].contiguous()
         return _score(q, c, neg, ids, nid, self.downscore_false_negatives, self.false_negative_score,
                       self.logits_temperature, pos_prob, neg_prob)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-catalog scoring (a14)
+# ------------------------------------------------------------------------------------------------
+class CategoricalOutput(Block):
+    """outputs/classification.py:127-216 with the weight-tied `EmbeddingTablePrediction` to_call
+    (:311-382): logits = x @ E^T + bias over the whole item table E (N_I, D).
+
+    call(x)                      -> (B, N_I) logits, materialised (what the reference returns; only
+                                    sensible for small catalogs)
+    softmax_ce_stats(x, targets) -> (B, 3) [row max, log-sum-exp, logit[target]] — everything
+                                    CategoricalCrossEntropy(from_logits=True) needs
+                                    (losses/listwise.py:38-50): loss = lse - logit[target]
+    top_k(x, k)                  -> (scores, ids) in tf.math.top_k order (outputs/topk.py:221-223)
+    The last two stream the catalog through one tcgen05 GEMM without ever writing (B, N_I)."""
+
+    def __init__(self, to_call, logits_temperature: float = 1.0, use_bias: bool = True, name: Optional[str] = None, **kwargs):
+        from .inputs import EmbeddingTable
+
+        super().__init__(name or unique_name("categorical_output"))
+        if not isinstance(to_call, EmbeddingTable):
+            raise NotImplementedError("CategoricalOutput(to_call=...) supports a weight-tied EmbeddingTable")
+        self.table = to_call
+        self.num_classes = to_call.input_dim
+        self.logits_temperature = float(logits_temperature)
+        self.use_bias = use_bias
+        self.bias: Optional[torch.Tensor] = None
+        self._e_split: Optional[torch.Tensor] = None
+        self._w_split: Optional[torch.Tensor] = None
+
+    def build(self, device=None):
+        self.table.build(device)
+        if self.use_bias and self.bias is None:
+            self.bias = torch.zeros(self.num_classes, dtype=torch.float32, device=self.table.table.device)
+        self.built = True
+        return self
+
+    def weights(self):
+        out = {"embeddings": self.table.embeddings}
+        if self.bias is not None:
+            out["bias"] = self.bias
+        return out
+
+    def refresh(self) -> None:
+        """Drop the cached split-bf16 copies (call after changing the table)."""
+        self._e_split = self._w_split = None
+
+    def _catalog_split(self) -> torch.Tensor:
+        if self._e_split is None:
+            self._e_split = ops.split_rows(self.table.embeddings)  # (N_I, 2*Kp), once per catalog
+        return self._e_split
+
+    def call(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
+        self.build(x.device)
+        if self._w_split is None:
+            self._w_split = ops.split_weights(self.table.embeddings.t().contiguous())
+        out = torch.empty((x.shape[0], self.num_classes), dtype=torch.float32, device=x.device)
+        ops.dense_tc(ops.split_rows(x), x.shape[1], self._w_split, self.num_classes, self.bias, "linear", out_f32=out)
+        if self.logits_temperature != 1.0:
+            raise NotImplementedError("materialised logits with a temperature: use softmax_ce_stats / top_k on x / T")
+        return out
+
+    def softmax_ce_stats(self, x: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        self.build(x.device)
+        stats, _, _ = ops.catalog_score(x, self._catalog_split(), self.num_classes, bias=self.bias, targets=targets, k=0)
+        return stats
+
+    def top_k(self, x: torch.Tensor, k: int):
+        self.build(x.device)
+        _, scores, ids = ops.catalog_score(x, self._catalog_split(), self.num_classes, bias=self.bias, k=k, want_stats=False)
+        return scores, ids
