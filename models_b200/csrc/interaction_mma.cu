@@ -134,41 +134,60 @@ interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
     if (MODE == 1 && lane < p.T && it < n_mine) return my_idx_ptr[gw + it * wstride];
     return (IdxT)0;
   };
+  // Per-lane row constants: lane r (< rows) owns staged row r.  Its destination inside a sample
+  // buffer (byte offset of the slot + the slot's chunk swizzle) never changes; its source pointer is
+  // computed once per sample by the owner and broadcast with shuffles in the copy loop, so the loop
+  // body is 3 shuffles + a few integer ops + one LDGSTS per 16 bytes.
+  int my_slot = lane;
+  const float* my_base = nullptr;  // table base (MODE 1) — row-invariant part of the source
+  if (MODE == 1 && lane < p.T) {
+    my_slot = gp.t[lane].out_col >> p.log2D;
+    my_base = gp.t[lane].weights;
+  } else if (MODE == 1 && lane == p.T) {
+    my_slot = p.bottom_slot;
+  }
+  // destination descriptor: (slot * DS * 4 bytes) | swizzle (low 3 bits; the offset is a multiple of 64 B)
+  const uint32_t my_dst = (uint32_t)(my_slot * DS * 4) | (uint32_t)(((my_slot & 3) << 1) & (V - 1));
+
   auto issue = [&](long long it, IdxT idx_raw) {
     if (it < n_mine) {
       const long long s = gw + it * wstride;
       const int buf = (int)(it % NBUF);
       const uint32_t xs_u32 = smem_u32(wbase + (size_t)buf * p.in_bytes);
-      int idx32 = -1;  // row index within the table (tables have < 2^31 rows), -1 = zero row
-      if (MODE == 1 && lane < p.T) {
-        const long long idx = (long long)idx_raw;
-        if (idx >= 0 && idx < my_rows) idx32 = (int)idx;
-        else if (p.oob_count) atomicAdd(p.oob_count, 1);
-      }
-      const int total = p.rows << p.log2V;
-      for (int e0 = 0; e0 < total; e0 += 32) {  // warp-uniform trip count (shuffles inside)
-        const int e = e0 + lane;
-        const bool act = e < total;
-        const int r = act ? e >> p.log2V : 0, v = e & (V - 1);
-        const float* src;
-        uint32_t bytes = 16;
-        int slot = r;
-        if (MODE == 1) {
-          const int ridx = __shfl_sync(0xffffffffu, idx32, r);
-          if (r < p.T) {
-            slot = gp.t[r].out_col >> p.log2D;
-            src = gp.t[r].weights + ((long long)(ridx < 0 ? 0 : ridx) << p.log2D) + v * 4;
-            if (ridx < 0) bytes = 0;
-          } else {
-            slot = p.bottom_slot;
-            src = p.prefix + s * p.prefix_stride + v * 4;
+      // owner lanes: source row pointer and copy size (0 = zero fill)
+      const float* my_src = my_base;
+      uint32_t my_bytes = 16;
+      if (MODE == 1) {
+        if (lane < p.T) {
+          const long long idx = (long long)idx_raw;
+          if (idx >= 0 && idx < my_rows) my_src = my_base + (idx << p.log2D);
+          else {
+            my_bytes = 0;
+            if (p.oob_count) atomicAdd(p.oob_count, 1);
           }
         } else {
-          src = r < F ? p.x + s * p.x_stride + ((long long)r << p.log2D) + v * 4
-                      : p.prefix + s * p.prefix_stride + v * 4;
+          my_src = p.prefix + s * p.prefix_stride;
         }
-        if (act) cp_async16_zfill(xs_u32 + (uint32_t)((slot * DS + ((v ^ (((slot & 3) << 1) & (V - 1))) << 2)) * 4), src, bytes);
+      } else {
+        my_src = lane < F ? p.x + s * p.x_stride + ((long long)lane << p.log2D) : p.prefix + s * p.prefix_stride;
       }
+      const uint32_t src_lo = (uint32_t)(uintptr_t)my_src, src_hi = (uint32_t)((uintptr_t)my_src >> 32);
+      const uint32_t my_info = my_dst | (my_bytes << 24);  // dst offset < 2^24, bytes in the top byte
+      const int total = p.rows << p.log2V;
+      const int v = lane & (V - 1), rsub = lane >> p.log2V;  // rows per step = 32 / V
+      const int rstep = 32 >> p.log2V;
+      for (int r0 = 0; r0 < p.rows; r0 += rstep) {  // warp-uniform trip count (shuffles inside)
+        const int r = r0 + rsub;
+        const bool act = r < p.rows;
+        const int rr = act ? r : 0;
+        const uint32_t lo = __shfl_sync(0xffffffffu, src_lo, rr);
+        const uint32_t hi = __shfl_sync(0xffffffffu, src_hi, rr);
+        const uint32_t info = __shfl_sync(0xffffffffu, my_info, rr);
+        const float* src = reinterpret_cast<const float*>(((uintptr_t)hi << 32) | lo) + v * 4;
+        const uint32_t dst = xs_u32 + (info & 0x00fffff8u) + (((uint32_t)v ^ (info & 7u)) << 4);
+        if (act) cp_async16_zfill(dst, src, info >> 24);
+      }
+      (void)total;
     }
     cp_async_commit();  // one group per sample (empty past the end keeps the group count in step)
   };

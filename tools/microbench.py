@@ -47,6 +47,7 @@ def timeit(fn, iters, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="gather,interact,fused,dense,scores")
+    ap.add_argument("--catalog-items", type=int, default=10_000_000)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--law", default="uniform")
@@ -65,7 +66,7 @@ def main():
             r["GBps"] = bytes_ / (ms_mean * 1e-3) / 1e9
             r["frac_hbm"] = r["GBps"] / hbm
         if flops is not None:
-            r["TFLOPs"] = flops / (ms_mean * 1e-3) / 1e12
+            r["TFLOPs"] = flops / (ms_mean * 1e-3) / 1e12  # tensor-core FLOPs actually issued (x3 for the split)
             r["frac_bf16_peak"] = r["TFLOPs"] / tf
         print(json.dumps(r), flush=True)
         res.append(r)
@@ -118,6 +119,54 @@ def main():
             m, mn = timeit(lambda i: ops.inbatch_scores(q, it, it, o, pos_ids=ids, neg_ids=ids, tensor_cores=tc), max(5, args.iters // 2))
             report(f"mm_inbatch_scores 16384x16384 D=64 ({'tcgen05 split-bf16 incl. operand split' if tc else 'fp32 SIMT'})", m, mn,
                    bytes_=Bq * (Bq + 1) * 4, flops=2.0 * Bq * Bq * Dq)
+
+    if "catalog" in only:
+        Bq, Dq, I = 16384, 64, args.catalog_items
+        q = torch.randn((Bq, Dq), device=dev)
+        E = torch.empty((I, Dq), device=dev)
+        ops.init_uniform_hash(E, 77, -0.5, 0.5)
+        es = ops.split_rows(E)
+        tg = torch.randint(0, I, (Bq,), device=dev)
+        for k, stats in ((0, True), (10, False), (10, True)):
+            m, mn = timeit(lambda i: ops.catalog_score(q, es, I, targets=tg if stats else None, k=k, want_stats=stats), 3, warmup=1)
+            report(f"mm_catalog_score B=16384 I={I} D=64 (lse={stats}, topk={k})", m, mn, flops=2.0 * Bq * I * Dq * 3,
+                   logical_flops=2.0 * Bq * I * Dq)
+
+    if "tc_dense" in only:
+        for (K, N) in [(415, 128), (128, 64), (13, 128), (1024, 1024), (1037, 1037), (512, 256), (415, 1024)]:
+            x = torch.randn((B, K), device=dev)
+            W = torch.randn((K, N), device=dev) * 0.05
+            b = torch.zeros(N, device=dev)
+            a, w = ops.split_rows(x), ops.split_weights(W)
+            nxt = torch.zeros((B, 2 * ops.tc_padded_k(N)), dtype=torch.bfloat16, device=dev)
+            m, mn = timeit(lambda i: ops.dense_tc(a, K, w, N, b, "relu", out_split=nxt), max(5, args.iters // 2))
+            report(f"mm_dense_tc {K}->{N} (3-pass split-bf16, split out)", m, mn, flops=2.0 * B * K * N * 3,
+                   bytes_=B * (2 * ops.tc_padded_k(K) * 2 + 2 * ops.tc_padded_k(N) * 2), logical_flops=2.0 * B * K * N)
+
+    if "models" in only:
+        mm.set_seed(1)
+        # config 5: DCN-v2, bundled Criteo, inferred dims (d = 1037), depth 3, deep [256, 128]
+        schema = datasets.criteo_schema()
+        dcn = mm.DCNModel(schema, depth=3, deep_block=mm.MLPBlock([256, 128]),
+                          embeddings_initializer={"hash_seed": 99})
+        b, _ = datasets.split_targets(schema, datasets.generate_batch(schema, B, seed=5, index_law="uniform"))
+        cf = dcn.compile(b)
+        m, mn = timeit(lambda i: cf.replay(), max(5, args.iters // 2))
+        report("mm.DCNModel fwd (config 5: d=1037, depth 3, deep [256,128], B=65536, graph)", m, mn,
+               flops=3 * (3 * 2 * 1037 * 1037 + 2 * (1037 * 256 + 256 * 128)) * B, logical_flops=7.05e6 * B,
+               samples_per_s=B / (m * 1e-3))
+        del dcn, cf
+        torch.cuda.empty_cache()
+        # config 3: two-tower, 10M-item catalog, in-batch negatives, B = 16384
+        rs = datasets.retrieval_10m_schema()
+        tt = mm.TwoTowerModel(rs, query_tower=mm.MLPBlock([256, 128]),
+                              embedding_options=mm.EmbeddingOptions(embeddings_initializers={"hash_seed": 5}))
+        Bt = 16384
+        tb = datasets.generate_batch(rs, Bt, seed=6, index_law="zipf")
+        cft = tt.compile(tb, training=True)
+        m, mn = timeit(lambda i: cft.replay(), max(5, args.iters // 2))
+        report("mm.TwoTowerModel train-mode fwd (config 3: 10M items, towers [256,128], in-batch, B=16384, graph)", m, mn,
+               bytes_=Bt * (Bt + 1) * 4, samples_per_s=Bt / (m * 1e-3))
 
 
 if __name__ == "__main__":

@@ -37,19 +37,23 @@ elif what in ("gather", "fused", "interact"):
     emb.build(dev)
     names = emb.feature_names
     slots = {n: i for i, n in enumerate(sorted(names + ["bottom_block"]))}
-    b = datasets.generate_batch(cat, B, seed=100, index_law="uniform")
-    idx = [torch.from_numpy(b[n]).to(dev) for n in names]
+    idxs = []
+    for i in range(4):  # rotating batches: the captured launch sees rows that are not L2-resident
+        b = datasets.generate_batch(cat, B, seed=100 + i, index_law="uniform")
+        idxs.append([torch.from_numpy(b[n]).to(dev) for n in names])
     tables = [emb.feature_to_table[n].table for n in names]
     stack = torch.empty((B, F * D), dtype=torch.float32, device=dev)
     bottom = torch.randn((B, D), device=dev)
-    out = torch.empty((B, D + F * (F - 1) // 2), dtype=torch.float32, device=dev)
-    for _ in range(5):
+    out = torch.empty((B, 2 * ops.tc_padded_k(D + F * (F - 1) // 2)), dtype=torch.bfloat16, device=dev)
+    xs = [torch.randn((B, F, D), device=dev) for _ in range(2)]
+    for i in range(6):
+        idx = idxs[i % 4]
         if what == "gather":
             ops.gather_multi(tables, idx, [slots[n] * D for n in names], stack)
         elif what == "fused":
             ops.dlrm_gather_interact(tables, idx, [slots[n] for n in names], D, bottom, slots["bottom_block"], out)
         else:
-            ops.dot_interaction(torch.randn((B, F, D), device=dev), out, prefix=bottom)
+            ops.dot_interaction(xs[i % 2], out, prefix=bottom)
 elif what == "scores":
     Bq, Dq = 16384, 64
     q = torch.randn((Bq, Dq), device=dev)
