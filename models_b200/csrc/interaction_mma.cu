@@ -248,31 +248,9 @@ interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
       }
     }
 
-    // ---- assemble the output row in shared memory
-    if (p.out_split) {
-      __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(ostage);
-      __nv_bfloat16* ol = oh + p.out_Kp;
-      if (p.P > 0) {
-        const int prow = MODE == 1 ? p.bottom_slot : F;
-        const float* pr = xs + prow * DS;
-        for (int e = lane; e < p.P; e += 32) {
-          const float v = pr[((((e >> 2) ^ (((prow & 3) << 1) & ((D >> 2) - 1)))) << 2) + (e & 3)];
-          const __nv_bfloat16 h = __float2bfloat16_rn(v);
-          oh[e] = h;
-          ol[e] = __float2bfloat16_rn(v - __bfloat162float(h));
-        }
-      }
-#pragma unroll
-      for (int ti = 0; ti < 6; ++ti)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (off[ti][c] >= 0) {
-            const float v = acc[ti][c];
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            oh[off[ti][c]] = h;
-            ol[off[ti][c]] = __float2bfloat16_rn(v - __bfloat162float(h));
-          }
-    } else {
+    // ---- assemble the fp32 output row in shared memory (one predicated 4-byte store per accumulator);
+    // the split into bf16 (hi, lo) happens in the coalesced store pass, 8 columns per lane at a time
+    {
       float* os = reinterpret_cast<float*>(ostage);
       if (p.P > 0) {
         const int prow = MODE == 1 ? p.bottom_slot : F;
@@ -289,23 +267,29 @@ interact_mma_kernel(const __grid_constant__ GatherParams gp, const Params p) {
 
     // ---- coalesced row store
     if (p.out_split) {
-      const uint4* src = reinterpret_cast<const uint4*>(ostage);
-      uint4* dst = reinterpret_cast<uint4*>(p.out_split + s * (2ll * p.out_Kp));
-      const int n16 = p.out_Kp >> 2;  // 2*Kp bf16 = Kp/4 x 16 B
-      for (int e = lane; e < n16; e += 32) dst[e] = src[e];
-    }
-    if (p.out_f32) {
+      // staging holds out_Kp floats (columns >= OW are the zero padding written once at kernel start)
+      const float4* src = reinterpret_cast<const float4*>(ostage);
+      __nv_bfloat16* drow = p.out_split + s * (2ll * p.out_Kp);
+      const int groups = p.out_Kp >> 3;  // 8 columns = one 16-byte bf16 store for hi and one for lo
+      for (int gidx = lane; gidx < groups; gidx += 32) {
+        const float4 a = src[2 * gidx], b = src[2 * gidx + 1];
+        uint32_t h[4], l[4];
+        split_pair(make_float2(a.x, a.y), h[0], l[0]);
+        split_pair(make_float2(a.z, a.w), h[1], l[1]);
+        split_pair(make_float2(b.x, b.y), h[2], l[2]);
+        split_pair(make_float2(b.z, b.w), h[3], l[3]);
+        *reinterpret_cast<uint4*>(drow + 8 * gidx) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(drow + p.out_Kp + 8 * gidx) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    } else if (p.out_f32) {
       const float* os = reinterpret_cast<const float*>(ostage);
       float* dst = p.out_f32 + s * p.out_stride;
-      if (!p.out_split) {
-        if (((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0)) {
-          const int n4 = OW >> 2;
-          for (int e = lane; e < n4; e += 32)
-            reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(os)[e];
-          for (int e = (n4 << 2) + lane; e < OW; e += 32) dst[e] = os[e];
-        } else {
-          for (int e = lane; e < OW; e += 32) dst[e] = os[e];
-        }
+      if (((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0)) {
+        const int n4 = OW >> 2;
+        for (int e = lane; e < n4; e += 32) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<const float4*>(os)[e];
+        for (int e = (n4 << 2) + lane; e < OW; e += 32) dst[e] = os[e];
+      } else {
+        for (int e = lane; e < OW; e += 32) dst[e] = os[e];
       }
     }
     __syncwarp();  // staging may be overwritten by the next sample
@@ -353,7 +337,7 @@ int launch(const float* x, int64_t x_stride, const GatherParams& gp, const float
   p.out_Kp = out_Kp;
   p.oob_count = oob;
   p.in_bytes = (unsigned)(rows * D * 4);
-  const unsigned stage = out_split ? (unsigned)(2 * out_Kp * 2) : (unsigned)(((OW + 3) & ~3) * 4);
+  const unsigned stage = out_split ? (unsigned)(out_Kp * 4) : (unsigned)(((OW + 3) & ~3) * 4);  // fp32 row (+ zero padding)
   p.per_warp_bytes = (NBUF * p.in_bytes + stage + 127u) & ~127u;
   int warps = (int)((226u * 1024u) / p.per_warp_bytes);
   if (warps > MAX_WARPS) warps = MAX_WARPS;
