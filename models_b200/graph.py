@@ -178,6 +178,27 @@ class PipelinedForward:
         self.n += 1
         return k
 
+    def submit_device(self, packed: torch.Tensor) -> int:
+        """Same as submit() for a batch that is already resident on the device (packed HostBatch layout):
+        D2D refresh of the slot's static input buffer + graph replay on the slot's stream; no D2H."""
+        k = self.n % len(self.slots)
+        cf, st = self.slots[k], self.streams[k]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            cf.dev_buffer.copy_(packed, non_blocking=True)
+            cf.graph.replay()
+            self.done[k].record(st)
+        self.n += 1
+        return k
+
+    def join(self) -> None:
+        """Make the current stream wait for everything submitted so far."""
+        for st in self.streams:
+            torch.cuda.current_stream().wait_stream(st)
+
+    def output(self, ticket: int) -> torch.Tensor:
+        return self.slots[ticket].output
+
     def result(self, ticket: int) -> torch.Tensor:
         self.done[ticket].synchronize()
         self.busy[ticket] = False
