@@ -187,6 +187,13 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
                 int64_t x_stride, float* out_f32, int64_t out_stride, void* out_split,
                 int out_Kp, void* stream);
 
+/* mm_dense_tc with a fused output head: out_head[m] = head_act( act(x W + b)[m,:] . head_w + head_b ),
+ * i.e. the layer followed by Dense(N -> 1) (BinaryOutput's Dense(1, sigmoid),
+ * outputs/classification.py:114) evaluated in the GEMM epilogue; N <= 32.  head_w: (N,) device. */
+int mm_dense_tc_head(const void* a_split, int64_t M, int K, int Kp, const void* w_split, int N, int Np,
+                     const float* bias, int act, int passes, const float* head_w, float head_b,
+                     int head_act, float* head_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K8/K9  Two-tower scoring.
  * mm_rowwise_dot: inference scorer  s[b] = sum_d q[b,d]*i[b,d]

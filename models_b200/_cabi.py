@@ -70,6 +70,7 @@ SIGNATURES = {
     "mm_split_weights": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "mm_dense_tc": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _i64, _vp, _i64,
                          _vp, _i, _vp]),
+    "mm_dense_tc_head": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _f, _i, _vp, _vp]),
     "mm_rowwise_dot": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
     "mm_catalog_workspace_bytes": (_i64, [_i64, _i64, _i]),
     "mm_catalog_score": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp]),

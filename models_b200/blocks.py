@@ -60,11 +60,22 @@ def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: 
     if a_split is None:
         a = ops.split_rows(x)
     out = None
+    # a trailing Dense(N -> 1) (BinaryOutput) after a layer with N <= 32 units is evaluated inside that
+    # layer's GEMM epilogue: one launch and one HBM round trip fewer
+    fuse_head = (len(layers) >= 2 and layers[-1].units == 1 and layers[-2].units <= 32
+                 and layers[-1].input_dim == layers[-2].units)
+    if fuse_head:
+        head, layers = layers[-1], layers[:-1]
     for i, l in enumerate(layers):
         last = i == len(layers) - 1
         if K != l.input_dim:
             raise ValueError(f"{l.name}: input width {K} != kernel rows {l.input_dim}")
         nxt = None
+        if last and fuse_head:
+            out = torch.empty((B, 1), dtype=torch.float32, device=device)
+            ops.dense_tc_head(a, K, l.split_kernel(), l.units, l.bias, l.activation, head.kernel.reshape(-1),
+                              head.bias_value(), head.activation, out)
+            return out
         if last:
             out = torch.empty((B, l.units), dtype=torch.float32, device=device)
         else:
@@ -113,6 +124,14 @@ class _Dense(Block):
             self._split_bufs[key] = buf
         return buf
 
+    def bias_value(self) -> float:
+        """Scalar bias of a 1-unit layer (cached on the host: it is a kernel argument of the fused head)."""
+        if self.bias is None:
+            return 0.0
+        if getattr(self, "_bias_host", None) is None:
+            self._bias_host = float(self.bias.reshape(-1)[0].item())
+        return self._bias_host
+
     def build(self, input_dim: Optional[int] = None, device=None) -> "_Dense":
         if self.kernel is None:
             if input_dim is None:
@@ -134,6 +153,7 @@ class _Dense(Block):
         self.bias = None if bias is None else torch.as_tensor(bias, dtype=torch.float32).to(dev).contiguous()
         self.use_bias = bias is not None
         self._w_split = None
+        self._bias_host = None
         self.built = True
 
     def weights(self):

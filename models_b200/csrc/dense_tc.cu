@@ -55,6 +55,12 @@ struct Params {
   const void* neg_ids;
   float fns;
   float temperature;
+  // fused output head: after this layer's activation, out_head[m] = head_act(sum_n v[m,n] * head_w[n] + head_b)
+  // — a following Dense(N -> 1) evaluated in the epilogue on CUDA cores (N <= 32: the row sits in one thread)
+  const float* head_w;
+  float head_b;
+  int head_act;
+  float* head_out;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -208,6 +214,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float b = 0.0f;
         if (p.bias && n < p.N) b = p.score_mode ? -logf(p.bias[n] + 1e-16f) : p.bias[n];
         bias_s[i] = b;
+        if (p.head_w) {  // 32 head weights, zero beyond N
+          bias_s[128 + i] = n < p.N ? p.head_w[n] : 0.0f;
+          if (i + p.BN < 32) bias_s[128 + i + p.BN] = 0.0f;
+        }
         if (p.score_mode && p.neg_ids)
           ids_s[i] = n < p.N ? (p.id_is64 ? reinterpret_cast<const long long*>(p.neg_ids)[n]
                                           : (long long)reinterpret_cast<const int*>(p.neg_ids)[n])
@@ -303,6 +313,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (n0 + c0 + j >= p.N) v[j] = 0.0f;
+        }
+        if (p.head_w) {  // fused Dense(N -> 1): BN <= 32, so this chunk is the whole row
+          float h = p.head_b;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h = fmaf(v[j], bias_s[128 + j], h);
+          if (row0 + lane < p.M) p.head_out[row0 + lane] = apply_act(h, p.head_act);
         }
         if (p.out_f32) {
           __syncwarp();
@@ -450,7 +466,8 @@ static int dense_tc_launch(const void* a_split, int64_t M, int K, int Kp, const 
                            const float* bias, int act, int passes, const float* x0, const float* xres,
                            int64_t x_stride, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
                            int score_mode, const void* pos_ids, const void* neg_ids, int id_is64, float fns,
-                           float temperature, int64_t b_rows, void* stream) {
+                           float temperature, int64_t b_rows, const float* head_w, float head_b, int head_act,
+                           float* head_out, void* stream) {
   using namespace mm::tc;
   MM_REQUIRE(a_split && w_split && M >= 0 && K > 0 && N > 0, MM_ERR_ARG, "mm_dense_tc: null operand or non-positive K/N");
   MM_REQUIRE(Kp == mm_tc_padded_k(K) && Np == mm_tc_padded_n(N), MM_ERR_ARG,
@@ -460,7 +477,11 @@ static int dense_tc_launch(const void* a_split, int64_t M, int K, int Kp, const 
   MM_REQUIRE((x0 == nullptr) == (xres == nullptr), MM_ERR_ARG, "mm_dense_tc: x0 and xres go together");
   MM_REQUIRE(!score_mode || (!x0 && !out_split), MM_ERR_ARG, "mm_dense_tc: scorer epilogue excludes cross / split outputs");
   MM_REQUIRE(!x0 || x_stride >= N, MM_ERR_ARG, "mm_dense_tc: x_stride < N for the cross epilogue");
-  MM_REQUIRE(out_f32 || out_split, MM_ERR_ARG, "mm_dense_tc: no output requested");
+  MM_REQUIRE(out_f32 || out_split || head_out, MM_ERR_ARG, "mm_dense_tc: no output requested");
+  MM_REQUIRE((head_w == nullptr) == (head_out == nullptr), MM_ERR_ARG, "mm_dense_tc: head weights and head output go together");
+  MM_REQUIRE(!head_w || (Np <= 32 && !score_mode && !x0), MM_ERR_UNSUPPORTED,
+             "mm_dense_tc: the fused Dense(N->1) head needs N <= 32 and a plain dense epilogue");
+  MM_REQUIRE(!head_w || (head_act >= MM_ACT_LINEAR && head_act <= MM_ACT_GELU), MM_ERR_ARG, "mm_dense_tc: unknown head activation");
   MM_REQUIRE(!out_f32 || out_stride >= N, MM_ERR_ARG, "mm_dense_tc: out_stride < N");
   MM_REQUIRE(!out_split || (out_Kp == mm_tc_padded_k(N) && ((uintptr_t)out_split % 16) == 0), MM_ERR_ARG,
              "mm_dense_tc: out_Kp must be mm_tc_padded_k(N)=%d and out_split 16-B aligned", mm_tc_padded_k(N));
@@ -492,6 +513,10 @@ static int dense_tc_launch(const void* a_split, int64_t M, int K, int Kp, const 
   p.neg_ids = neg_ids;
   p.fns = fns;
   p.temperature = temperature;
+  p.head_w = head_w;
+  p.head_b = head_b;
+  p.head_act = head_act;
+  p.head_out = head_out;
   const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.BN * BLOCK_K * 2;
   const size_t epi_bytes = 256 * sizeof(long long) + 256 * sizeof(float) + (size_t)kEpiWarps * EPI_STAGE_BYTES;
   int stages = (int)((224 * 1024 - 2048 - epi_bytes) / stage_bytes);
@@ -528,7 +553,14 @@ int mm_dense_tc(const void* a_split, int64_t M, int K, int Kp, const void* w_spl
                 int64_t x_stride, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
                 void* stream) {
   return dense_tc_launch(a_split, M, K, Kp, w_split, N, Np, bias, act, passes, x0, xres, x_stride, out_f32, out_stride,
-                         out_split, out_Kp, 0, nullptr, nullptr, 0, 0.0f, 1.0f, Np, stream);
+                         out_split, out_Kp, 0, nullptr, nullptr, 0, 0.0f, 1.0f, Np, nullptr, 0.0f, 0, nullptr, stream);
+}
+
+int mm_dense_tc_head(const void* a_split, int64_t M, int K, int Kp, const void* w_split, int N, int Np,
+                     const float* bias, int act, int passes, const float* head_w, float head_b, int head_act,
+                     float* head_out, void* stream) {
+  return dense_tc_launch(a_split, M, K, Kp, w_split, N, Np, bias, act, passes, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0,
+                         nullptr, nullptr, 0, 0.0f, 1.0f, Np, head_w, head_b, head_act, head_out, stream);
 }
 
 int mm_inbatch_scores_tc(const void* q_split, const void* neg_split, int64_t B, int64_t N, int D,
@@ -544,7 +576,7 @@ int mm_inbatch_scores_tc(const void* q_split, const void* neg_split, int64_t B, 
   return dense_tc_launch(q_split, B, D, mm_tc_padded_k(D), neg_split, (int)N, mm_tc_padded_n((int)N), neg_prob,
                          MM_ACT_LINEAR, 3, nullptr, nullptr, 0, out + 1, out_stride, nullptr, 0, 1,
                          downscore ? pos_ids : nullptr, downscore ? neg_ids : nullptr, id_dtype == MM_I64,
-                         false_neg_score, temperature, N, stream);
+                         false_neg_score, temperature, N, nullptr, 0.0f, 0, nullptr, stream);
 }
 
 

@@ -396,3 +396,21 @@ def catalog_score(q: torch.Tensor, e_split: torch.Tensor, n_items: int, bias: Op
                                 _ptr(stats), k, _ptr(scores), _ptr(ids), ws.data_ptr(), nbytes, _stream()),
         "mm_catalog_score")
     return stats, scores, ids
+
+
+def dense_tc_head(a_split: torch.Tensor, K: int, w_split: torch.Tensor, N: int, bias: Optional[torch.Tensor],
+                  act: Optional[str], head_w: torch.Tensor, head_b: float, head_act: Optional[str],
+                  out: torch.Tensor, passes: int = 3) -> torch.Tensor:
+    """Tensor-core dense layer (N <= 32) with the following Dense(N -> 1) fused into its epilogue
+    (mm_dense_tc_head): out (M, 1) = head_act(act(x W + b) @ head_w + head_b)."""
+    _dev(a_split, "a_split", torch.bfloat16), _dev(w_split, "w_split", torch.bfloat16), _dev(out, "out", torch.float32)
+    _dev(head_w, "head_w", torch.float32)
+    M = a_split.shape[0]
+    if head_w.numel() != N or not head_w.is_contiguous() or out.numel() != M or not out.is_contiguous():
+        raise ValueError("head_w must hold N weights and out M contiguous values")
+    _cabi.check(
+        _lib().mm_dense_tc_head(a_split.data_ptr(), M, K, tc_padded_k(K), w_split.data_ptr(), N, tc_padded_n(N), _ptr(bias),
+                                ACTIVATIONS[act], passes, head_w.data_ptr(), float(head_b), ACTIVATIONS[head_act],
+                                out.data_ptr(), _stream()),
+        "mm_dense_tc_head")
+    return out

@@ -107,3 +107,34 @@ def test_dense_tc_argument_errors(device):
         ops.dense_tc(a, 64, w, 1, None, "relu", passes=2, out_f32=out)
     with pytest.raises(ValueError, match="no output"):
         ops.dense_tc(a, 64, w, 1, None, "relu")
+
+
+@pytest.mark.parametrize("N,head_act", [(32, "sigmoid"), (16, "linear"), (24, "relu")])
+def test_dense_tc_fused_head(device, N, head_act):
+    rng = np.random.default_rng(6)
+    M, K = 3000, 64
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    hw = (rng.standard_normal((N, 1)) * 0.3).astype(np.float32)
+    out = torch.empty((M, 1), dtype=torch.float32, device=device)
+    ops.dense_tc_head(ops.split_rows(dev(x, device)), K, ops.split_weights(dev(W, device)), N, dev(b, device), "relu",
+                      dev(hw.reshape(-1), device), 0.25, head_act, out)
+    ref = oracle.dense(oracle.dense(x, W, b, "relu"), hw, np.array([0.25], np.float32), head_act)
+    assert H.rel_err(out.cpu().numpy(), ref) < 5e-5
+
+
+def test_mlp_plus_head_chain_equals_unfused(device):
+    mm.set_seed(8)
+    rng = np.random.default_rng(8)
+    x = dev(rng.standard_normal((1500, 415)).astype(np.float32), device)
+    mlp = mm.MLPBlock([128, 64, 32])
+    head = mm.BinaryOutput("label")
+    from models_b200.blocks import run_dense_chain
+
+    fused = run_dense_chain(x, mlp.dense_layers + [head.to_call]).cpu().numpy()
+    body = mlp(x)
+    unfused = head(body).cpu().numpy()
+    ref = oracle.dense(oracle.mlp(x.cpu().numpy(), H.mlp_layers(mlp)), H.to_numpy(head.to_call.kernel),
+                       H.to_numpy(head.to_call.bias), "sigmoid")
+    assert H.rel_err(fused, ref) < 5e-5 and H.rel_err(unfused, ref) < 5e-5
