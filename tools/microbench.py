@@ -157,6 +157,17 @@ def main():
                samples_per_s=B / (m * 1e-3))
         del dcn, cf
         torch.cuda.empty_cache()
+        # wide-tower DLRM (SURVEY §8(d) config 2 variant): bottom [512,256,64], top [1024,1024,512,256]
+        wide = mm.DLRMModel(schema, embedding_dim=64, bottom_block=mm.MLPBlock([512, 256, 64]),
+                            top_block=mm.MLPBlock([1024, 1024, 512, 256]),
+                            embedding_options=mm.EmbeddingOptions(embeddings_initializers={"hash_seed": 4321}))
+        cfw = wide.compile(b)
+        m, mn = timeit(lambda i: cfw.replay(), max(5, args.iters // 2))
+        wf = 2.0 * (13 * 512 + 512 * 256 + 256 * 64 + 415 * 1024 + 1024 * 1024 + 1024 * 512 + 512 * 256 + 256) * B
+        report("mm.DLRMModel wide towers fwd (bottom [512,256,64], top [1024,1024,512,256], B=65536, graph)", m, mn,
+               flops=3 * wf, logical_flops=wf, samples_per_s=B / (m * 1e-3))
+        del wide, cfw
+        torch.cuda.empty_cache()
         # config 3: two-tower, 10M-item catalog, in-batch negatives, B = 16384
         rs = datasets.retrieval_10m_schema()
         tt = mm.TwoTowerModel(rs, query_tower=mm.MLPBlock([256, 128]),
