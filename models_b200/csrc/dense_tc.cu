@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A_hi | A_lo | B_hi | B_lo] (1024-B aligned tiles), then barriers
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared state space (LDS/STS, not generic LD/ST)
   const uint32_t B_TILE_BYTES = (uint32_t)p.BN * BLOCK_K * 2;
   const uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
