@@ -24,7 +24,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Bounded wait: a protocol bug must trap, not hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
+  uint32_t ok = 0, spins = 0;
   const long long t0 = clock64();
   while (true) {
     asm volatile(
@@ -33,7 +33,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > 8000000000ll) __trap();
+    if ((++spins & 1023u) == 0u && clock64() - t0 > 8000000000ll) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
