@@ -194,6 +194,26 @@ int mm_dense_tc_head(const void* a_split, int64_t M, int K, int Kp, const void* 
                      const float* bias, int act, int passes, const float* head_w, float head_b,
                      int head_act, float* head_out, void* stream);
 
+/* Whole MLP tower in ONE launch (MLPBlock = SequentialBlock of Dense layers, blocks/mlp.py:97-139,
+ * `_Dense.call` :275-280; optionally followed by BinaryOutput's Dense(1), outputs/classification.py:114):
+ *   h_1 = act_1(x W_1 + b_1); h_l = act_l(h_{l-1} W_l + b_l), l = 2..n_layers (n_layers <= 4);
+ *   out (M, widths[n-1]) fp32 rows (or null) and/or head_out[m] = head_act(h_n[m,:] . head_w + head_b).
+ * Layer 1 is the TMA-fed tcgen05 GEMM of mm_dense_tc (any K); layers 2..n run on chip: the
+ * activations go TMEM -> registers (bias, activation, bf16 split) -> TMEM and are the A operand of the
+ * next tcgen05.mma, the weights of layers 2..n stay resident in shared memory.  Every width must be
+ * <= 128 (README towers: 13->128->64 and 415->128->64->32->1); fp32 parity by 3-pass split-bf16.
+ * a_split: mm_split_rows layout (M, 2*Kp(K)); w_split[l]: mm_split_weights layout of layer l;
+ * bias[l]: (widths[l],) device or null; acts[l]: MM_ACT_*; the head needs widths[n-1] <= 32.
+ * Returns MM_ERR_UNSUPPORTED when the tower does not fit (caller then chains mm_dense_tc);
+ * mm_mlp_tc_supported(K, n_layers, widths, with_head) answers that question (1 / 0) without launching:
+ * 2..4 layers, widths <= 128, head only after <= 32 units, resident weights + two pipeline stages
+ * within 227 KB of shared memory. */
+int mm_mlp_tc_supported(int K, int n_layers, const int* widths, int with_head);
+int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* const* w_split,
+              const int* widths, const float* const* bias, const int* acts, float* out,
+              int64_t out_stride, const float* head_w, float head_b, int head_act, float* head_out,
+              void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K8/K9  Two-tower scoring.
  * mm_rowwise_dot: inference scorer  s[b] = sum_d q[b,d]*i[b,d]

@@ -5,6 +5,8 @@ execution is a handful of fused kernel launches (models_b200.ops), not a Keras l
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence, Union
 
 import torch
@@ -35,6 +37,20 @@ def _use_tc() -> bool:
     return _DENSE_ENGINE[0] in ("auto", "tc")
 
 
+_MLP_FUSION = [os.environ.get("MM_MLP_FUSION", "1") != "0"]
+_LAST_PATH = ["none"]
+
+
+def set_mlp_fusion(on: bool) -> None:
+    """Whole-tower kernel (mm_mlp_tc) for towers whose widths are all <= 128; off = one launch per layer."""
+    _MLP_FUSION[0] = bool(on)
+
+
+def last_dense_path() -> str:
+    """"mlp_tc" | "dense_tc" | "fp32": which kernels the most recent run_dense_chain used (tests / notes)."""
+    return _LAST_PATH[0]
+
+
 def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: Optional[torch.Tensor] = None,
                     K: Optional[int] = None) -> torch.Tensor:
     """A chain of Dense layers on one input matrix.
@@ -56,6 +72,7 @@ def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: 
             raise ValueError("the fp32 dense engine needs an fp32 input")
         for l in layers:
             x = l(x)
+        _LAST_PATH[0] = "fp32"
         return x
     if a_split is None:
         a = ops.split_rows(x)
@@ -66,6 +83,23 @@ def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: 
                  and layers[-1].input_dim == layers[-2].units)
     if fuse_head:
         head, layers = layers[-1], layers[:-1]
+    if K != layers[0].input_dim:
+        raise ValueError(f"{layers[0].name}: input width {K} != kernel rows {layers[0].input_dim}")
+    widths = [l.units for l in layers]
+    if _MLP_FUSION[0] and ops.mlp_tc_supported(K, widths, head=fuse_head):
+        # whole tower in one launch: layers 2..n run on chip, activations stay in tensor memory
+        _LAST_PATH[0] = "mlp_tc"
+        kw = {}
+        if fuse_head:
+            out = torch.empty((B, 1), dtype=torch.float32, device=device)
+            kw = dict(head_w=head.kernel.reshape(-1), head_b=head.bias_value(), head_act=head.activation, head_out=out)
+        else:
+            out = torch.empty((B, widths[-1]), dtype=torch.float32, device=device)
+            kw = dict(out=out)
+        ops.mlp_tc(a, K, [l.split_kernel() for l in layers], widths, [l.bias for l in layers],
+                   [l.activation for l in layers], **kw)
+        return out
+    _LAST_PATH[0] = "dense_tc"
     for i, l in enumerate(layers):
         last = i == len(layers) - 1
         if K != l.input_dim:

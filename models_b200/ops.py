@@ -398,6 +398,60 @@ def catalog_score(q: torch.Tensor, e_split: torch.Tensor, n_items: int, bias: Op
     return stats, scores, ids
 
 
+def mlp_tc_supported(K: int, widths: Sequence[int], head: bool = False) -> bool:
+    """True when mm_mlp_tc can run the tower (mm_mlp_tc_supported): 2..4 layers, every width <= 128, head only
+    after <= 32 units, resident weights of layers 2..n + two layer-1 pipeline stages within shared memory."""
+    n = len(widths)
+    if n < 2 or n > 4:
+        return False
+    wd = (C.c_int * n)(*[int(w) for w in widths])
+    return bool(_lib().mm_mlp_tc_supported(int(K), n, wd, 1 if head else 0))
+
+
+def mlp_tc(a_split: torch.Tensor, K: int, w_splits: Sequence[torch.Tensor], widths: Sequence[int],
+           biases: Sequence[Optional[torch.Tensor]], acts: Sequence[Optional[str]], out: Optional[torch.Tensor] = None,
+           head_w: Optional[torch.Tensor] = None, head_b: float = 0.0, head_act: Optional[str] = None,
+           head_out: Optional[torch.Tensor] = None):
+    """Whole MLP tower in one launch (mm_mlp_tc): layer 1 from the split-bf16 rows `a_split`, layers 2..n on
+    chip (activations stay in tensor memory).  out: (M, widths[-1]) fp32 and/or head_out: (M, 1)."""
+    n = len(widths)
+    if not (len(w_splits) == len(biases) == len(acts) == n):
+        raise ValueError("mlp_tc: w_splits / widths / biases / acts must have one entry per layer")
+    _dev(a_split, "a_split", torch.bfloat16)
+    M = a_split.shape[0]
+    if a_split.dim() != 2 or a_split.shape[1] != 2 * tc_padded_k(K) or not a_split.is_contiguous():
+        raise ValueError(f"a_split must be a contiguous (M, {2 * tc_padded_k(K)}) bf16 matrix")
+    k = K
+    for l in range(n):
+        _dev(w_splits[l], f"w_split[{l}]", torch.bfloat16)
+        if tuple(w_splits[l].shape) != (tc_padded_n(int(widths[l])), 2 * tc_padded_k(k)) or not w_splits[l].is_contiguous():
+            raise ValueError(f"w_split[{l}] must be the mm_split_weights layout of a ({k}, {widths[l]}) kernel")
+        if biases[l] is not None:
+            _dev(biases[l], f"bias[{l}]", torch.float32)
+            if biases[l].numel() != int(widths[l]):
+                raise ValueError(f"bias[{l}] must hold {widths[l]} values")
+        k = int(widths[l])
+    if out is not None:
+        _dev(out, "out", torch.float32)
+        if out.dim() != 2 or tuple(out.shape) != (M, int(widths[-1])) or out.stride(1) != 1:
+            raise ValueError(f"out must be ({M}, {widths[-1]}) fp32 with unit column stride")
+    if (head_w is None) != (head_out is None):
+        raise ValueError("head_w and head_out go together")
+    if head_w is not None:
+        _dev(head_w, "head_w", torch.float32), _dev(head_out, "head_out", torch.float32)
+        if head_w.numel() != int(widths[-1]) or not head_w.is_contiguous() or head_out.numel() != M or not head_out.is_contiguous():
+            raise ValueError("head_w must hold widths[-1] weights and head_out M contiguous values")
+    wp = (C.c_void_p * n)(*[w.data_ptr() for w in w_splits])
+    bp = (C.c_void_p * n)(*[_ptr(b) for b in biases])
+    wd = (C.c_int * n)(*[int(w) for w in widths])
+    ac = (C.c_int * n)(*[ACTIVATIONS[a] for a in acts])
+    _cabi.check(
+        _lib().mm_mlp_tc(a_split.data_ptr(), M, K, n, wp, wd, bp, ac, _ptr(out), out.stride(0) if out is not None else 0,
+                         _ptr(head_w), float(head_b), ACTIVATIONS[head_act], _ptr(head_out), _stream()),
+        "mm_mlp_tc")
+    return out if out is not None else head_out
+
+
 def dense_tc_head(a_split: torch.Tensor, K: int, w_split: torch.Tensor, N: int, bias: Optional[torch.Tensor],
                   act: Optional[str], head_w: torch.Tensor, head_b: float, head_act: Optional[str],
                   out: torch.Tensor, passes: int = 3) -> torch.Tensor:

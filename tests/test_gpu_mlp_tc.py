@@ -1,0 +1,147 @@
+"""Whole-tower MLP kernel (mm_mlp_tc: layer 1 TMA-fed tcgen05, layers 2..n on chip with the A operand
+in tensor memory) against the fp64 NumPy chain of oracle.dense — the reference's MLPBlock
+(merlin/models/tf/blocks/mlp.py:97-139) + BinaryOutput Dense(1) (outputs/classification.py:114).
+Tolerance: 5e-5 of the output scale per layer (3-pass split-bf16), 20x inside the north-star 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+import models_b200 as mm
+from models_b200 import blocks, ops
+from oracle import oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def _tower(rng, K, widths):
+    Ws, bs, k = [], [], K
+    for n in widths:
+        Ws.append((rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32))
+        bs.append((rng.standard_normal(n) * 0.1).astype(np.float32))
+        k = n
+    return Ws, bs
+
+
+def _oracle_chain(x, Ws, bs, acts):
+    for W, b, a in zip(Ws, bs, acts):
+        x = oracle.dense(x, W, b, a)
+    return x
+
+
+@pytest.mark.parametrize("M,K,widths", [
+    (65536 // 16, 415, [128, 64, 32]),      # README top tower
+    (1000, 13, [128, 64]),                  # README bottom tower
+    (777, 415, [128, 64]),
+    (129, 69, [32, 128, 64, 128]),          # wide chain: A and D regions of TMEM full, 96 KB of resident weights
+    (5, 200, [100, 50, 20]),                # widths that are not multiples of 16 / 32
+    (300, 64, [16, 16]),
+    (4096, 129, [96, 48, 112, 8]),
+])
+@pytest.mark.parametrize("acts", ["relu", "mixed"])
+def test_mlp_tc_matches_oracle_chain(device, M, K, widths, acts):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    Ws, bs = _tower(rng, K, widths)
+    names = ["relu"] * len(widths) if acts == "relu" else (["tanh", "relu", "sigmoid", "linear"] * 2)[: len(widths)]
+    a = ops.split_rows(dev(x, device))
+    out = torch.full((M, widths[-1]), 7.0, dtype=torch.float32, device=device)
+    ops.mlp_tc(a, K, [ops.split_weights(dev(W, device)) for W in Ws], widths, [dev(b, device) for b in bs], names, out=out)
+    ref = _oracle_chain(x, Ws, bs, names)
+    assert H.rel_err(out.cpu().numpy(), ref) < 5e-5 * len(widths)
+
+
+@pytest.mark.parametrize("head_act", ["sigmoid", "linear"])
+@pytest.mark.parametrize("widths", [[128, 64, 32], [64, 16], [128, 24]])
+def test_mlp_tc_fused_head(device, widths, head_act):
+    rng = np.random.default_rng(12)
+    M, K = 3000, 415
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    Ws, bs = _tower(rng, K, widths)
+    hw = (rng.standard_normal((widths[-1], 1)) / np.sqrt(widths[-1])).astype(np.float32)
+    hb = np.float32(0.25)
+    a = ops.split_rows(dev(x, device))
+    w = [ops.split_weights(dev(W, device)) for W in Ws]
+    b = [dev(v, device) for v in bs]
+    acts = ["relu"] * len(widths)
+    head_out = torch.empty((M, 1), dtype=torch.float32, device=device)
+    body = torch.empty((M, widths[-1]), dtype=torch.float32, device=device)
+    ops.mlp_tc(a, K, w, widths, b, acts, out=body, head_w=dev(hw.reshape(-1), device), head_b=float(hb), head_act=head_act,
+               head_out=head_out)
+    h = _oracle_chain(x, Ws, bs, acts)
+    assert H.rel_err(body.cpu().numpy(), h) < 2e-4
+    ref = oracle.dense(h, hw, np.array([hb], np.float32), head_act)
+    assert H.rel_err(head_out.cpu().numpy(), ref) < 2e-4
+    only_head = torch.empty((M, 1), dtype=torch.float32, device=device)
+    ops.mlp_tc(a, K, w, widths, b, acts, head_w=dev(hw.reshape(-1), device), head_b=float(hb), head_act=head_act,
+               head_out=only_head)
+    assert torch.equal(only_head, head_out)
+
+
+def test_mlp_tc_equals_layer_by_layer_tc(device):
+    """Same arithmetic as the per-layer mm_dense_tc chain (3-pass split-bf16, fp32 accumulate): the
+    fused tower must agree with it to the last few ulps, on many tiles (persistent CTAs wrap around)."""
+    rng = np.random.default_rng(13)
+    M, K, widths = 148 * 128 * 2 + 77, 415, [128, 64, 32]
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    Ws, bs = _tower(rng, K, widths)
+    a = ops.split_rows(dev(x, device))
+    w = [ops.split_weights(dev(W, device)) for W in Ws]
+    b = [dev(v, device) for v in bs]
+    fused = torch.empty((M, 32), dtype=torch.float32, device=device)
+    ops.mlp_tc(a, K, w, widths, b, ["relu"] * 3, out=fused)
+    cur, k = a, K
+    for i, n in enumerate(widths):
+        last = i == len(widths) - 1
+        nxt = None if last else torch.zeros((M, 2 * ops.tc_padded_k(n)), dtype=torch.bfloat16, device=device)
+        o = torch.empty((M, n), dtype=torch.float32, device=device) if last else None
+        ops.dense_tc(cur, k, w[i], n, b[i], "relu", passes=3, out_f32=o, out_split=nxt)
+        cur, k = nxt, n
+    # same operands, different accumulation order of the three passes: a few fp32 ulps per layer
+    diff = float((fused - o).abs().max())
+    assert diff < 2e-5, diff
+    again = torch.empty_like(fused)
+    ops.mlp_tc(a, K, w, widths, b, ["relu"] * 3, out=again)
+    assert torch.equal(again, fused)  # deterministic
+
+
+def test_mlp_block_uses_fused_tower_and_matches_fp32_engine(device):
+    rng = np.random.default_rng(14)
+    x = dev(rng.standard_normal((2049, 415)).astype(np.float32), device)
+    mm.set_seed(5)
+    mlp = mm.MLPBlock([128, 64, 32])
+    got = mlp(x)
+    assert blocks.last_dense_path() == "mlp_tc"
+    blocks.set_dense_engine("fp32")
+    try:
+        ref = mlp(x)
+    finally:
+        blocks.set_dense_engine("auto")
+    assert H.rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 2e-4
+    wide = mm.MLPBlock([256, 64])  # first width > 128: layer-by-layer path
+    wide(x)
+    assert blocks.last_dense_path() == "dense_tc"
+
+
+def test_mlp_tc_argument_errors(device):
+    a = ops.split_rows(torch.zeros((8, 13), device=device))
+    w1 = ops.split_weights(torch.zeros((13, 128), device=device))
+    w2 = ops.split_weights(torch.zeros((128, 64), device=device))
+    out = torch.empty((8, 64), device=device)
+    with pytest.raises(ValueError):
+        ops.mlp_tc(a, 13, [w1, w2], [128, 64], [None], ["relu", "relu"], out=out)
+    with pytest.raises(ValueError):
+        ops.mlp_tc(a, 13, [w1, w1], [128, 64], [None, None], ["relu", "relu"], out=out)  # wrong layout for layer 2
+    with pytest.raises(ValueError, match="no output"):
+        ops.mlp_tc(a, 13, [w1, w2], [128, 64], [None, None], ["relu", "relu"])
+    assert not ops.mlp_tc_supported(13, [256, 64]) and not ops.mlp_tc_supported(13, [128])
+    assert ops.mlp_tc_supported(415, [128, 64, 32], head=True) and not ops.mlp_tc_supported(415, [128, 64], head=True)
+    assert not ops.mlp_tc_supported(69, [128, 128, 128, 128])  # 192 KB of resident weights do not fit
+    with pytest.raises(ValueError, match="does not fit"):
+        w = ops.split_weights(torch.zeros((128, 128), device=device))
+        ops.mlp_tc(ops.split_rows(torch.zeros((8, 128), device=device)), 128, [w] * 4, [128] * 4, [None] * 4, ["relu"] * 4,
+                   out=torch.empty((8, 128), device=device))

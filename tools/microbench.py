@@ -143,6 +143,45 @@ def main():
             report(f"mm_dense_tc {K}->{N} (3-pass split-bf16, split out)", m, mn, flops=2.0 * B * K * N * 3,
                    bytes_=B * (2 * ops.tc_padded_k(K) * 2 + 2 * ops.tc_padded_k(N) * 2), logical_flops=2.0 * B * K * N)
 
+    if "mlp" in only:
+        # README towers: whole-tower kernel (mm_mlp_tc) vs the per-layer tcgen05 chain (mm_dense_tc)
+        for K, widths, head in ((415, [128, 64, 32], True), (13, [128, 64], False)):
+            x = torch.randn((B, K), device=dev)
+            Ws = [torch.randn((k, n), device=dev) / (k ** 0.5) for k, n in zip([K] + widths[:-1], widths)]
+            bs = [torch.zeros(n, device=dev) for n in widths]
+            ws = [ops.split_weights(W) for W in Ws]
+            a = ops.split_rows(x)
+            hw = torch.randn(widths[-1], device=dev)
+            out = torch.empty((B, 1 if head else widths[-1]), device=dev)
+            acts = ["relu"] * len(widths)
+            io_bytes = B * (2 * ops.tc_padded_k(K) * 2 + out.shape[1] * 4)
+
+            def fused(i):
+                if head:
+                    ops.mlp_tc(a, K, ws, widths, bs, acts, head_w=hw, head_b=0.1, head_act="sigmoid", head_out=out)
+                else:
+                    ops.mlp_tc(a, K, ws, widths, bs, acts, out=out)
+
+            bufs = [torch.zeros((B, 2 * ops.tc_padded_k(n)), dtype=torch.bfloat16, device=dev) for n in widths[:-1]]
+
+            def layered(i):
+                cur, k = a, K
+                for li, n in enumerate(widths):
+                    last = li == len(widths) - 1
+                    if last and head:
+                        ops.dense_tc_head(cur, k, ws[li], n, bs[li], "relu", hw, 0.1, "sigmoid", out)
+                    elif last:
+                        ops.dense_tc(cur, k, ws[li], n, bs[li], "relu", out_f32=out)
+                    else:
+                        ops.dense_tc(cur, k, ws[li], n, bs[li], "relu", out_split=bufs[li])
+                        cur, k = bufs[li], n
+
+            name = f"{K}->" + "->".join(map(str, widths)) + ("->1" if head else "")
+            m, mn = timeit(fused, args.iters)
+            report(f"mm_mlp_tc {name} (one launch)", m, mn, bytes_=io_bytes)
+            m, mn = timeit(layered, args.iters)
+            report(f"mm_dense_tc chain {name} ({len(widths)} launches)", m, mn, bytes_=io_bytes)
+
     if "models" in only:
         mm.set_seed(1)
         # config 5: DCN-v2, bundled Criteo, inferred dims (d = 1037), depth 3, deep [256, 128]
