@@ -124,6 +124,13 @@ typedef struct {
 int mm_concat_columns(const mm_concat_piece* pieces_host, int n_pieces, int64_t B, float* out,
                       int64_t out_stride, void* stream);
 
+/* mm_concat_columns fused with mm_split_rows: the concatenated row leaves directly as the
+ * split-bf16 operand (B, 2*Kp) [hi | lo] of mm_dense_tc / mm_mlp_tc, zero padded to Kp
+ * (ConcatFeatures core/aggregation.py:54-66 feeding the first Dense of an MLPBlock, blocks/mlp.py:275-277).
+ * Pieces as above (out_col + width <= Kp, at most 64 pieces, Kp <= 320). */
+int mm_concat_split(const mm_concat_piece* pieces_host, int n_pieces, int64_t B, void* out_split, int Kp,
+                    void* stream);
+
 /* L2Norm (transforms/regularization.py:27-82): x / sqrt(max(sum(x^2, -1), 1e-12)); in place ok */
 int mm_l2_normalize(const float* x, int64_t B, int D, int64_t x_stride, float* out,
                     int64_t out_stride, void* stream);

@@ -240,6 +240,11 @@ class MLP(SequentialBlock):
         if isinstance(x, dict):
             if self.filter_names is not None:
                 x = {k: v for k, v in x.items() if k in self.filter_names}
+            pieces = [x[k] for k in sorted(x)]
+            if _use_tc() and ops.concat_split_supported(pieces) and batch_size_of(x) > 0:
+                # ConcatFeatures straight into the split-bf16 operand of the first tensor-core layer
+                a, K = ops.concat_split(pieces)
+                return run_dense_chain(None, self.dense_layers, a_split=a, K=K)
             x = concat_sorted(x)
         return run_dense_chain(x, self.dense_layers)
 

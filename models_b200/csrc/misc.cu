@@ -1,6 +1,8 @@
 // Column concat (+cast to fp32) and row-wise L2 normalisation.
 // Replaces ConcatFeatures (merlin/models/tf/core/aggregation.py:54-66), ContinuousFeatures'
 // expand_dims (inputs/continuous.py:134-138) and L2Norm (transforms/regularization.py:27-82).
+#include <cuda_bf16.h>
+
 #include <cstring>
 
 #include "mm_common.cuh"
@@ -60,6 +62,46 @@ __global__ void concat_columns_kernel(const __grid_constant__ ConcatParams cp, l
   }
 }
 
+// Concat fused with the bf16 split of the tensor-core dense path: same transposing read as above, but the
+// rows leave as the (B, 2*Kp) [hi | lo] operand of mm_dense_tc / mm_mlp_tc (zero padded to Kp), so the
+// fp32 (B, W) matrix never exists.  Pieces sit at their out_col offsets inside the row.
+__global__ void concat_split_kernel(const __grid_constant__ ConcatParams cp, long long B,
+                                    __nv_bfloat16* __restrict__ out, int Kp) {
+  extern __shared__ float tile[];  // [32][Kp+1], zero outside the pieces
+  const long long b0 = (long long)blockIdx.x * 32;
+  const int ld = Kp + 1;
+  for (int e = threadIdx.x; e < 32 * ld; e += blockDim.x) tile[e] = 0.0f;
+  __syncthreads();
+  const int W = cp.total_width;
+  for (int e = threadIdx.x; e < W * 32; e += blockDim.x) {
+    const int r = e & 31, c = e >> 5;
+    int pi = 0, base = 0;
+    while (pi < cp.n - 1 && c >= base + cp.p[pi].width) {
+      base += cp.p[pi].width;
+      ++pi;
+    }
+    const long long b = b0 + r;
+    if (b < B) tile[r * ld + cp.p[pi].out_col + (c - base)] = load_as_f32(cp.p[pi].src, b * cp.p[pi].src_stride + (c - base), cp.p[pi].dtype);
+  }
+  __syncthreads();
+  const int groups = Kp >> 3;  // 8 bf16 = 16 bytes per store
+  for (int e = threadIdx.x; e < 32 * groups; e += blockDim.x) {
+    const int g = e % groups, r = e / groups;
+    const long long b = b0 + r;
+    if (b >= B) continue;
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = tile[r * ld + g * 8 + j];
+      h[j] = __float2bfloat16_rn(v);
+      l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
+    }
+    __nv_bfloat16* o = out + b * (2ll * Kp) + g * 8;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(o + Kp) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
 __global__ void l2_normalize_kernel(const float* __restrict__ x, long long B, int D, long long x_stride,
                                     float* __restrict__ out, long long out_stride) {
   const int lane = threadIdx.x & 31;
@@ -110,6 +152,31 @@ int mm_concat_columns(const mm_concat_piece* pieces_host, int n_pieces, int64_t 
     if (rc) return rc;
   }
   return MM_OK;
+}
+
+int mm_concat_split(const mm_concat_piece* pieces_host, int n_pieces, int64_t B, void* out_split, int Kp,
+                    void* stream) {
+  MM_REQUIRE(pieces_host && out_split && n_pieces > 0 && B >= 0, MM_ERR_ARG, "mm_concat_split: null pointer or no pieces");
+  MM_REQUIRE(n_pieces <= mm::MAX_PIECES, MM_ERR_UNSUPPORTED, "mm_concat_split: more than %d pieces", mm::MAX_PIECES);
+  MM_REQUIRE(Kp > 0 && Kp % 64 == 0, MM_ERR_ARG, "mm_concat_split: Kp must be a positive multiple of 64");
+  MM_REQUIRE(((uintptr_t)out_split % 16) == 0, MM_ERR_ALIGN, "mm_concat_split: out_split must be 16-B aligned");
+  if (B == 0) return MM_OK;
+  mm::ConcatParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.n = n_pieces;
+  for (int i = 0; i < n_pieces; ++i) {
+    const mm_concat_piece& pc = pieces_host[i];
+    MM_REQUIRE(pc.src && pc.width > 0 && pc.src_stride >= 0 && pc.out_col >= 0 && (int64_t)pc.out_col + pc.width <= Kp,
+               MM_ERR_ARG, "mm_concat_split: piece %d: null src, bad width or beyond Kp", i);
+    MM_REQUIRE(pc.dtype >= MM_I32 && pc.dtype <= MM_F64, MM_ERR_ARG, "mm_concat_split: piece %d: unknown dtype %d", i, pc.dtype);
+    cp.p[i] = pc;
+    cp.total_width += pc.width;
+  }
+  const size_t smem = (size_t)32 * (Kp + 1) * sizeof(float);
+  MM_REQUIRE(smem <= 48 * 1024, MM_ERR_UNSUPPORTED, "mm_concat_split: Kp = %d exceeds the 48 KB tile", Kp);
+  const unsigned blocks = (unsigned)((B + 31) / 32);
+  mm::concat_split_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(cp, B, (__nv_bfloat16*)out_split, Kp);
+  return mm::check_launch("mm_concat_split");
 }
 
 int mm_l2_normalize(const float* x, int64_t B, int D, int64_t x_stride, float* out,

@@ -15,10 +15,15 @@
 // fp32 parity: all operands are split-bf16 pairs (x = hi + lo), every layer accumulates
 // hi*lo + lo*hi + hi*hi into one fp32 TMEM accumulator (same arithmetic as mm_dense_tc, passes = 3).
 //
-// CTA = 11 warps, persistent over 128-row tiles: warp 0 TMA producer (layer-1 operands; the chain
-// weights once), warp 1 layer-1 MMA issuer, warp 2 chain MMA issuer, warps 3-10 epilogue.
-// TMEM (512 columns): D1[0] 0..127, D1[1] 128..255 (layer 1 of tile t+1 overlaps the chain of tile t),
-// chain operand A 256..383 (hi pairs at +0, lo pairs at +64), chain accumulator D 384..511.
+// CTA = 12 warps, persistent over 128-row tiles: warp 0 TMA producer (layer-1 operands; the chain
+// weights once), warp 1 layer-1 MMA issuer, warps 2-3 chain MMA issuers, warps 4-11 epilogue.
+// The chain of one tile is a serial ping-pong (epilogue -> MMA -> epilogue ...), so two tiles are kept in
+// flight whenever tensor memory allows it:
+//   dual mode (every chain width <= 64): D1 0..127 (single buffer), two chain sets s = 0, 1 with operand
+//     A_s at 128 + 192 s (hi pairs +0, lo pairs +64) and accumulator D_s at A_s + 128; epilogue group s
+//     (4 warps, one per TMEM lane quarter) and chain issuer s own the tiles with local index = s mod 2;
+//   single mode (a chain width > 64): D1[0] 0..127, D1[1] 128..255, A 256..383, D 384..511, all eight
+//     epilogue warps on every tile (two per lane quarter, interleaved over 32-column chunks).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -38,11 +43,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (3 + kEpiWarps);
+constexpr int kThreads = 32 * (4 + kEpiWarps);
 constexpr int kMaxChain = 3;
 constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr uint32_t EPI_STAGE_BYTES = 32 * 36 * 4;         // per epilogue warp: 32 x 32 fp32 transpose tile (+4 pad)
-constexpr uint32_t COL_D1 = 0, COL_A = 256, COL_A_LO = 64, COL_D = 384;
+constexpr uint32_t COL_A_LO = 64;  // lo pairs sit 64 columns after the hi pairs inside a chain operand region
 
 struct ChainLayer {
   int N, Np;        // true / padded (multiple of 16) width of this layer
@@ -54,7 +59,7 @@ struct ChainLayer {
 
 struct Params {
   long long M;
-  int K1p, N1, N1p, act1, stages, n_chain;
+  int K1p, N1, N1p, act1, stages, n_chain, dual;
   ChainLayer c[kMaxChain];
   const float* bias[kMaxChain + 1];  // layer 1, chain layers
   uint32_t w_bytes;                  // total resident weight bytes
@@ -64,7 +69,6 @@ struct Params {
   float head_b;
   int head_act;
   float* head_out;
-  int dbg;
   long long* trace;  // MM_MLP_TRACE=1: CTA 0 logs (tag, clock64) pairs here (debug only)
 };
 
@@ -123,11 +127,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* empty_bar = bars + p.stages;            // [stages]
   uint64_t* d1_full = bars + 2 * p.stages;          // [2] tcgen05.commit of layer 1
   uint64_t* d1_empty = bars + 2 * p.stages + 2;     // [2] count kEpiWarps
-  uint64_t* a_full = bars + 2 * p.stages + 4;       // chain operand written (count kEpiWarps)
-  uint64_t* d_full = bars + 2 * p.stages + 5;       // chain accumulator complete (tcgen05.commit)
-  uint64_t* w_full = bars + 2 * p.stages + 6;       // resident weights landed
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 7);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * p.stages + 8);  // [kMaxChain + 1][128], zero padded
+  uint64_t* a_full = bars + 2 * p.stages + 4;       // [2] chain operand of set s written (count = warps of a group)
+  uint64_t* d_full = bars + 2 * p.stages + 6;       // [2] chain accumulator of set s complete (tcgen05.commit)
+  uint64_t* w_full = bars + 2 * p.stages + 8;       // resident weights landed
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 9);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * p.stages + 10);  // [kMaxChain + 1][128], zero padded
   float* head_s = bias_s + (kMaxChain + 1) * 128;                     // [32], zero padded
   uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(head_s + 32);     // kEpiWarps x EPI_STAGE_BYTES
 
@@ -142,12 +146,13 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_init(smem_u32(full_bar + s), 1);
       mbar_init(smem_u32(empty_bar + s), 1);
     }
+    const uint32_t group_warps = p.dual ? kEpiWarps / 2 : kEpiWarps;
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(d1_full + a), 1);
-      mbar_init(smem_u32(d1_empty + a), kEpiWarps);
+      mbar_init(smem_u32(d1_empty + a), group_warps);
+      mbar_init(smem_u32(a_full + a), group_warps);
+      mbar_init(smem_u32(d_full + a), 1);
     }
-    mbar_init(smem_u32(a_full), kEpiWarps);
-    mbar_init(smem_u32(d_full), 1);
     mbar_init(smem_u32(w_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -212,13 +217,17 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const uint32_t idesc = make_idesc(BLOCK_M, p.N1p);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(d1_empty + acc), acc_phase ^ 1);
+      long long it = 0;  // local tile index; barrier pair index = it & 1, use count = it >> 1
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int acc = (int)(it & 1);
+        if (p.dual) {  // one D1 buffer: wait until the previous tile's first epilogue has drained it
+          if (it > 0) mbar_wait(smem_u32(d1_empty + ((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));
+        } else {       // two D1 buffers: wait for the drain of tile it - 2
+          mbar_wait(smem_u32(d1_empty + acc), (uint32_t)(((it >> 1) & 1) ^ 1));
+        }
         tcgen05_fence_after();
         trace_event(p, 100);
-        const uint32_t d_tmem = tmem_base + COL_D1 + (uint32_t)(acc * 128);
+        const uint32_t d_tmem = tmem_base + (p.dual ? 0u : (uint32_t)(acc * 128));
         uint32_t accumulate = 0;
         for (int kb = 0; kb < KB; ++kb) {
           // hi slot: the dominant hi*hi product starts as soon as it lands
@@ -255,22 +264,22 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         tcgen05_commit(smem_u32(d1_full + acc));
         trace_event(p, 200);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == 2 || warp == 3) {
     // ===================== chain MMA issuer (A operand in TMEM, weights resident in smem) =====================
-    if (lane == 0 && p.n_chain > 0) {
+    const int set = warp - 2;  // dual mode: issuer of chain set `set`; single mode: warp 2 serves every tile
+    if (lane == 0 && p.n_chain > 0 && (p.dual || set == 0)) {
       mbar_wait(smem_u32(w_full), 0);
       uint32_t a_phase = 0;
-      const uint32_t a_hi = tmem_base + COL_A, a_lo = tmem_base + COL_A + COL_A_LO, d_tmem = tmem_base + COL_D;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const uint32_t col_a = p.dual ? 128u + 192u * (uint32_t)set : 256u;
+      const uint32_t a_hi = tmem_base + col_a, a_lo = a_hi + COL_A_LO, d_tmem = a_hi + 128;
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        if (p.dual && (it & 1) != set) continue;
         for (int c = 0; c < p.n_chain; ++c) {
           const ChainLayer& L = p.c[c];
-          mbar_wait(smem_u32(a_full), a_phase);
+          mbar_wait(smem_u32(a_full + set), a_phase);
           a_phase ^= 1;
           tcgen05_fence_after();
           trace_event(p, 300 + c);
@@ -279,33 +288,36 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t w_hi = smem_u32(wres + L.w_off), w_lo = w_hi + (uint32_t)(L.Kp / BLOCK_K) * tile_b;
           uint32_t accumulate = 0;
           // a k-step covers 16 K elements = 8 packed TMEM columns of A and 32 bytes of a weight row
-          if (!(p.dbg & 1))
           for (int ks = 0; ks < L.ksteps; ++ks) {
             umma_bf16_ts(d_tmem, a_hi + ks * 8, make_desc_sw128(w_lo + (ks >> 2) * tile_b + (ks & 3) * 32), idesc, accumulate);
             accumulate = 1;
           }
-          if (!(p.dbg & 1))
           for (int ks = 0; ks < L.ksteps; ++ks)
             umma_bf16_ts(d_tmem, a_lo + ks * 8, make_desc_sw128(w_hi + (ks >> 2) * tile_b + (ks & 3) * 32), idesc, 1);
-          if (!(p.dbg & 2))
           for (int ks = 0; ks < L.ksteps; ++ks)
             umma_bf16_ts(d_tmem, a_hi + ks * 8, make_desc_sw128(w_hi + (ks >> 2) * tile_b + (ks & 3) * 32), idesc, 1);
-          tcgen05_commit(smem_u32(d_full));
+          tcgen05_commit(smem_u32(d_full + set));
         }
       }
     }
   } else {
     // ===================== epilogue warps (3..10) =====================
-    const int e = warp - 3;
-    const int q = warp & 3;   // TMEM lane quarter this warp may access
-    const int half = e >> 2;  // which interleaved set of 32-column chunks
+    const int e = warp - 4;
+    const int q = warp & 3;    // TMEM lane quarter this warp may access
+    const int group = e >> 2;  // dual: owns the tiles with local index = group mod 2; single: chunk interleave
+    const int half = p.dual ? 0 : group, chunk_step = p.dual ? 1 : 2;
+    const int set = p.dual ? group : 0;
+    const uint32_t col_a = p.dual ? 128u + 192u * (uint32_t)set : 256u;
     float* stg_f = reinterpret_cast<float*>(stage_tiles + (size_t)e * EPI_STAGE_BYTES);
     const bool vec_f32 = p.out_f32 && ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    int acc = 0;
-    uint32_t acc_phase = 0, d_phase = 0;
+    uint32_t d_phase = 0;
+    long long it = 0;
 
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      if (p.dual && (it & 1) != group) continue;
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const long long row0 = tile * BLOCK_M + q * 32;
       for (int layer = 0; layer <= p.n_chain; ++layer) {
         const bool last = layer == p.n_chain;
@@ -316,16 +328,16 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint32_t src;
         if (layer == 0) {
           mbar_wait(smem_u32(d1_full + acc), acc_phase);
-          src = lane_base + COL_D1 + (uint32_t)(acc * 128);
+          src = lane_base + (p.dual ? 0u : (uint32_t)(acc * 128));
         } else {
-          mbar_wait(smem_u32(d_full), d_phase);
+          mbar_wait(smem_u32(d_full + set), d_phase);
           d_phase ^= 1;
-          src = lane_base + COL_D;
+          src = lane_base + col_a + 128;
         }
         tcgen05_fence_after();
-        if (e == 0) trace_event(p, 400 + layer);
+        if ((e & 3) == 0) trace_event(p, (e ? 450 : 400) + layer);
         const int n_chunks = (Np + 31) >> 5;
-        for (int ch = half; ch < n_chunks; ch += 2) {
+        for (int ch = half; ch < n_chunks; ch += chunk_step) {
           const int c0 = ch << 5;
           const int ncols = min(32, Np - c0);  // Np is a multiple of 16
           uint32_t r[32];
@@ -349,11 +361,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               if (c0 + j >= N) v[j] = 0.0f;
           }
           if (!last) {
-            // next layer's A operand: packed bf16 pairs, hi at COL_A + c0/2, lo 64 columns further
+            // next layer's A operand: packed bf16 pairs, hi at col_a + c0/2, lo 64 columns further
             uint32_t h[16], l[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], h[j], l[j]);
-            const uint32_t dst = lane_base + COL_A + (uint32_t)(c0 >> 1);
+            const uint32_t dst = lane_base + col_a + (uint32_t)(c0 >> 1);
             if (ncols == 32) {
               tmem_st_32x32b_x16(dst, h);
               tmem_st_32x32b_x16(dst + COL_A_LO, l);
@@ -403,7 +415,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         // all of this warp's TMEM reads of the layer's accumulator are done
         tcgen05_fence_before();
-        if (e == 0) trace_event(p, 500 + layer);
+        if ((e & 3) == 0) trace_event(p, (e ? 550 : 500) + layer);
         if (layer == 0) {
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(d1_empty + acc));
@@ -412,12 +424,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tmem_st_wait();
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(a_full));
+          if (lane == 0) mbar_arrive(smem_u32(a_full + set));
         }
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
   }
@@ -455,18 +463,24 @@ static bool plan_tower(int K, int n_layers, const int* widths, bool fp32_rows, m
     prev_n = L.N;
   }
   p.w_bytes = w_off;
+  // Two chain sets (two tiles in flight) cost the second layer-1 accumulator: measured SLOWER on the README
+  // towers (top 41 -> 46.5 us, bottom 29.6 -> 30.4 us: the next tile's layer 1 then waits for the first
+  // epilogue of the previous one), so the mode is opt-in (MM_MLP_DUAL=1) and kept for narrow/deep towers.
+  p.dual = p.n_chain > 0 && getenv("MM_MLP_DUAL") && getenv("MM_MLP_DUAL")[0] == '1';
+  for (int c = 0; c < p.n_chain; ++c)
+    if (p.c[c].Np > 64) p.dual = 0;  // two chain sets only fit when every chain accumulator is <= 64 columns
   // ring slot = one half ({A_hi, W_hi} or {A_lo, W_lo}) of a k-block; the fp32 transpose tiles of the
   // epilogue are only carved when fp32 rows are written (the head-only top tower gets a deeper ring)
   const size_t stage_bytes = (size_t)A_TILE_BYTES + (size_t)p.N1p * BLOCK_K * 2;
   const size_t epi = fp32_rows ? (size_t)kEpiWarps * EPI_STAGE_BYTES : 0;
-  const size_t fixed = 1024 + (size_t)p.w_bytes + 32 * sizeof(uint64_t) + ((kMaxChain + 1) * 128 + 32) * sizeof(float) + epi;
+  const size_t fixed = 1024 + (size_t)p.w_bytes + 40 * sizeof(uint64_t) + ((kMaxChain + 1) * 128 + 32) * sizeof(float) + epi;
   if (fixed + 4 * stage_bytes > 227 * 1024) return false;
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > 12) stages = 12;
   const int kb1 = p.K1p / BLOCK_K;
   if (stages > 4 * kb1) stages = 4 * kb1 > 4 ? 4 * kb1 : 4;
   p.stages = stages;
-  smem = 1024 + stages * stage_bytes + p.w_bytes + (2 * stages + 8) * sizeof(uint64_t) +
+  smem = 1024 + stages * stage_bytes + p.w_bytes + (2 * stages + 10) * sizeof(uint64_t) +
          ((kMaxChain + 1) * 128 + 32) * sizeof(float) + epi;
   return true;
 }
@@ -520,7 +534,6 @@ int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* c
   p.head_b = head_b;
   p.head_act = head_act;
   p.head_out = head_out;
-  { const char* e = getenv("MM_MLP_DBG"); p.dbg = e ? atoi(e) : 0; }
 
   CUtensorMap tmA, tmW1, tmC[kMaxChain];
   int rc = mm::tc::make_map(&tmA, a_split, (uint64_t)M, (uint64_t)2 * p.K1p, BLOCK_M);

@@ -298,6 +298,40 @@ def concat_columns(pieces: Sequence[torch.Tensor], out: torch.Tensor, out_cols: 
     return out
 
 
+def concat_split_supported(pieces: Sequence[torch.Tensor]) -> bool:
+    """mm_concat_split handles up to 64 pieces and 320 padded columns in one launch."""
+    width = sum(1 if t.dim() == 1 else int(t.shape[1]) for t in pieces)
+    return 0 < len(pieces) <= 64 and tc_padded_k(width) <= 320 and all(t.dtype in _CONCAT_DTYPES for t in pieces)
+
+
+def concat_split(pieces: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None):
+    """ConcatFeatures + bf16 split in one launch (mm_concat_split): returns (a_split (B, 2*Kp) bf16, K).
+    Pieces in the reference's sorted-name order; (B,) pieces count as (B,1)."""
+    flat, col = [], 0
+    B = pieces[0].shape[0]
+    for i, t in enumerate(pieces):
+        _dev(t, f"pieces[{i}]")
+        if t.dtype not in _CONCAT_DTYPES:
+            raise TypeError(f"pieces[{i}]: unsupported dtype {t.dtype}")
+        if t.dim() == 1:
+            t = t.unsqueeze(1)
+        if t.dim() != 2 or t.shape[0] != B or (t.shape[1] > 1 and t.stride(1) != 1):
+            raise ValueError(f"pieces[{i}] must be (B,) or (B,w) with unit inner stride, got {tuple(t.shape)}")
+        flat.append((t.data_ptr(), t.stride(0), int(t.shape[1]), _CONCAT_DTYPES[t.dtype], col))
+        col += int(t.shape[1])
+    K, Kp = col, tc_padded_k(col)
+    if out is None:
+        out = torch.empty((B, 2 * Kp), dtype=torch.bfloat16, device=pieces[0].device)
+    _dev(out, "out", torch.bfloat16)
+    if tuple(out.shape) != (B, 2 * Kp) or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous ({B}, {2 * Kp}) bf16 matrix")
+    arr = (_cabi.ConcatPiece * len(flat))()
+    for i, (ptr, sstride, w, dt, oc) in enumerate(flat):
+        arr[i].src, arr[i].src_stride, arr[i].width, arr[i].dtype, arr[i].out_col = ptr, sstride, w, dt, oc
+    _cabi.check(_lib().mm_concat_split(arr, len(flat), B, out.data_ptr(), Kp, _stream()), "mm_concat_split")
+    return out, K
+
+
 def l2_normalize(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _dev(x, "x", torch.float32)
     if out is None:

@@ -145,3 +145,60 @@ def test_mlp_tc_argument_errors(device):
         w = ops.split_weights(torch.zeros((128, 128), device=device))
         ops.mlp_tc(ops.split_rows(torch.zeros((8, 128), device=device)), 128, [w] * 4, [128] * 4, [None] * 4, ["relu"] * 4,
                    out=torch.empty((8, 128), device=device))
+
+
+def test_concat_split_equals_concat_then_split(device):
+    """mm_concat_split == mm_split_rows(mm_concat_columns(...)) bit for bit, mixed dtypes / widths / strides."""
+    rng = np.random.default_rng(15)
+    B = 1000
+    wide = dev(rng.standard_normal((B, 40)).astype(np.float32), device)
+    pieces = [dev(rng.standard_normal(B).astype(np.float32), device),
+              dev(rng.integers(-5, 5, B).astype(np.int64), device),
+              wide[:, 3:20],                                   # strided view, unit inner stride
+              dev(rng.standard_normal((B, 1)).astype(np.float64), device),
+              dev(rng.integers(0, 100, (B, 2)).astype(np.int32), device)]
+    a, K = ops.concat_split(pieces)
+    assert K == 1 + 1 + 17 + 1 + 2 and tuple(a.shape) == (B, 2 * 64)
+    ref = torch.empty((B, K), dtype=torch.float32, device=device)
+    ops.concat_columns(pieces, ref)
+    assert torch.equal(a, ops.split_rows(ref))
+    thirteen = [dev(rng.random(B).astype(np.float32), device) for _ in range(13)]
+    a13, K13 = ops.concat_split(thirteen)
+    ref13 = torch.empty((B, 13), dtype=torch.float32, device=device)
+    ops.concat_columns(thirteen, ref13)
+    assert K13 == 13 and torch.equal(a13, ops.split_rows(ref13))
+    assert not ops.concat_split_supported([wide] * 9)  # 360 columns > 320
+
+
+def test_mlp_block_on_feature_dict_uses_concat_split(device):
+    rng = np.random.default_rng(16)
+    feats = {f"I{i}": dev(rng.random(777).astype(np.float32), device) for i in range(1, 14)}
+    mm.set_seed(6)
+    mlp = mm.MLPBlock([128, 64])
+    got = mlp(feats)
+    assert blocks.last_dense_path() == "mlp_tc"
+    x = torch.stack([feats[k] for k in sorted(feats)], dim=1)  # ConcatFeatures order: I1, I10, ..., I13, I2, ...
+    layers = [{"kernel": l.kernel.cpu().numpy(), "bias": l.bias.cpu().numpy(), "activation": l.activation} for l in mlp.dense_layers]
+    ref = x.cpu().numpy()
+    for l in layers:
+        ref = oracle.dense(ref, l["kernel"], l["bias"], l["activation"])
+    assert H.rel_err(got.cpu().numpy(), ref) < 1e-4
+
+
+def test_mlp_tc_dual_chain_sets_match_single(device, monkeypatch):
+    """MM_MLP_DUAL=1: two tiles in flight (two chain sets in tensor memory, two epilogue groups) — same
+    arithmetic, so the result must be bit-identical to the default single-set schedule."""
+    rng = np.random.default_rng(17)
+    M, K, widths = 148 * 128 * 3 + 5, 415, [128, 64, 32]
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    Ws, bs = _tower(rng, K, widths)
+    a = ops.split_rows(dev(x, device))
+    w = [ops.split_weights(dev(W, device)) for W in Ws]
+    b = [dev(v, device) for v in bs]
+    single = torch.empty((M, 32), dtype=torch.float32, device=device)
+    ops.mlp_tc(a, K, w, widths, b, ["relu"] * 3, out=single)
+    monkeypatch.setenv("MM_MLP_DUAL", "1")
+    dual = torch.empty((M, 32), dtype=torch.float32, device=device)
+    ops.mlp_tc(a, K, w, widths, b, ["relu"] * 3, out=dual)
+    torch.cuda.synchronize()
+    assert torch.equal(single, dual)

@@ -192,7 +192,7 @@ def test_compiled_forward_matches_eager_and_checks_indices(device):
     b0, _ = datasets.split_targets(schema, datasets.generate_batch(schema, 700, seed=1, index_law="uniform"))
     b1, _ = datasets.split_targets(schema, datasets.generate_batch(schema, 700, seed=2, index_law="uniform"))
     cf = model.compile(b0)
-    assert cf.launches_per_replay >= 5
+    assert cf.launches_per_replay >= 3  # concat+split, bottom tower, gather+interaction, top tower (+head)
     for b in (b0, b1, b0):
         hb = mm.HostBatch.like(b, model.input_columns())
         got = cf(hb).clone().numpy()
