@@ -21,6 +21,7 @@ from .models import (BinaryClassificationTask, BinaryOutput, DCNModel, DLRMModel
                      RetrievalModel, TwoTowerModel)
 from .graph import CompiledForward, HostBatch, PipelinedForward  # noqa: F401
 from .sharded import ShardedEmbeddings, shard_model  # noqa: F401
-from . import datasets, ops  # noqa: F401
+from . import datasets, io, ops  # noqa: F401
+from .io import load_merlin_metadata, save_merlin_metadata  # noqa: F401
 
 __version__ = "0.1.0"

@@ -140,6 +140,13 @@ class _Dense(Block):
         self._w_split: Optional[torch.Tensor] = None
         self._split_bufs: Dict[tuple, torch.Tensor] = {}
 
+    _TRANSIENT = {"_w_split": None, "_split_bufs": {}, "_bias_host": None}
+
+    def _weights_changed(self) -> None:
+        """Variables were assigned (load_weights): drop everything derived from them."""
+        self._w_split = None
+        self._bias_host = None
+
     def split_kernel(self) -> torch.Tensor:
         """(Np, 2*Kp) split-bf16 K-major copy of the kernel for the tensor-core path (built once)."""
         if self._w_split is None:

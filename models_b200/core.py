@@ -86,6 +86,8 @@ def _generator(device, salt: str) -> torch.Generator:
 def create_variable(shape: Tuple[int, ...], initializer: InitializerType, device, name: str) -> torch.Tensor:
     shape = tuple(int(s) for s in shape)
     if isinstance(initializer, (np.ndarray, torch.Tensor)):
+        if isinstance(initializer, np.ndarray):
+            initializer = np.array(initializer, dtype=np.float32)  # private writable copy (frames can be read-only)
         t = torch.as_tensor(initializer, dtype=torch.float32)
         if tuple(t.shape) != shape:
             raise ValueError(f"{name}: initial value has shape {tuple(t.shape)}, expected {shape}")
@@ -179,9 +181,23 @@ def concat_sorted(d: TabularData, device=None) -> torch.Tensor:
 class Block:
     """Callable unit with lazily created device weights (Keras `build` on first call)."""
 
+    # attribute -> value restored when the block is pickled (models_b200/io.py): caches and device scratch
+    # derived from the variables are rebuilt on demand instead of being written to disk
+    _TRANSIENT: Dict[str, object] = {}
+
     def __init__(self, name: Optional[str] = None):
         self.name = name or unique_name(_snake(type(self).__name__))
         self.built = False
+
+    def __getstate__(self):
+        import copy as _copy
+
+        state = dict(self.__dict__)
+        for klass in type(self).__mro__:
+            for k, v in vars(klass).get("_TRANSIENT", {}).items():
+                if k in state:
+                    state[k] = _copy.copy(v)
+        return state
 
     def build(self, device=None) -> "Block":
         self.built = True

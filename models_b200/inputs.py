@@ -90,6 +90,8 @@ class EmbeddingTable(Block):
         """inputs/embedding.py:283-345 (array form): rows x dim matrix as the table."""
         import numpy as np
 
+        if hasattr(data, "to_numpy") and not isinstance(data, torch.Tensor):  # pandas / cudf DataFrame (df_to_tensor)
+            data = data.to_numpy()
         arr = data.detach().cpu().numpy() if isinstance(data, torch.Tensor) else np.asarray(data, dtype=np.float32)
         rows, dim = arr.shape
         if col_schema is None:
@@ -113,6 +115,18 @@ class EmbeddingTable(Block):
 
     def weights(self):
         return {"embeddings": self.embeddings}
+
+    def to_df(self, gpu=None):
+        """inputs/embedding.py:363-379: the table as a DataFrame with one column per embedding dimension
+        (pandas; `gpu` is accepted for signature parity — cudf is not a dependency here)."""
+        import pandas as pd
+
+        return pd.DataFrame(self.embeddings.detach().cpu().numpy())
+
+    @classmethod
+    def from_dataset(cls, data, trainable=True, name=None, col_schema=None, **kwargs) -> "EmbeddingTable":
+        """inputs/embedding.py:327-349."""
+        return cls.from_pretrained(data, col_schema=col_schema, trainable=trainable, name=name, **kwargs)
 
     # -- execution --------------------------------------------------------------------------------
     def lookup_kind(self, feat) -> str:
@@ -191,6 +205,8 @@ class EmbeddingsBlock(Block):
         self.check_indices = check_indices
         self.oob_counter: Optional[torch.Tensor] = None  # persistent device int32[1]
         self.defer_check = False  # CUDA-graph capture: the owner checks the counter after replay
+
+    _TRANSIENT = {"oob_counter": None, "defer_check": False}
 
     def counter(self, device) -> Optional[torch.Tensor]:
         if not self.check_indices:

@@ -96,9 +96,45 @@ class Model(Block):
         self.schema = schema
         self._pinned: Dict[str, torch.Tensor] = {}
 
+    _TRANSIENT = {"_pinned": {}}
+
     @property
     def blocks(self) -> List[Block]:
         return [self.body, self.prediction]
+
+    # -- checkpoint boundary (models_b200/io.py; reference: models/base.py:1687-1728) -----------
+    def save(self, export_path, include_optimizer: bool = True, save_traces: bool = True) -> None:
+        """Variables (Keras layouts, one .npy each), block structure and `.merlin` schema metadata.
+        `include_optimizer` / `save_traces` are accepted for signature parity (forward path only)."""
+        from . import io as _io
+
+        _io.save_model(self, export_path)
+
+    @classmethod
+    def load(cls, export_path, device=None) -> "Model":
+        from . import io as _io
+
+        return _io.load_model(export_path, device)
+
+    def load_weights(self, source, name_map=None, strict: bool = True):
+        """Assign variables from an export directory or a {name: array} mapping (e.g. a Keras checkpoint
+        exported as `{v.name: v.numpy()}`); see io.load_weights."""
+        from . import io as _io
+
+        return _io.load_weights(self, source, name_map=name_map, strict=strict)
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        from . import io as _io
+
+        return _io.state_dict(self)
+
+    def output_schema(self) -> Schema:
+        """One float column per prediction task (what `get_output_schema` records for the reference)."""
+        from .schema import ColumnSchema
+
+        target = getattr(self.prediction, "target", None) or getattr(self.prediction, "target_name", None)
+        name = f"{target}/{self.prediction.name}" if target else self.prediction.name
+        return Schema([ColumnSchema(name, dtype="float32")])
 
     def weights(self):
         out = {f"body/{k}": v for k, v in self.body.weights().items()}

@@ -362,9 +362,13 @@ class CategoricalOutput(Block):
             out["bias"] = self.bias
         return out
 
+    _TRANSIENT = {"_e_split": None, "_w_split": None}
+
     def refresh(self) -> None:
         """Drop the cached split-bf16 copies (call after changing the table)."""
         self._e_split = self._w_split = None
+
+    _weights_changed = refresh
 
     def _catalog_split(self) -> torch.Tensor:
         if self._e_split is None:

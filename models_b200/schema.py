@@ -243,7 +243,44 @@ class Schema:
 
     @classmethod
     def load(cls, path: str) -> "Schema":
-        return cls.from_json(path) if str(path).endswith(".json") else cls.from_proto_text(str(path))
+        return cls.from_json(str(path)) if str(path).endswith(".json") else cls.from_proto_text(str(path))
+
+    # -- writer (tensorflow-metadata JSON, merlin/models/utils/schema_utils.py schema_to_tensorflow_metadata_json) --
+    def to_json(self, path=None) -> str:
+        feats = []
+        for c in self:
+            is_int = c.dtype.startswith(("int", "uint"))
+            f = {"name": c.name, "type": "INT" if is_int else ("BYTES" if c.dtype == "str" else "FLOAT")}
+            vc = c.properties.get("value_count")
+            if c.is_list:
+                v = {}
+                if vc and vc.get("min") is not None:
+                    v["min"] = str(int(vc["min"]))
+                if vc and vc.get("max") is not None:
+                    v["max"] = str(int(vc["max"]))
+                f["valueCount"] = v
+            d = c.properties.get("domain")
+            if d is not None:
+                if is_int:
+                    dom = {"min": str(int(d.get("min", 0) or 0))}
+                    if d.get("max") is not None:
+                        dom["max"] = str(int(d["max"]))
+                    dom["isCategorical"] = "categorical" in c.tags
+                else:
+                    dom = {"min": float(d.get("min", 0) or 0)}
+                    if d.get("max") is not None:
+                        dom["max"] = float(d["max"])
+                if d.get("name") is not None:
+                    dom["name"] = d["name"]
+                f["intDomain" if is_int else "floatDomain"] = dom
+            if c.tags:
+                f["annotation"] = {"tag": list(c.tags)}
+            feats.append(f)
+        text = json.dumps({"feature": feats}, indent=2)
+        if path is not None:
+            with open(path, "w") as fh:
+                fh.write(text)
+        return text
 
 
 # ---------------------------------------------------------------------------------------------

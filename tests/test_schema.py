@@ -72,3 +72,24 @@ def test_generate_batch_follows_reference_generator():
     assert u["C6"].max() <= 3 and u["C1"].dtype.name == "int32"
     with pytest.raises(ValueError):
         datasets.generate_batch(m, 4, index_law="bogus")
+
+
+def test_schema_json_writer_round_trips(tmp_path):
+    """Schema.to_json writes the tensorflow-metadata JSON the reference stores under `.merlin/`
+    (merlin/models/io.py:26-55); reading it back gives the same columns, tags, domains and list-ness."""
+    import models_b200 as mm
+
+    for schema in (datasets.criteo_schema(), datasets.movielens_1m_schema()):
+        p = tmp_path / "input_schema.json"
+        schema.to_json(p)
+        back = mm.Schema.load(str(p))
+        assert back.column_names == schema.column_names
+        for a, b in zip(schema, back):
+            assert set(a.tags) == set(b.tags), a.name
+            assert a.is_list == b.is_list and a.is_ragged == b.is_ragged, a.name
+            assert (a.int_domain is None) == (b.int_domain is None), a.name
+            if a.int_domain is not None:
+                assert (a.int_domain.max, a.int_domain.name) == (b.int_domain.max, b.int_domain.name)
+    mm.save_merlin_metadata(tmp_path, datasets.criteo_schema(), None)
+    inp, out = mm.load_merlin_metadata(tmp_path)
+    assert inp.column_names == datasets.criteo_schema().column_names and out is None
