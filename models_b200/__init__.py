@@ -19,6 +19,8 @@ from .retrieval import (CategoricalOutput, ContrastiveOutput, InBatchSampler, In
                         ItemRetrievalTask, L2Norm, TwoTowerBlock, log_uniform_sampling_probs)
 from .models import (BinaryClassificationTask, BinaryOutput, DCNModel, DLRMModel, Model,  # noqa: F401
                      RetrievalModel, TwoTowerModel)
+from .topk import (AvgPrecisionAt, BruteForce, MRRAt, NDCGAt, PrecisionAt, RecallAt, TopKEncoder,  # noqa: F401
+                   TopKIndexBlock, TopKPrediction, encode_candidates, unique_rows_by_features)
 from .graph import CompiledForward, HostBatch, PipelinedForward  # noqa: F401
 from .sharded import ShardedEmbeddings, shard_model  # noqa: F401
 from . import datasets, io, ops  # noqa: F401

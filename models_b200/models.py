@@ -322,8 +322,16 @@ def DCNModel(schema: Schema, depth: int, deep_block: Optional[MLP] = None, stack
     return RankingModel(body, prediction, schema)
 
 
+def _brute_force(k: int):
+    from .topk import BruteForce
+
+    return BruteForce(k=k)
+
+
 class RetrievalModel(Model):
     """models/base.py:2259-2489, forward only."""
+
+    _TRANSIENT = {"pre_eval_topk": None}
 
     def build(self, device=None):
         self.body.build(device)
@@ -342,6 +350,92 @@ class RetrievalModel(Model):
             self.build(next(iter(inputs.values())).device)
         emb = self.body(inputs, training=False)
         return self.prediction(emb, features=inputs, training=training, testing=testing)
+
+    # -- top-k retrieval / evaluation (models/base.py:2266-2489) ---------------------
+    @property
+    def retrieval_block(self) -> TwoTowerBlock:
+        return self.body
+
+    def query_encoder(self) -> Block:
+        """Query tower (+ the model's `post`, e.g. L2 normalisation) as a feature-dict -> (B, D) block."""
+        from .topk import TowerEncoder
+
+        return TowerEncoder(self.body.query, self.body.post)
+
+    def candidate_encoder(self) -> Block:
+        from .topk import TowerEncoder
+
+        return TowerEncoder(self.body.item, self.body.post)
+
+    def _item_id_column(self) -> str:
+        tagged = self.schema.select_by_tag(Tags.ITEM_ID)
+        if not tagged:
+            raise ValueError("the schema has no column tagged ITEM_ID")
+        return tagged.first.name
+
+    def query_embeddings(self, data: Dict[str, np.ndarray], batch_size: int = 65536, query_id: Optional[str] = None):
+        """models/base.py:2354-2385: (ids, embeddings) of the query tower over `data`."""
+        from .topk import encode_rows
+
+        query_id = query_id or (self.schema.select_by_tag(Tags.USER_ID).first.name if self.schema.select_by_tag(Tags.USER_ID) else None)
+        return encode_rows(self.query_encoder(), data, query_id, batch_size)
+
+    def item_embeddings(self, data: Dict[str, np.ndarray], batch_size: int = 65536, item_id: Optional[str] = None):
+        """models/base.py:2387-2418: (ids, embeddings) of the item tower over `data`."""
+        from .topk import encode_rows
+
+        return encode_rows(self.candidate_encoder(), data, item_id or self._item_id_column(), batch_size)
+
+    def to_top_k_encoder(self, candidates, candidate_id: Optional[str] = None, k: int = 10, batch_size: int = 65536,
+                         **kwargs):
+        """models/base.py `to_top_k_encoder`: query tower -> brute-force top-k over `candidates` — raw item
+        features (dict, encoded by the item tower) or precomputed (ids, embeddings) / a DataFrame indexed by id."""
+        from .topk import TopKEncoder
+
+        enc = TopKEncoder(self.query_encoder(), candidates=None if isinstance(candidates, dict) else candidates,
+                          candidate_encoder=self.candidate_encoder(), k=k, target=self._item_id_column(),
+                          topk_layer=kwargs.pop("topk_layer", None) or _brute_force(k), **kwargs)
+        if isinstance(candidates, dict):
+            enc.index_candidates(candidates, candidate_id or self._item_id_column(), batch_size)
+        return enc
+
+    def evaluate(self, x, item_corpus=None, metrics=None, batch_size: int = 65536, return_dict: bool = True, **kwargs):
+        """models/base.py:2266-2351.  `x`: one feature-dict batch or an iterable of them (host arrays or device
+        tensors).  With `item_corpus` (a TopKIndexBlock, or the item features of the corpus as a dict: deduplicated
+        by item id and encoded by the item tower) every query is ranked against the whole corpus by the fused
+        score + top-k kernel; without it the batch's own items are the candidates (in-batch evaluation)."""
+        from .topk import (NDCGAt, RecallAt, TopKIndexBlock, evaluate_topk, unique_rows_by_features)
+
+        metrics = list(metrics) if metrics else [RecallAt(10), NDCGAt(10)]
+        kmax = max(m.k for m in metrics)
+        item_id = self._item_id_column()
+        if item_corpus is not None:
+            if isinstance(item_corpus, TopKIndexBlock):
+                index = item_corpus
+                if index._k < kmax:
+                    raise ValueError(f"the index returns {index._k} candidates, the metrics need {kmax}")
+            elif isinstance(item_corpus, dict):
+                corpus = unique_rows_by_features(item_corpus, item_id)
+                if not self.built:
+                    self.build(default_device())
+                index = TopKIndexBlock.from_block(self.candidate_encoder(), corpus, k=kmax, id_column=item_id,
+                                                  batch_size=batch_size)
+            else:
+                raise ValueError(f"`item_corpus` must be either a `TopKIndexBlock` or a dict of item features. Got {type(item_corpus)}")
+            self.pre_eval_topk = index
+            q = self.query_encoder()
+
+            def predict(b):
+                if not self.built:
+                    self.build(next(iter(b.values())).device)
+                return index.call_outputs(b[item_id].reshape(-1), q(b))
+        else:
+            def predict(b):
+                out = self(b, testing=True)
+                k = min(kmax, out.outputs.shape[1])
+                scores, order = torch.topk(out.outputs, k, dim=1)
+                return Prediction(scores, torch.gather(out.targets, 1, order))
+        return evaluate_topk(predict, x, metrics)
 
 
 def TwoTowerModel(schema: Schema, query_tower: MLP, item_tower: Optional[MLP] = None, query_tower_tag=Tags.USER,

@@ -378,3 +378,60 @@ def topk(logits: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
     index first."""
     idx = np.argsort(-logits, axis=-1, kind="stable")[:, :k]
     return np.take_along_axis(logits, idx, axis=-1), idx.astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# top-k retrieval evaluation (SURVEY §8f-2)
+# ------------------------------------------------------------------------------------------------
+def topk_index(queries: np.ndarray, values: np.ndarray, ids: Optional[np.ndarray], k: int):
+    """TopKIndexBlock.call (core/index.py:232-250) / BruteForce.call (outputs/topk.py:221-223):
+    scores = queries @ values^T; top_k; ids gathered.  Returns (top_scores (B,k), top_ids (B,k))."""
+    scores = queries.astype(np.float32) @ values.astype(np.float32).T
+    s, idx = topk(scores, k)
+    return s, (idx if ids is None else np.asarray(ids)[idx])
+
+
+def topk_targets(positive_ids: np.ndarray, top_ids: np.ndarray) -> np.ndarray:
+    """core/index.py:272-276, outputs/topk.py:236-238: one-hot of the positive id among the top ids."""
+    return (np.asarray(positive_ids).reshape(-1, 1) == top_ids).astype(np.float32)
+
+
+def _div_no_nan(a, b):
+    return np.where(b != 0, a / np.where(b != 0, b, 1), 0.0).astype(np.float32)
+
+
+def recall_at(y_true, label_relevant_counts, k):
+    """metrics/topk.py:48-66."""
+    rel = np.clip(label_relevant_counts, 1, float(k))
+    return _div_no_nan(y_true[:, :k].sum(-1), rel)
+
+
+def precision_at(y_true, label_relevant_counts, k):
+    """metrics/topk.py:69-84."""
+    return y_true[:, :k].mean(-1).astype(np.float32)
+
+
+def average_precision_at(y_true, label_relevant_counts, k):
+    """metrics/topk.py:87-113."""
+    precisions = np.stack([precision_at(y_true, None, j) for j in range(1, k + 1)], axis=-1)
+    total = (precisions * y_true[:, :k]).sum(-1)
+    return _div_no_nan(total, np.clip(label_relevant_counts, 1, float(k)))
+
+
+def dcg_at(y_true, k, log_base=2):
+    """metrics/topk.py:116-139."""
+    disc = 1.0 / (np.log(np.arange(k, dtype=np.float32) + 2) / np.log(np.float32(log_base)))
+    return (y_true[:, :k] * disc[None, :]).sum(-1).astype(np.float32)
+
+
+def ndcg_at(y_true, label_relevant_counts, k, log_base=2):
+    """metrics/topk.py:142-166."""
+    ideal = (np.arange(k)[None, :] < np.asarray(label_relevant_counts)[:, None]).astype(np.float32)
+    return _div_no_nan(dcg_at(y_true, k, log_base), dcg_at(ideal, k, log_base))
+
+
+def mrr_at(y_true, label_relevant_counts, k):
+    """metrics/topk.py:169-187."""
+    first = (np.argmax(y_true, axis=-1) + 1).astype(np.float32)
+    hit = y_true[:, :k].max(-1)
+    return _div_no_nan(np.ones_like(first), first * hit)
