@@ -221,6 +221,24 @@ int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* c
               int64_t out_stride, const float* head_w, float head_b, int head_act, float* head_out,
               void* stream);
 
+/* Whole-op entry points over fp32 Keras-layout weights (kernel (in, out) row-major, bias (out,) or
+ * NULL) and a caller-provided workspace — for callers outside this package's Python host; nothing is
+ * allocated, no pre-split weights are needed (the bf16 splits live in the workspace).
+ *   mm_mlp_forward: MLPBlock, h_l = act_l(h_{l-1} W_l + b_l), 1..8 layers (blocks/mlp.py:97-139,
+ *     :275-280); the whole-tower kernel when mm_mlp_tc_supported, else one tcgen05 launch per layer.
+ *   mm_cross_forward: CrossBlock, x_{l+1} = x0 * (x_l W_l + b_l) + x_l, W_l (d, d)
+ *     (blocks/cross.py:29-109, :188-202); depth > 1 needs x_stride == d.
+ * workspace: 256-B aligned device memory of at least mm_*_workspace_bytes(...) (-1 on bad arguments). */
+int64_t mm_mlp_workspace_bytes(int64_t M, int K, int n_layers, const int* widths);
+int mm_mlp_forward(const float* x, int64_t M, int K, int64_t x_stride, int n_layers,
+                   const float* const* kernels, const float* const* biases, const int* widths,
+                   const int* acts, float* out, int64_t out_stride, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+int64_t mm_cross_workspace_bytes(int64_t M, int d, int depth);
+int mm_cross_forward(const float* x0, int64_t M, int d, int64_t x_stride, int depth,
+                     const float* const* kernels, const float* const* biases, float* out,
+                     int64_t out_stride, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K8/K9  Two-tower scoring.
  * mm_rowwise_dot: inference scorer  s[b] = sum_d q[b,d]*i[b,d]

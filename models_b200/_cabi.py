@@ -72,6 +72,11 @@ SIGNATURES = {
     "mm_dense_tc": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _i64, _vp, _i64,
                          _vp, _i, _vp]),
     "mm_dense_tc_head": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _f, _i, _vp, _vp]),
+    "mm_mlp_workspace_bytes": (_i64, [_i64, _i, _i, C.POINTER(C.c_int)]),
+    "mm_mlp_forward": (_i, [_vp, _i64, _i, _i64, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
+                            C.POINTER(C.c_int), _vp, _i64, _vp, _i64, _vp]),
+    "mm_cross_workspace_bytes": (_i64, [_i64, _i, _i]),
+    "mm_cross_forward": (_i, [_vp, _i64, _i, _i64, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp, _i64, _vp, _i64, _vp]),
     "mm_mlp_tc_supported": (_i, [_i, _i, C.POINTER(C.c_int), _i]),
     "mm_mlp_tc": (_i, [_vp, _i64, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
                        _vp, _i64, _vp, _f, _i, _vp, _vp]),

@@ -432,6 +432,60 @@ def catalog_score(q: torch.Tensor, e_split: torch.Tensor, n_items: int, bias: Op
     return stats, scores, ids
 
 
+def mlp_forward(x: torch.Tensor, kernels: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+                acts: Sequence[Optional[str]], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """MLPBlock in ONE C call over fp32 Keras-layout kernels (mm_mlp_forward): the bf16 splits of the input,
+    the weights and the intermediate activations live in a workspace allocated here."""
+    _dev(x, "x", torch.float32)
+    M, K = x.shape
+    n = len(kernels)
+    widths = [int(k.shape[1]) for k in kernels]
+    kk = K
+    for l, kern in enumerate(kernels):
+        _dev(kern, f"kernels[{l}]", torch.float32)
+        if kern.dim() != 2 or kern.shape[0] != kk or not kern.is_contiguous():
+            raise ValueError(f"kernels[{l}] must be a contiguous ({kk}, units) matrix, got {tuple(kern.shape)}")
+        if biases[l] is not None:
+            _dev(biases[l], f"biases[{l}]", torch.float32)
+        kk = widths[l]
+    if out is None:
+        out = torch.empty((M, widths[-1]), dtype=torch.float32, device=x.device)
+    wd = (C.c_int * n)(*widths)
+    need = int(_lib().mm_mlp_workspace_bytes(M, K, n, wd))
+    if need < 0:
+        raise ValueError("mm_mlp_workspace_bytes rejected the tower (1..8 layers, positive widths)")
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=x.device)
+    kp = (C.c_void_p * n)(*[k.data_ptr() for k in kernels])
+    bp = (C.c_void_p * n)(*[_ptr(b) for b in biases])
+    ac = (C.c_int * n)(*[ACTIVATIONS[a] for a in acts])
+    _cabi.check(_lib().mm_mlp_forward(x.data_ptr(), M, K, _row_stride(x, "x"), n, kp, bp, wd, ac, out.data_ptr(),
+                                      _row_stride(out, "out"), ws.data_ptr(), need, _stream()), "mm_mlp_forward")
+    return out
+
+
+def cross_forward(x0: torch.Tensor, kernels: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CrossBlock stack in ONE C call (mm_cross_forward): x_{l+1} = x0 * (x_l W_l + b_l) + x_l."""
+    _dev(x0, "x0", torch.float32)
+    M, d = x0.shape
+    depth = len(kernels)
+    for l, kern in enumerate(kernels):
+        _dev(kern, f"kernels[{l}]", torch.float32)
+        if tuple(kern.shape) != (d, d) or not kern.is_contiguous():
+            raise ValueError(f"kernels[{l}] must be a contiguous ({d}, {d}) matrix")
+    if out is None:
+        out = torch.empty((M, d), dtype=torch.float32, device=x0.device)
+    need = int(_lib().mm_cross_workspace_bytes(M, d, depth))
+    if need < 0:
+        raise ValueError(f"Number of cross layers (depth) should be positive but is {depth}.")
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=x0.device)
+    kp = (C.c_void_p * depth)(*[k.data_ptr() for k in kernels])
+    bp = (C.c_void_p * depth)(*[_ptr(b) for b in biases])
+    _cabi.check(_lib().mm_cross_forward(x0.data_ptr(), M, d, _row_stride(x0, "x0"), depth, kp, bp, out.data_ptr(),
+                                        _row_stride(out, "out"), ws.data_ptr(), need, _stream()), "mm_cross_forward")
+    return out
+
+
 def mlp_tc_supported(K: int, widths: Sequence[int], head: bool = False) -> bool:
     """True when mm_mlp_tc can run the tower (mm_mlp_tc_supported): 2..4 layers, every width <= 128, head only
     after <= 32 units, resident weights of layers 2..n + two layer-1 pipeline stages within shared memory."""
