@@ -65,16 +65,17 @@ __global__ void concat_columns_kernel(const __grid_constant__ ConcatParams cp, l
 // Concat fused with the bf16 split of the tensor-core dense path: same transposing read as above, but the
 // rows leave as the (B, 2*Kp) [hi | lo] operand of mm_dense_tc / mm_mlp_tc (zero padded to Kp), so the
 // fp32 (B, W) matrix never exists.  Pieces sit at their out_col offsets inside the row.
-__global__ void concat_split_kernel(const __grid_constant__ ConcatParams cp, long long B,
-                                    __nv_bfloat16* __restrict__ out, int Kp) {
-  extern __shared__ float tile[];  // [32][Kp+1], zero outside the pieces
-  const long long b0 = (long long)blockIdx.x * 32;
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+concat_split_kernel(const __grid_constant__ ConcatParams cp, long long B, __nv_bfloat16* __restrict__ out, int Kp) {
+  extern __shared__ float tile[];  // [ROWS][Kp+1], zero outside the pieces
+  const long long b0 = (long long)blockIdx.x * ROWS;
   const int ld = Kp + 1;
-  for (int e = threadIdx.x; e < 32 * ld; e += blockDim.x) tile[e] = 0.0f;
+  for (int e = threadIdx.x; e < ROWS * ld; e += blockDim.x) tile[e] = 0.0f;
   __syncthreads();
   const int W = cp.total_width;
-  for (int e = threadIdx.x; e < W * 32; e += blockDim.x) {
-    const int r = e & 31, c = e >> 5;
+  for (int e = threadIdx.x; e < W * ROWS; e += blockDim.x) {
+    const int r = e % ROWS, c = e / ROWS;  // r fastest: a warp reads 32 consecutive rows of one column (coalesced)
     int pi = 0, base = 0;
     while (pi < cp.n - 1 && c >= base + cp.p[pi].width) {
       base += cp.p[pi].width;
@@ -85,7 +86,7 @@ __global__ void concat_split_kernel(const __grid_constant__ ConcatParams cp, lon
   }
   __syncthreads();
   const int groups = Kp >> 3;  // 8 bf16 = 16 bytes per store
-  for (int e = threadIdx.x; e < 32 * groups; e += blockDim.x) {
+  for (int e = threadIdx.x; e < ROWS * groups; e += blockDim.x) {
     const int g = e % groups, r = e / groups;
     const long long b = b0 + r;
     if (b >= B) continue;
@@ -172,10 +173,18 @@ int mm_concat_split(const mm_concat_piece* pieces_host, int n_pieces, int64_t B,
     cp.p[i] = pc;
     cp.total_width += pc.width;
   }
-  const size_t smem = (size_t)32 * (Kp + 1) * sizeof(float);
-  MM_REQUIRE(smem <= 48 * 1024, MM_ERR_UNSUPPORTED, "mm_concat_split: Kp = %d exceeds the 48 KB tile", Kp);
-  const unsigned blocks = (unsigned)((B + 31) / 32);
-  mm::concat_split_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(cp, B, (__nv_bfloat16*)out_split, Kp);
+  MM_REQUIRE((size_t)32 * (Kp + 1) * sizeof(float) <= 48 * 1024, MM_ERR_UNSUPPORTED,
+             "mm_concat_split: Kp = %d exceeds the 48 KB tile", Kp);
+  // 128 rows per block when the tile fits in 48 KB and the batch still fills the SMs (fewer, fatter blocks);
+  // 32 rows otherwise
+  const size_t smem128 = (size_t)128 * (Kp + 1) * sizeof(float);
+  if (smem128 <= 48 * 1024 && B >= 128ll * mm::sm_count()) {
+    mm::concat_split_kernel<128><<<(unsigned)((B + 127) / 128), 256, smem128, (cudaStream_t)stream>>>(
+        cp, B, (__nv_bfloat16*)out_split, Kp);
+  } else {
+    mm::concat_split_kernel<32><<<(unsigned)((B + 31) / 32), 256, (size_t)32 * (Kp + 1) * sizeof(float), (cudaStream_t)stream>>>(
+        cp, B, (__nv_bfloat16*)out_split, Kp);
+  }
   return mm::check_launch("mm_concat_split");
 }
 
