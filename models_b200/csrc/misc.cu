@@ -175,16 +175,9 @@ int mm_concat_split(const mm_concat_piece* pieces_host, int n_pieces, int64_t B,
   }
   MM_REQUIRE((size_t)32 * (Kp + 1) * sizeof(float) <= 48 * 1024, MM_ERR_UNSUPPORTED,
              "mm_concat_split: Kp = %d exceeds the 48 KB tile", Kp);
-  // 128 rows per block when the tile fits in 48 KB and the batch still fills the SMs (fewer, fatter blocks);
-  // 32 rows otherwise
-  const size_t smem128 = (size_t)128 * (Kp + 1) * sizeof(float);
-  if (false && smem128 <= 48 * 1024 && B >= 128ll * mm::sm_count()) {  // measured slower (12.5 vs 10.4 us at B = 65 536): kept for reference
-    mm::concat_split_kernel<128><<<(unsigned)((B + 127) / 128), 256, smem128, (cudaStream_t)stream>>>(
-        cp, B, (__nv_bfloat16*)out_split, Kp);
-  } else {
-    mm::concat_split_kernel<32><<<(unsigned)((B + 31) / 32), 256, (size_t)32 * (Kp + 1) * sizeof(float), (cudaStream_t)stream>>>(
-        cp, B, (__nv_bfloat16*)out_split, Kp);
-  }
+  // 32-row blocks: 128-row blocks (4x fewer, fatter CTAs) measured slower, 12.5 vs 10.4 us at B = 65 536
+  mm::concat_split_kernel<32><<<(unsigned)((B + 31) / 32), 256, (size_t)32 * (Kp + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      cp, B, (__nv_bfloat16*)out_split, Kp);
   return mm::check_launch("mm_concat_split");
 }
 
