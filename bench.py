@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the B200 hot path (BASELINE.json: DLRM fwd samples/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload dlrm|twotower|dcn] [--batch B]
+                    [--workload dlrm|dlrm-sharded|twotower|dcn] [--batch B]
 
 N=1 workload = BASELINE.json configs[1]: mm.DLRMModel, Criteo shape (26 cat, 13 dense, emb 64,
 bundled cardinalities = 45.6 M rows / 11.7 GB of tables), batch 65 536, README MLP dims.
@@ -15,6 +15,9 @@ e2e = the same metric through the public host-buffer call (pinned H2D + forward 
 timed region), roofline = dominant kernel vs measured HBM peak, cpu_baseline = CPU restatement
 of the reference op sequence on this box's host cores (rank 0, N=1 only).
 `--impl reference` times that CPU restatement alone (TensorFlow is not installable: no network).
+`--workload twotower` (configs[2]: 10 M-item catalog, in-batch negatives, batch 16 384) and `--workload dcn`
+(configs[4]: DCN-v2 depth 3 + MLP[256,128], batch 65 536) print the same kind of line for the other
+single-GPU configurations; `--workload dlrm-sharded` is configs[3] (row-sharded tables, torchrun).
 """
 from __future__ import annotations
 
@@ -177,8 +180,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dlrm", choices=["dlrm", "dlrm-sharded"])
-    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--workload", default="dlrm", choices=["dlrm", "dlrm-sharded", "twotower", "dcn"])
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -195,6 +198,8 @@ def main():
     from models_b200 import datasets, ops
     from models_b200.blocks import run_dense_chain
 
+    if args.batch is None:
+        args.batch = 16384 if args.workload == "twotower" else 65536
     B = args.batch
     cores = usable_cores()
 
@@ -216,6 +221,8 @@ def main():
 
     if args.workload == "dlrm-sharded":
         return sharded_arm(args, mm, datasets, ops, dev, rank, local_rank, world)
+    if args.workload in ("twotower", "dcn"):
+        return secondary_arm(args, mm, datasets, ops, dev, rank, local_rank, world)
 
     schema, model = build_dlrm(mm, datasets)
     model.build(dev)
@@ -490,6 +497,177 @@ def sharded_arm(args, mm, datasets, ops, dev, rank, local_rank, world):
             "clocks": clocks, "gpu_launches": int(lt.item()),
         }))
     dist.destroy_process_group()
+    return 0
+
+
+def secondary_arm(args, mm, datasets, ops, dev, rank, local_rank, world):
+    """BASELINE configs[2] (two-tower, 10 M-item catalog, in-batch negatives, B = 16 384) and configs[4]
+    (DCN-v2, depth 3, deep [256,128], B = 65 536): same timing protocol as the DLRM arm (graph replay on two
+    streams for `value`, packed pinned host batches for `e2e`, CUDA events, clocks), replicas under torchrun."""
+    import torch
+
+    B = args.batch
+    mm.set_seed(1)
+    if args.workload == "twotower":
+        schema = datasets.retrieval_10m_schema()
+        model = mm.TwoTowerModel(schema, query_tower=mm.MLPBlock([256, 128]),
+                                 embedding_options=mm.EmbeddingOptions(embeddings_initializers={"hash_seed": 5}))
+        call_kwargs = {"training": True}
+        law = "zipf"
+        label = "mm.TwoTowerModel 10M-item catalog, towers [256,128], in-batch sampled softmax (train-mode forward: (B, 1+B) logits)"
+        metric = "TwoTower fwd samples/sec (10M-item catalog, in-batch negatives, batch 16384/GPU)"
+    else:
+        schema = datasets.criteo_schema()
+        model = mm.DCNModel(schema, depth=3, deep_block=mm.MLPBlock([256, 128]), embeddings_initializer={"hash_seed": 99})
+        call_kwargs = {}
+        law = "uniform"
+        label = "mm.DCNModel (DCN-v2) cross depth 3 (d = 1037) + MLP[256,128]"
+        metric = "DCN-v2 fwd samples/sec (Criteo shape, batch 65536/GPU)"
+    n_bufs = 4
+    hosts = []
+    for i in range(n_bufs):
+        b = datasets.generate_batch(schema, B, seed=1234 + 1000 * rank + i, index_law=law, index_dtype=np.int32)
+        hosts.append(datasets.split_targets(schema, b)[0])
+    model.build(dev)
+    hbs = [mm.HostBatch.like(h, model.input_columns()) for h in hosts]
+    packed_dev = [hb.buffer.to(dev) for hb in hbs]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    cf = model.compile(hbs[0], **call_kwargs)
+    pf = model.pipeline(hbs[0], depth=2, **call_kwargs)
+    for i in range(args.warmup):
+        pf.submit_device(packed_dev[i % n_bufs])
+    pf.join()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        pf.submit_device(packed_dev[i % n_bufs])
+    pf.join()
+    t1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = t0.elapsed_time(t1)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(args.steps):
+        cf.load_device(packed_dev[i % n_bufs])
+        cf.replay()
+    s1.record()
+    torch.cuda.synchronize()
+    serial_ms = s0.elapsed_time(s1) / args.steps
+
+    # dominant kernel, one launch per CUDA-event pair
+    if args.workload == "twotower":
+        D = 128
+        q = torch.randn((B, D), device=dev)
+        it = torch.randn((B, D), device=dev)
+        ids = torch.from_numpy(hosts[0][schema.select_by_tag(mm.Tags.ITEM_ID).first.name].astype(np.int64).reshape(-1)).to(dev)
+        qs, its = ops.split_rows(q), ops.split_rows(it)
+        logits = torch.empty((B, B + 4), dtype=torch.float32, device=dev)[:, 3:4 + B]  # (B, 1+B); negatives 16-byte aligned
+        from models_b200 import _cabi
+
+        lib = _cabi.load()
+
+        def dominant(i):
+            _cabi.check(lib.mm_inbatch_scores_tc(qs.data_ptr(), its.data_ptr(), B, B, D, ids.data_ptr(), ids.data_ptr(),
+                                                 _cabi.MM_I64, 1, -655.04, None, 1.0, logits.data_ptr(), logits.stride(0),
+                                                 torch.cuda.current_stream().cuda_stream), "mm_inbatch_scores_tc")
+
+        algo = float(B) * (B + 1) * 4 + 2.0 * B * D * 4
+        roof = {"bound": "hbm", "kernel": "dense_tc_kernel<scorer epilogue> (mm_inbatch_scores_tc)", "unit": "GB/s"}
+    else:
+        d = 1037
+        x = torch.randn((B, d), device=dev)
+        W = torch.randn((d, d), device=dev) * 0.03
+        a, w = ops.split_rows(x), ops.split_weights(W)
+        o = torch.empty((B, d), dtype=torch.float32, device=dev)
+        nxt = torch.zeros((B, 2 * ops.tc_padded_k(d)), dtype=torch.bfloat16, device=dev)
+
+        def dominant(i):
+            ops.dense_tc(a, d, w, d, None, "linear", passes=3, out_f32=o, out_split=nxt, x0=x, xres=x)
+
+        algo = 2.0 * B * d * d
+        roof = {"bound": "tensor", "kernel": "dense_tc_kernel<cross epilogue> (mm_dense_tc, one of the 3 cross layers)",
+                "unit": "TFLOP/s", "note": "algorithmic fp32 FLOPs; 3 bf16 passes are issued for fp32 parity (x3 tensor work)"}
+    for i in range(3):
+        dominant(i)
+    torch.cuda.synchronize()
+    kev = []
+    for i in range(max(5, args.steps // 2)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dominant(i)
+        e1.record()
+        kev.append((e0, e1))
+    torch.cuda.synchronize()
+    kern_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in kev]))
+
+    # e2e: pinned packed host batch in, predictions (logits for the two-tower) out, pipelined
+    e2e_steps = max(5, min(args.steps, 20))
+
+    def e2e_loop(n):
+        tickets, res = [], None
+        for i in range(n):
+            tickets.append(pf.submit(hbs[i % n_bufs]))
+            if len(tickets) == 2:
+                res = pf.result(tickets.pop(0))
+        while tickets:
+            res = pf.result(tickets.pop(0))
+        return res
+
+    e2e_loop(3)
+    barrier()
+    w0 = time.perf_counter()
+    res = e2e_loop(e2e_steps)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - w0) * 1e3
+    barrier()
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([elapsed_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms, kern_ms = (float(v) for v in t.tolist())
+    if rank == 0:
+        hbm, hbm_src = measured_peaks()
+        tf_peak = None
+        pth = ROOT / "MEASURED_PEAKS.json"
+        if pth.exists():
+            tf_peak = json.loads(pth.read_text()).get("bf16_tflops")
+        if roof["bound"] == "hbm":
+            achieved, peak, src = algo / (kern_ms * 1e-3) / 1e9, hbm, hbm_src
+        else:
+            achieved, peak, src = algo / (kern_ms * 1e-3) / 1e12, tf_peak or 1590.0, "measured (MEASURED_PEAKS.json)" if tf_peak else "fallback (B200_PROFILING.md)"
+        roof.update({"achieved": achieved, "peak": peak, "frac": achieved / peak, "peak_source": src, "kernel_ms": kern_ms,
+                     "algorithmic_per_launch": algo, "traffic": None})
+        print(json.dumps({
+            "metric": metric, "value": world * B * args.steps / (elapsed_ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": f"synthetic ({law} indices; hash-initialised tables, random-init towers)",
+            "config": {"workload": label, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"replicas x{world} (no data-path collective)",
+                       "l2": f"{n_bufs} rotating input batches; tables and the (B,1+B) logits exceed L2",
+                       "runtime": "CUDA graph replay, 2 graph instances on 2 streams", "ms_per_step_single_stream": serial_ms},
+            "clocks": clocks,
+            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": int(hbs[0].payload_bytes()), "d2h_bytes_per_step": int(res.numel() * res.element_size()),
+                    "steps": e2e_steps},
+            "gpu_launches": cf.launches_per_replay * args.steps * world, "roofline": roof,
+        }))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
     return 0
 
 
