@@ -39,6 +39,10 @@ static_assert(EPI_STAGE_BYTES >= 32 * 36 * 4, "transpose tile too small");
 struct Params {
   long long M;
   int N, Np, Kp, BN, n_tiles_n, passes, act, stages;
+  // resident-A schedule (scorer with Kp <= 128): a CTA owns a CONTIGUOUS range of tiles (n fastest), keeps the A
+  // (query) k-blocks of the current m-tile in shared memory and streams only B (item) tiles through the ring
+  int resident_a;
+  long long tiles_per_cta;
   const float* bias;
   const float* x0;
   const float* xres;
@@ -72,14 +76,20 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // carve: [stages][A_hi | A_lo | B_hi | B_lo] (1024-B aligned tiles), then barriers
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared state space (LDS/STS, not generic LD/ST)
   const uint32_t B_TILE_BYTES = (uint32_t)p.BN * BLOCK_K * 2;
-  const uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  const int KB_ = p.Kp / BLOCK_K;
+  const uint32_t A_RES_BYTES = p.resident_a ? (uint32_t)KB_ * 2 * A_TILE_BYTES : 0u;  // [kb][A_hi | A_lo]
+  const uint32_t STAGE_BYTES = p.resident_a ? 2 * B_TILE_BYTES : 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  uint8_t* a_res = smem;
+  smem += A_RES_BYTES;  // the ring starts after the resident A region
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
   uint64_t* full_bar = bars;                       // [stages]
   uint64_t* empty_bar = bars + p.stages;           // [stages]
   uint64_t* tmem_full = bars + 2 * p.stages;       // [2]
   uint64_t* tmem_empty = bars + 2 * p.stages + 2;  // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
-  long long* ids_s = reinterpret_cast<long long*>(bars + 2 * p.stages + 6);                // [256] negative ids of the tile (scorer)
+  uint64_t* a_full = bars + 2 * p.stages + 4;      // resident A landed (TMA tx)
+  uint64_t* a_empty = bars + 2 * p.stages + 5;     // MMAs of the m-row retired (tcgen05.commit)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 6);
+  long long* ids_s = reinterpret_cast<long long*>(bars + 2 * p.stages + 8);                // [256] negative ids of the tile (scorer)
   float* bias_s = reinterpret_cast<float*>(ids_s + 256);                                   // [256] bias of the tile, zero padded
   uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(bias_s + 256);                         // kEpiWarps x EPI_STAGE_BYTES
 
@@ -87,6 +97,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const long long tiles = m_tiles * p.n_tiles_n;
   const int KB = p.Kp / BLOCK_K;
+  // tile sequence of this CTA: interleaved (tile, tile + grid, ...) or, resident-A, a contiguous range
+  const long long tile_first = p.resident_a ? (long long)blockIdx.x * p.tiles_per_cta : (long long)blockIdx.x;
+  const long long tile_step = p.resident_a ? 1 : (long long)gridDim.x;
+  const long long tile_end = p.resident_a ? (tile_first + p.tiles_per_cta < tiles ? tile_first + p.tiles_per_cta : tiles) : tiles;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
 
@@ -101,6 +115,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(smem_u32(tmem_full + a), 1);
       mbar_init(smem_u32(tmem_empty + a), kEpiWarps);  // one arrive per epilogue warp
     }
+    mbar_init(smem_u32(a_full), 1);
+    mbar_init(smem_u32(a_empty), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation (whole warp, .sync.aligned)
@@ -120,19 +136,38 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (p.passes == 3) ? STAGE_BYTES : (A_TILE_BYTES + B_TILE_BYTES);
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      int cur_m = -1;
+      uint32_t a_loads = 0;
+      for (long long tile = tile_first; tile < tile_end; tile += tile_step) {
         const int m0 = (int)(tile / p.n_tiles_n) * BLOCK_M;
         const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
+        if (p.resident_a && m0 != cur_m) {  // new m-row: (re)load the query k-blocks once the previous row's MMAs retired
+          if (a_loads > 0) mbar_wait(smem_u32(a_empty), (a_loads - 1) & 1);
+          const uint32_t ab = smem_u32(a_full);
+          mbar_expect_tx(ab, A_RES_BYTES);
+          for (int kb = 0; kb < KB; ++kb) {
+            tma_load_2d(smem_u32(a_res + (size_t)kb * 2 * A_TILE_BYTES), &tmA, ab, kb * BLOCK_K, m0);
+            tma_load_2d(smem_u32(a_res + (size_t)kb * 2 * A_TILE_BYTES + A_TILE_BYTES), &tmA, ab, p.Kp + kb * BLOCK_K, m0);
+          }
+          cur_m = m0;
+          ++a_loads;
+        }
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t fb = smem_u32(full_bar + stage);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-          mbar_expect_tx(fb, tx);
-          tma_load_2d(smem_u32(st), &tmA, fb, kb * BLOCK_K, m0);
-          tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &tmB, fb, kb * BLOCK_K, n0);
-          if (p.passes == 3) {
-            tma_load_2d(smem_u32(st + A_TILE_BYTES), &tmA, fb, p.Kp + kb * BLOCK_K, m0);
-            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + B_TILE_BYTES), &tmB, fb, p.Kp + kb * BLOCK_K, n0);
+          if (p.resident_a) {  // only the item tiles stream
+            mbar_expect_tx(fb, STAGE_BYTES);
+            tma_load_2d(smem_u32(st), &tmB, fb, kb * BLOCK_K, n0);
+            tma_load_2d(smem_u32(st + B_TILE_BYTES), &tmB, fb, p.Kp + kb * BLOCK_K, n0);
+          } else {
+            mbar_expect_tx(fb, tx);
+            tma_load_2d(smem_u32(st), &tmA, fb, kb * BLOCK_K, m0);
+            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &tmB, fb, kb * BLOCK_K, n0);
+            if (p.passes == 3) {
+              tma_load_2d(smem_u32(st + A_TILE_BYTES), &tmA, fb, p.Kp + kb * BLOCK_K, m0);
+              tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + B_TILE_BYTES), &tmB, fb, p.Kp + kb * BLOCK_K, n0);
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -149,7 +184,14 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      long long cur_mrow = -1;
+      uint32_t a_seen = 0;
+      for (long long tile = tile_first; tile < tile_end; tile += tile_step) {
+        if (p.resident_a && tile / p.n_tiles_n != cur_mrow) {
+          mbar_wait(smem_u32(a_full), a_seen & 1);
+          ++a_seen;
+          cur_mrow = tile / p.n_tiles_n;
+        }
         mbar_wait(smem_u32(tmem_empty + acc), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
@@ -158,8 +200,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(smem_u32(full_bar + stage), phase);
           tcgen05_fence_after();
           const uint32_t st = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
-          const uint32_t b_hi = st + 2 * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+          const uint32_t a_hi = p.resident_a ? smem_u32(a_res + (size_t)kb * 2 * A_TILE_BYTES) : st, a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = p.resident_a ? st : st + 2 * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
           if (p.passes == 3) {
             // small cross terms first, the dominant hi*hi product last
 #pragma unroll
@@ -183,6 +225,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         tcgen05_commit(smem_u32(tmem_full + acc));  // accumulator complete -> epilogue
+        if (p.resident_a && (tile + 1 >= tile_end || (tile + 1) / p.n_tiles_n != cur_mrow))
+          tcgen05_commit(smem_u32(a_empty));  // last tile of this m-row: the resident A may be replaced once these MMAs retire
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -203,27 +247,43 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool vec_f32 = p.out_f32 && ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
     const bool vec_x = p.x0 && ((p.x_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x0) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(p.xres) & 15) == 0);
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    float col_b = 0.0f, col_h = 0.0f;
+    long long col_id = 0;
+    auto load_columns = [&](int n0_, float& b, float& h, long long& id) {  // thread i < BN owns column n0_ + i (BN <= 256 threads)
+      const int i = (int)threadIdx.x - 64;
+      b = 0.0f;
+      h = 0.0f;
+      id = -0x7fffffffffffffffll;
+      if (i < p.BN) {
+        const int n = n0_ + i;
+        if (p.bias && n < p.N) b = p.score_mode ? -logf(p.bias[n] + 1e-16f) : p.bias[n];
+        if (p.head_w && n < p.N) h = p.head_w[n];
+        if (p.score_mode && p.neg_ids && n < p.N)
+          id = p.id_is64 ? reinterpret_cast<const long long*>(p.neg_ids)[n] : (long long)reinterpret_cast<const int*>(p.neg_ids)[n];
+      }
+    };
+    for (long long tile = tile_first; tile < tile_end; tile += tile_step) {
       const long long m0 = (tile / p.n_tiles_n) * BLOCK_M;
       const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
       const long long row0 = m0 + q * 32;  // first row of this warp
-      // per-tile column data: bias (or -log sampling prob) and, for the scorer, the negative ids
+      // per-tile column data: bias (or -log sampling prob), head weights and, for the scorer, the negative ids.
+      // The global loads for tile t+1 are issued while tile t is processed (registers), so only shared-memory
+      // stores sit between the two barriers — not a global-memory round trip per tile.
+      if (tile == tile_first) load_columns(n0, col_b, col_h, col_id);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // previous tile's readers are done
-      for (int i = threadIdx.x - 64; i < p.BN; i += 32 * kEpiWarps) {
-        const int n = n0 + i;
-        float b = 0.0f;
-        if (p.bias && n < p.N) b = p.score_mode ? -logf(p.bias[n] + 1e-16f) : p.bias[n];
-        bias_s[i] = b;
-        if (p.head_w) {  // 32 head weights, zero beyond N
-          bias_s[128 + i] = n < p.N ? p.head_w[n] : 0.0f;
-          if (i + p.BN < 32) bias_s[128 + i + p.BN] = 0.0f;
+      {
+        const int i = (int)threadIdx.x - 64;
+        if (i < p.BN) {
+          bias_s[i] = col_b;
+          if (p.head_w) {
+            bias_s[128 + i] = col_h;
+            if (i + p.BN < 32) bias_s[128 + i + p.BN] = 0.0f;
+          }
+          if (p.score_mode && p.neg_ids) ids_s[i] = col_id;
         }
-        if (p.score_mode && p.neg_ids)
-          ids_s[i] = n < p.N ? (p.id_is64 ? reinterpret_cast<const long long*>(p.neg_ids)[n]
-                                          : (long long)reinterpret_cast<const int*>(p.neg_ids)[n])
-                             : -0x7fffffffffffffffll;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      if (tile + tile_step < tile_end) load_columns((int)((tile + tile_step) % p.n_tiles_n) * p.BN, col_b, col_h, col_id);
       long long my_pid = 0;
       if (p.score_mode && p.pos_ids && row0 + lane < p.M)
         my_pid = p.id_is64 ? reinterpret_cast<const long long*>(p.pos_ids)[row0 + lane]
@@ -517,14 +577,17 @@ static int dense_tc_launch(const void* a_split, int64_t M, int K, int Kp, const 
   p.head_b = head_b;
   p.head_act = head_act;
   p.head_out = head_out;
-  const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.BN * BLOCK_K * 2;
+  // resident-A schedule: many n-tiles per m-tile and a short K (the in-batch scorer): operand traffic halves
+  p.resident_a = (score_mode && passes == 3 && Kp <= 2 * BLOCK_K && p.n_tiles_n >= 8) ? 1 : 0;
+  const size_t a_res_bytes = p.resident_a ? (size_t)(Kp / BLOCK_K) * 2 * A_TILE_BYTES : 0;
+  const size_t stage_bytes = (p.resident_a ? 0 : 2 * (size_t)A_TILE_BYTES) + 2 * (size_t)p.BN * BLOCK_K * 2;
   const size_t epi_bytes = 256 * sizeof(long long) + 256 * sizeof(float) + (size_t)kEpiWarps * EPI_STAGE_BYTES;
-  int stages = (int)((224 * 1024 - 2048 - epi_bytes) / stage_bytes);
+  int stages = (int)((224 * 1024 - 2048 - epi_bytes - a_res_bytes) / stage_bytes);
   if (stages > 6) stages = 6;
-  if (stages > Kp / BLOCK_K * 2) stages = Kp / BLOCK_K * 2 > 2 ? Kp / BLOCK_K * 2 : 2;
+  if (!p.resident_a && stages > Kp / BLOCK_K * 2) stages = Kp / BLOCK_K * 2 > 2 ? Kp / BLOCK_K * 2 : 2;
   MM_REQUIRE(stages >= 2, MM_ERR_UNSUPPORTED, "mm_dense_tc: tile does not fit two pipeline stages");
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + epi_bytes;
+  const size_t smem = 1024 + a_res_bytes + stages * stage_bytes + (2 * stages + 8) * sizeof(uint64_t) + epi_bytes;
 
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a_split, (uint64_t)M, (uint64_t)2 * Kp, BLOCK_M);
@@ -543,7 +606,9 @@ static int dense_tc_launch(const void* a_split, int64_t M, int K, int Kp, const 
   }
   const long long tiles = ((M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles_n;
   const int sms = mm::sm_count();
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  p.tiles_per_cta = (tiles + grid - 1) / grid;
+  if (p.resident_a) grid = (unsigned)((tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);  // no empty CTAs
   dense_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return mm::check_launch("mm_dense_tc");
 }
