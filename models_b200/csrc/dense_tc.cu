@@ -249,6 +249,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                        ((reinterpret_cast<uintptr_t>(p.xres) & 15) == 0);
     float col_b = 0.0f, col_h = 0.0f;
     long long col_id = 0;
+    uint32_t tile_wide = 0u;  // 1 when a negative id of the current tile needs 64 bits (OR-reduced by the staging barrier)
     auto load_columns = [&](int n0_, float& b, float& h, long long& id) {  // thread i < BN owns column n0_ + i (BN <= 256 threads)
       const int i = (int)threadIdx.x - 64;
       b = 0.0f;
@@ -273,16 +274,26 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // previous tile's readers are done
       {
         const int i = (int)threadIdx.x - 64;
+        const bool col_hi_flag = p.score_mode && p.neg_ids && i < p.BN && col_id != -0x7fffffffffffffffll &&
+                                 ((unsigned long long)col_id >> 32) != 0ull;
         if (i < p.BN) {
           bias_s[i] = col_b;
           if (p.head_w) {
             bias_s[128 + i] = col_h;
             if (i + p.BN < 32) bias_s[128 + i + p.BN] = 0.0f;
           }
-          if (p.score_mode && p.neg_ids) ids_s[i] = col_id;
+          if (p.score_mode && p.neg_ids) {
+            uint32_t* lo_s = reinterpret_cast<uint32_t*>(ids_s);
+            lo_s[i] = (uint32_t)(unsigned long long)col_id;
+            lo_s[256 + i] = (uint32_t)((unsigned long long)col_id >> 32);
+          }
         }
+        // the barrier that publishes the column data also ORs "some negative id of this tile needs 64 bits"
+        asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.or.pred p, 1, %2, q;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(tile_wide)
+                     : "r"((uint32_t)col_hi_flag), "n"(32 * kEpiWarps)
+                     : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       if (tile + tile_step < tile_end) load_columns((int)((tile + tile_step) % p.n_tiles_n) * p.BN, col_b, col_h, col_id);
       long long my_pid = 0;
       if (p.score_mode && p.pos_ids && row0 + lane < p.M)
@@ -310,8 +321,20 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) mbar_arrive(smem_u32(tmem_empty + acc));
         }
         float v[32];
+        if (p.bias != nullptr) {  // warp-uniform; bias_s is zero padded, read 4 columns per shared-memory load
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c0 + j];  // bias_s is zero padded
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = b4[j >> 2];
+            v[j] = __uint_as_float(r[j]) + b.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
         if (p.x0) {
           // cross epilogue: x0 * (xW + b) + x ; x0 / x tiles come in through the transpose tile (coalesced)
 #pragma unroll 1
@@ -352,9 +375,28 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else if (p.score_mode) {
           // false-negative mask (utils/tf_utils.py:140-150) then LogitsTemperatureScaler (x / T)
           if (p.pos_ids != nullptr) {
+            // ids are stored as (low word, high word) arrays; when every high word of the tile's columns and
+            // of this warp's rows is zero (ids < 2^32, the common case) the compare is one 32-bit ISETP per
+            // logit on 128-bit shared-memory loads, else the exact 64-bit compare
+            const uint32_t* lo_s = reinterpret_cast<const uint32_t*>(ids_s);
+            const uint32_t* hi_s = lo_s + 256;
+            const uint32_t pid_lo = (uint32_t)(unsigned long long)my_pid, pid_hi = (uint32_t)((unsigned long long)my_pid >> 32);
+            const bool narrow = (tile_wide == 0u) && !__any_sync(0xffffffffu, pid_hi != 0u);
+            if (narrow) {
+              const uint4* l4 = reinterpret_cast<const uint4*>(lo_s + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ids_s[c0 + j] == my_pid) v[j] = p.fns;
+              for (int j = 0; j < 32; j += 4) {
+                const uint4 L = l4[j >> 2];
+                v[j] = L.x == pid_lo ? p.fns : v[j];
+                v[j + 1] = L.y == pid_lo ? p.fns : v[j + 1];
+                v[j + 2] = L.z == pid_lo ? p.fns : v[j + 2];
+                v[j + 3] = L.w == pid_lo ? p.fns : v[j + 3];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (lo_s[c0 + j] == pid_lo && hi_s[c0 + j] == pid_hi) v[j] = p.fns;
+            }
           }
           if (p.temperature != 1.0f) {  // x / 1 == x exactly: skip the IEEE division in the common case
 #pragma unroll
@@ -386,7 +428,15 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(stg_f + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           __syncwarp();
-          if (vec_f32) {
+          if (vec_f32 && row0 + 32 <= p.M && n0 + c0 + 32 <= p.N) {
+            // interior chunk (the common case): no per-element predicates
+            const int rsub = lane >> 3, cv = (lane & 7) * 4;
+            float* g = p.out_f32 + (row0 + rsub) * p.out_stride + (n0 + c0 + cv);
+            const float* src = stg_f + rsub * 36 + cv;
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              *reinterpret_cast<float4*>(g + (long long)it * 4 * p.out_stride) = *reinterpret_cast<const float4*>(src + it * 4 * 36);
+          } else if (vec_f32) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + (lane >> 3), cv = (lane & 7) * 4;

@@ -138,3 +138,25 @@ def test_mlp_plus_head_chain_equals_unfused(device):
     ref = oracle.dense(oracle.mlp(x.cpu().numpy(), H.mlp_layers(mlp)), H.to_numpy(head.to_call.kernel),
                        H.to_numpy(head.to_call.bias), "sigmoid")
     assert H.rel_err(fused, ref) < 5e-5 and H.rel_err(unfused, ref) < 5e-5
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 300), (2**33, 2**33 + 300), (-150, 150)])
+def test_scorer_false_negative_mask_narrow_and_wide_ids(device, lo, hi):
+    """The scorer epilogue compares 32-bit low words when every id of the tile fits (fast path) and falls back
+    to the exact 64-bit compare otherwise; ids that agree in the low word only must not be masked."""
+    rng = np.random.default_rng(30)
+    B, D = 700, 64
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    it = rng.standard_normal((B, D)).astype(np.float32)
+    ids = rng.integers(lo, hi, B).astype(np.int64)       # many duplicates -> many false negatives
+    ids[5], ids[6] = 7 + lo, 7 + lo + 2**32              # same low word, different id
+    dq, dit, dids = dev(q, device), dev(it, device), dev(ids, device)
+    out = torch.empty((B, 4 + B), dtype=torch.float32, device=device)[:, 3:4 + B]
+    ops.inbatch_scores(dq, dit, dit, out, pos_ids=dids, neg_ids=dids)
+    got = out.cpu().numpy()
+    fns = np.float32(oracle.MIN_FLOAT)
+    same = ids[:, None] == ids[None, :]
+    assert np.array_equal(got[:, 1:] == fns, same)
+    assert not same[5, 6] and got[5, 1 + 6] != fns
+    ref = (q.astype(np.float64) @ it.astype(np.float64).T)
+    np.testing.assert_allclose(got[:, 1:][~same], ref[~same], rtol=1e-4, atol=5e-4)

@@ -55,11 +55,11 @@ elif what in ("gather", "fused", "interact"):
         else:
             ops.dot_interaction(xs[i % 2], out, prefix=bottom)
 elif what == "scores":
-    Bq, Dq = 16384, 64
+    Bq, Dq = 16384, int(sys.argv[2]) if len(sys.argv) > 2 else 128
     q = torch.randn((Bq, Dq), device=dev)
     it = torch.randn((Bq, Dq), device=dev)
     ids = torch.randint(0, 10_000_000, (Bq,), device=dev, dtype=torch.int64)
-    o = torch.empty((Bq, Bq + 1), device=dev)
+    o = torch.empty((Bq, Bq + 4), device=dev)[:, 3:4 + Bq]  # (B, 1+B) view whose negatives start 16-byte aligned
     for _ in range(3):
         ops.inbatch_scores(q, it, it, o, pos_ids=ids, neg_ids=ids)
 torch.cuda.synchronize()
