@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-depth", type=int, default=2, help="graph instances / streams of model.pipeline")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -250,7 +251,7 @@ def main():
     # Steps are independent forward passes; two graph instances on two streams let the small kernels
     # of step i+1 (bottom MLP, narrow top layers) fill SMs that step i leaves idle — the same runtime
     # the host-buffer path uses.  K steps are still exactly K forward passes over K batches.
-    pf = model.pipeline(hbs[0], depth=2)
+    pf = model.pipeline(hbs[0], depth=args.pipeline_depth)
     pf.submit_device(packed_dev[1])
     pf.join()
     torch.cuda.synchronize()
@@ -329,7 +330,7 @@ def main():
         res = None
         for i in range(n):
             tickets.append(pf.submit(hbs[i % n_bufs]))
-            if len(tickets) == 2:
+            if len(tickets) == args.pipeline_depth:
                 res = pf.result(tickets.pop(0))
         while tickets:
             res = pf.result(tickets.pop(0))
@@ -379,7 +380,7 @@ def main():
                 "batch_per_gpu": B, "global_batch": B * world, "index_dtype": "int32", "table_rows": 45621194,
                 "table_gb": 11.68, "parallelism": f"replicas x{world} (no data-path collective)",
                 "l2": f"inputs larger than L2: 11.7 GB of tables, {n_bufs} rotating input batches, no flush",
-                "runtime": "CUDA graph replay, 2 graph instances on 2 streams (model.pipeline): independent steps overlap; "
+                "runtime": f"CUDA graph replay, {args.pipeline_depth} graph instances on {args.pipeline_depth} streams (model.pipeline): independent steps overlap; "
                            "input refresh = one D2D copy of the packed batch per step",
                 "ms_per_step_single_stream": serial_ms,
                 "dense_engine": mm.dense_engine(),
