@@ -184,7 +184,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline-depth", type=int, default=2, help="graph instances / streams of model.pipeline")
+    ap.add_argument("--pipeline-depth", type=int, default=3,
+                    help="graph instances / streams of model.pipeline (3: one more pinned H2D in flight than 2 — e2e 288 -> 337 M samples/s)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
