@@ -16,6 +16,10 @@ and runs the reference's module files unmodified, from where they lie:
   torch/blocks/cross.py     CrossBlock, LazyMirrorLinear
   torch/blocks/mlp.py       MLPBlock
   torch/inputs/embedding.py EmbeddingTable.forward_bag path via F.embedding_bag semantics
+  torch/outputs/contrastive.py  ContrastiveOutput.contrastive_outputs ([positive | negatives] logits, one-hot
+                            targets), rescore_false_negatives (accidental hits -> MIN_FLOAT)
+  torch/outputs/sampling/in_batch.py   InBatchNegativeSampler
+  torch/outputs/sampling/popularity.py LogUniformSampler.get_log_uniform_distr / get_unique_sampling_distr
 
 Nothing is copied from the reference; only its outputs on seeded inputs are stored, together with
 the inputs and weights, so tests/golden/replay.py can re-evaluate the oracle on the GPU box where
@@ -103,8 +107,9 @@ def install_stand_ins():
     _ns("merlin.core.dispatch", None, DataFrameType=object)
     _ns("merlin.dispatch", None)
     _ns("merlin.dispatch.lazy", None, LazyDispatcher=LazyDispatcher)
-    _ns("torchmetrics", None, Metric=_Inert, AUROC=_Inert, Accuracy=_Inert, Precision=_Inert, Recall=_Inert,
-        MeanSquaredError=_Inert, MetricCollection=_Inert)
+    tm = _ns("torchmetrics", None, Metric=_Inert, AUROC=_Inert, Accuracy=_Inert, Precision=_Inert, Recall=_Inert,
+             MeanSquaredError=_Inert, MetricCollection=_Inert)
+    tm.__getattr__ = lambda name: _Inert  # any other metric class (RetrievalHitRate, ...) is an inert placeholder
     _ns("pytorch_lightning", None, LightningModule=object, Trainer=_Inert, LightningDataModule=object)
     _ns("merlin.models", REF / "merlin" / "models")
     _ns("merlin.models.torch", REF / "merlin" / "models" / "torch")
@@ -184,6 +189,48 @@ def main():
     assert "embedding_bag" in src, "reference torch EmbeddingTable no longer uses F.embedding_bag"
     np.savez(OUT / "ref_torch_embedding_bag.npz", kind="embedding_bag", table=table, values=values, offsets=offsets,
              out_mean=outs["mean"], out_sum=outs["sum"])
+    # ---- 6. contrastive logits: [positive | negatives] layout, false-negative rescoring, targets ----
+    import types
+
+    con = importlib.import_module("merlin.models.torch.outputs.contrastive")
+    Bc, Dc, Nn = 29, 12, 17
+    q = rng.standard_normal((Bc, Dc)).astype(np.float32)
+    pos = rng.standard_normal((Bc, Dc)).astype(np.float32)
+    ids = rng.integers(0, 9, Bc).astype(np.int64)            # duplicates -> accidental hits beyond the diagonal
+    sampler = importlib.import_module("merlin.models.torch.outputs.sampling.in_batch").InBatchNegativeSampler()
+    neg_t, neg_id_t = sampler(torch.from_numpy(pos), torch.from_numpy(ids))   # in-batch: the batch's own items
+    # utils/constants.py:19 `np.finfo(np.float16).min / 100.0` is -655.04 under the NumPy 1.x the reference pins
+    # (value-based casting -> float64); under this container's NumPy 2 (NEP 50) the same expression stays float16 and
+    # rounds to -655.0.  The functions take the score as an argument: pass the reference's intended value.
+    MINF = float(np.finfo(np.float16).min) / 100.0
+    fake = types.SimpleNamespace(downscore_false_negatives=True, false_negative_score=MINF)
+    out_ds = con.ContrastiveOutput.contrastive_outputs(fake, torch.from_numpy(q), torch.from_numpy(pos), neg_t,
+                                                       positive_id=torch.from_numpy(ids), negative_id=neg_id_t)
+    target = fake.target.numpy().copy()
+    fake2 = types.SimpleNamespace(downscore_false_negatives=False, false_negative_score=MINF)
+    out_plain = con.ContrastiveOutput.contrastive_outputs(fake2, torch.from_numpy(q), torch.from_numpy(pos), neg_t)
+    # a separate negative set (sampled softmax shape): N != B
+    neg2 = rng.standard_normal((Nn, Dc)).astype(np.float32)
+    neg2_ids = rng.integers(0, 9, Nn).astype(np.int64)
+    scores2 = (q @ neg2.T).astype(np.float32)
+    resc, valid = con.rescore_false_negatives(torch.from_numpy(ids), torch.from_numpy(neg2_ids), torch.from_numpy(scores2),
+                                              MINF)
+    np.savez(OUT / "ref_torch_contrastive.npz", kind="contrastive", query=q, positive=pos, ids=ids,
+             negative=neg_t.numpy(), negative_ids=neg_id_t.numpy(), out_downscored=out_ds.numpy(), out_plain=out_plain.numpy(),
+             target=target, min_float=np.float32(MINF), min_float_as_imported=np.float32(con.MIN_FLOAT), neg2=neg2, neg2_ids=neg2_ids, scores2=scores2,
+             rescored2=resc.numpy(), valid2=valid.numpy())
+
+    # ---- 7. log-uniform (popularity) sampling probabilities --------------------------------------
+    pop = importlib.import_module("merlin.models.torch.outputs.sampling.popularity")
+    fs = types.SimpleNamespace()
+    cases = [(20, 0, 7), (50, 3, 11), (1000, 1, 100)]
+    blobs = {}
+    for i, (max_id, min_id, n_sample) in enumerate(cases):
+        d = pop.LogUniformSampler.get_log_uniform_distr(fs, max_id, min_id)
+        u = pop.LogUniformSampler.get_unique_sampling_distr(fs, d.clone(), n_sample)
+        blobs[f"probs_{i}"] = d.numpy()
+        blobs[f"unique_{i}"] = u.numpy()
+    np.savez(OUT / "ref_torch_log_uniform.npz", kind="log_uniform", cases=np.array(cases, dtype=np.int64), **blobs)
     print("wrote", sorted(p.name for p in OUT.glob("ref_torch_*.npz")))
 
 

@@ -18,11 +18,15 @@ PINNING STATUS
     (tests/unit/tf/inputs/test_embedding.py:248-253), inferred dims (:485-553), L2-normalised towers
     (tests/unit/tf/blocks/retrieval/test_two_tower.py:94-107);
   * pinned against the reference's OWN torch backend executed in the build container
-    (oracle/make_golden_from_reference_torch.py -> tests/golden/ref_torch_*.npz): DLRM interaction
-    ordering/values, embedding-bag combiners, MLP, DCN-v2 cross;
-  * everything else on the TF path (sorted-key concat/stack order, [bottom | interactions] order,
-    [pos | neg] layout, logQ) is restated from source and is PARITY UNPINNED by executed reference
-    code: TensorFlow cannot be run here.
+    (oracle/make_golden_from_reference_torch.py -> tests/golden/ref_torch_*.npz): sorted-name concat / stack
+    order, DLRM interaction ordering/values and the [bottom | interactions] concat, embedding-bag combiners,
+    MLP, DCN-v2 cross, the [positive | negatives] logits layout with false-negative rescoring and one-hot
+    targets (ContrastiveOutput.contrastive_outputs, rescore_false_negatives, InBatchNegativeSampler), the
+    log-uniform sampling distribution (the torch backend is one class short of the TF formula and its
+    "unique" variant computes a different quantity: characterised in tests/golden/replay.py, TF is the target);
+  * the remaining TF-only details (logQ correction arithmetic, safe_embedding_lookup_sparse's pruning of
+    ids < 0 / empty-bag zeros, the legacy InputBlock dict -> first-Dense order, top-k metric formulas) are
+    restated from source and are PARITY UNPINNED by executed reference code: TensorFlow cannot be run here.
 """
 from __future__ import annotations
 

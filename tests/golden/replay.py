@@ -52,6 +52,32 @@ def check(path: Path) -> None:
         for mode in ("mean", "sum"):
             got = oracle.embedding_bag(z["table"], z["values"], z["offsets"], mode)
             np.testing.assert_allclose(got, z[f"out_{mode}"], rtol=RTOL, atol=ATOL)
+    elif kind == "contrastive":
+        # reference torch ContrastiveOutput.contrastive_outputs: [positive | negatives], accidental hits -> MIN_FLOAT
+        assert abs(float(z["min_float"]) - oracle.MIN_FLOAT) < 1e-3
+        out, tgt = oracle.contrastive_logits(z["query"], z["positive"], z["negative"], z["ids"], z["negative_ids"], True,
+                                             float(z["min_float"]))
+        np.testing.assert_allclose(out, z["out_downscored"], rtol=RTOL, atol=ATOL)
+        assert np.array_equal(out == np.float32(z["min_float"]), z["out_downscored"] == np.float32(z["min_float"]))
+        assert np.array_equal(tgt, z["target"])
+        plain, _ = oracle.contrastive_logits(z["query"], z["positive"], z["negative"], None, None, False, float(z["min_float"]))
+        np.testing.assert_allclose(plain, z["out_plain"], rtol=RTOL, atol=ATOL)
+        resc, valid = oracle.rescore_false_negatives(z["ids"], z["neg2_ids"], z["scores2"], float(z["min_float"]))
+        np.testing.assert_allclose(resc, z["rescored2"], rtol=RTOL, atol=ATOL)
+        assert np.array_equal(valid, z["valid2"].astype(bool))
+    elif kind == "log_uniform":
+        # The torch backend normalises by log(R + 1) over R classes, the TF backend (the parity target,
+        # outputs/sampling/popularity.py:150-151) by log(R + 2) over R + 1: torch(max_id) == TF(max_id - 1).
+        for i, (max_id, min_id, n_sample) in enumerate(z["cases"].tolist()):
+            p = oracle.log_uniform_probs(max_id - 1, min_id, unique=False)
+            np.testing.assert_allclose(p, z[f"probs_{i}"], rtol=1e-5, atol=1e-7)
+            # "sampled at least once": TF computes 1 - (1 - p)^n as -expm1(n * log1p(-p)) (popularity.py:153-158);
+            # the torch backend's get_unique_sampling_distr applies log1p to +p, i.e. 1 - (1 + p)^-n — a different
+            # quantity.  TF is the parity target: the stored torch vector is only characterised, not matched.
+            p64 = p.astype(np.float64)
+            np.testing.assert_allclose(z[f"unique_{i}"], 1.0 - (1.0 + p64) ** (-float(n_sample)), rtol=2e-3, atol=2e-5)
+            u = oracle.log_uniform_probs(max_id - 1, min_id, unique=True, n_sampled=n_sample)
+            np.testing.assert_allclose(u, 1.0 - (1.0 - p64) ** float(n_sample), rtol=2e-3, atol=2e-5)  # p is stored in fp32
     elif kind == "oracle_model":
         spec = json.loads(str(z["spec"]))
         got = run_model_fixture(z, spec)

@@ -135,3 +135,40 @@ def test_golden_two_tower_model(device):
     batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
     pred = model(batch, training=True)
     np.testing.assert_allclose(pred.outputs.cpu().numpy(), z["expected"], rtol=2e-4, atol=2e-5)
+
+
+def test_reference_torch_contrastive_logits(device):
+    """Outputs of the reference's own torch ContrastiveOutput.contrastive_outputs / rescore_false_negatives
+    (tests/golden/ref_torch_contrastive.npz): [positive | negatives] layout, accidental hits == MIN_FLOAT exactly,
+    one-hot targets — against the CUDA scorer (tensor-core and exact-fp32 engines)."""
+    z = replay.load(G / "ref_torch_contrastive.npz")
+    q, pos, ids = dev(z["query"], device), dev(z["positive"], device), dev(z["ids"], device)
+    fns = float(z["min_float"])
+    out = mm.ContrastiveOutput(negative_samplers="in-batch", false_negative_score=fns)(
+        {"query": q, "candidate": pos}, candidate_ids=ids, training=True)
+    got = out.outputs.cpu().numpy()
+    hit = z["out_downscored"] == np.float32(fns)
+    assert np.array_equal(got == np.float32(fns), hit)            # the mask is exact (integer compare)
+    np.testing.assert_allclose(got[~hit], z["out_downscored"][~hit], rtol=RTOL, atol=2e-4)
+    assert np.array_equal(out.targets.cpu().numpy(), z["target"])
+    # exact-fp32 engine and a separate negative set (N != B)
+    B, N = z["scores2"].shape
+    buf = torch.empty((B, 1 + N), dtype=torch.float32, device=device)
+    ops.inbatch_scores(q, pos, dev(z["neg2"], device), buf, pos_ids=ids, neg_ids=dev(z["neg2_ids"], device), false_neg_score=fns,
+                       tensor_cores=False)
+    np.testing.assert_allclose(buf.cpu().numpy()[:, 1:], z["rescored2"], rtol=RTOL, atol=ATOL)
+    plain = torch.empty((B, 1 + B), dtype=torch.float32, device=device)
+    ops.inbatch_scores(q, pos, pos, plain, downscore=False, tensor_cores=False)
+    np.testing.assert_allclose(plain.cpu().numpy(), z["out_plain"], rtol=RTOL, atol=ATOL)
+
+
+def test_reference_torch_log_uniform_probabilities():
+    """mm.log_uniform_sampling_probs follows the TF formula (normaliser log(R + 2)); the reference's torch backend
+    computes the same expression one class short — torch(max_id) == ours(max_id - 1) (tests/golden/replay.py)."""
+    z = replay.load(G / "ref_torch_log_uniform.npz")
+    for i, (max_id, min_id, n_sample) in enumerate(z["cases"].tolist()):
+        p = mm.log_uniform_sampling_probs(max_id - 1, min_id, unique=False)
+        np.testing.assert_allclose(p, z[f"probs_{i}"], rtol=1e-5, atol=1e-7)
+        # unique=True follows TF's 1 - (1 - p)^n; the torch backend's variant (1 - (1 + p)^-n) is not the target
+        u = mm.log_uniform_sampling_probs(max_id - 1, min_id, max_num_samples=n_sample, unique=True)
+        np.testing.assert_allclose(u, 1.0 - (1.0 - p.astype(np.float64)) ** float(n_sample), rtol=2e-3, atol=2e-5)  # p is stored in fp32
