@@ -16,6 +16,9 @@ and runs the reference's module files unmodified, from where they lie:
   torch/blocks/cross.py     CrossBlock, LazyMirrorLinear
   torch/blocks/mlp.py       MLPBlock
   torch/inputs/embedding.py EmbeddingTable.forward_bag path via F.embedding_bag semantics
+  torch/blocks/dlrm.py      DLRMBlock END TO END (schema -> per-feature nn.Embedding tables -> bottom MLP over the
+                            concatenated continuous features -> Stack -> DLRMInteraction -> [bottom | interactions]
+                            -> top MLP), built from this repo's Schema shim standing in for merlin.schema
   torch/outputs/contrastive.py  ContrastiveOutput.contrastive_outputs ([positive | negatives] logits, one-hot
                             targets), rescore_false_negatives (accidental hits -> MIN_FLOAT)
   torch/outputs/sampling/in_batch.py   InBatchNegativeSampler
@@ -231,6 +234,37 @@ def main():
         blobs[f"probs_{i}"] = d.numpy()
         blobs[f"unique_{i}"] = u.numpy()
     np.savez(OUT / "ref_torch_log_uniform.npz", kind="log_uniform", cases=np.array(cases, dtype=np.int64), **blobs)
+    # ---- 8. the whole DLRMBlock of the reference's torch backend ----------------------------------
+    import models_b200.schema as S
+
+    cats = [("C1", 30), ("C10", 7), ("C2", 101), ("C21", 12), ("C3", 55)]      # Criteo-style names: 'C10' < 'C2'
+    conts = ["I1", "I10", "I2", "I3"]
+    cols = [S.ColumnSchema(n, tags=("categorical",), dtype="int64", properties={"domain": {"min": 0, "max": mx, "name": n}})
+            for n, mx in cats]
+    cols += [S.ColumnSchema(n, tags=("continuous",), dtype="float32") for n in conts]
+    torch.manual_seed(7)
+    dim, Bm = 16, 37
+    blk = dlrm.DLRMBlock(S.Schema(cols), dim, bottom_block=mlpm.MLPBlock([32, dim]), top_block=mlpm.MLPBlock([24, 8]))
+    batch = {n: rng.integers(0, mx + 1, Bm).astype(np.int64) for n, mx in cats}
+    batch.update({n: rng.random(Bm).astype(np.float32) for n in conts})
+    out = blk({k: torch.from_numpy(v) for k, v in batch.items()})
+    blobs = {}
+    lin_bottom, lin_top = [], []
+    for name, m in blk.named_modules():
+        if isinstance(m, torch.nn.Embedding):
+            feat = [n for n, _ in cats if f".{n}." in f".{name}."][0]
+            blobs[f"table_{feat}"] = m.weight.detach().numpy().copy()
+        elif isinstance(m, torch.nn.Linear):
+            (lin_bottom if ".continuous." in f".{name}." else lin_top).append(m)
+    assert len(lin_bottom) == 2 and len(lin_top) == 2 and len([k for k in blobs if k.startswith("table_")]) == len(cats)
+    for tag, lins in (("bottom", lin_bottom), ("top", lin_top)):
+        for i, l in enumerate(lins):
+            blobs[f"{tag}_kernel_{i}"] = l.weight.detach().numpy().T.copy()   # Keras layout (in, out)
+            blobs[f"{tag}_bias_{i}"] = l.bias.detach().numpy().copy()
+            blobs[f"{tag}_act_{i}"] = np.array("relu")
+    np.savez(OUT / "ref_torch_dlrm_block.npz", kind="dlrm_block", cat_names=np.array([n for n, _ in cats]),
+             cat_max=np.array([mx for _, mx in cats], dtype=np.int64), cont_names=np.array(conts), dim=np.int64(dim),
+             out=out.detach().numpy(), **{f"batch_{k}": v for k, v in batch.items()}, **blobs)
     print("wrote", sorted(p.name for p in OUT.glob("ref_torch_*.npz")))
 
 

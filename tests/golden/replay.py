@@ -78,6 +78,15 @@ def check(path: Path) -> None:
             np.testing.assert_allclose(z[f"unique_{i}"], 1.0 - (1.0 + p64) ** (-float(n_sample)), rtol=2e-3, atol=2e-5)
             u = oracle.log_uniform_probs(max_id - 1, min_id, unique=True, n_sampled=n_sample)
             np.testing.assert_allclose(u, 1.0 - (1.0 - p64) ** float(n_sample), rtol=2e-3, atol=2e-5)  # p is stored in fp32
+    elif kind == "dlrm_block":
+        # the reference torch DLRMBlock executed end to end: tables, bottom MLP, sorted stack, interaction,
+        # [bottom | interactions], top MLP
+        cat = [str(n) for n in z["cat_names"]]
+        batch = {k[len("batch_"):]: z[k] for k in z if k.startswith("batch_")}
+        tables = {n: z[f"table_{n}"] for n in cat}
+        got = oracle.dlrm_forward(batch, tables, {n: n for n in cat}, [str(n) for n in z["cont_names"]],
+                                  unpack_layers(z, "bottom"), unpack_layers(z, "top"), None)
+        np.testing.assert_allclose(got, z["out"], rtol=1e-4, atol=1e-5)
     elif kind == "oracle_model":
         spec = json.loads(str(z["spec"]))
         got = run_model_fixture(z, spec)

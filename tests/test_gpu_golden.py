@@ -172,3 +172,35 @@ def test_reference_torch_log_uniform_probabilities():
         # unique=True follows TF's 1 - (1 - p)^n; the torch backend's variant (1 - (1 + p)^-n) is not the target
         u = mm.log_uniform_sampling_probs(max_id - 1, min_id, max_num_samples=n_sample, unique=True)
         np.testing.assert_allclose(u, 1.0 - (1.0 - p.astype(np.float64)) ** float(n_sample), rtol=2e-3, atol=2e-5)  # p is stored in fp32
+
+
+def test_reference_torch_dlrm_block_end_to_end(device):
+    """The reference's torch DLRMBlock executed end to end in the build container
+    (tests/golden/ref_torch_dlrm_block.npz: schema -> embeddings -> bottom MLP -> sorted stack -> interaction ->
+    [bottom | interactions] -> top MLP) against mm.DLRMBlock with the same tables and kernels — fused and staged
+    paths, tensor-core and exact-fp32 dense engines."""
+    from models_b200 import blocks
+    from models_b200.schema import ColumnSchema, Schema
+
+    z = replay.load(G / "ref_torch_dlrm_block.npz")
+    cat = [str(n) for n in z["cat_names"]]
+    cols = [ColumnSchema(n, tags=("categorical",), dtype="int64", properties={"domain": {"min": 0, "max": int(mx), "name": n}})
+            for n, mx in zip(cat, z["cat_max"])]
+    cols += [ColumnSchema(str(n), tags=("continuous",), dtype="float32") for n in z["cont_names"]]
+    dim = int(z["dim"])
+    body = mm.DLRMBlock(Schema(cols), embedding_dim=dim, bottom_block=mm.MLPBlock([32, dim]), top_block=mm.MLPBlock([24, 8]))
+    _set_tables(body.embeddings, z)
+    _set_mlp(body.bottom_block, replay.unpack_layers(z, "bottom"))
+    _set_mlp(body.top_block, replay.unpack_layers(z, "top"))
+    body.build(device)  # nothing left to initialise: every variable was assigned above
+    batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
+    for engine in ("auto", "fp32"):
+        blocks.set_dense_engine(engine)
+        try:
+            for fused in (True, False):
+                body.fused = fused
+                got = body(batch).cpu().numpy()
+                assert got.shape == z["out"].shape
+                np.testing.assert_allclose(got, z["out"], rtol=2e-4, atol=2e-5)
+        finally:
+            blocks.set_dense_engine("auto")
