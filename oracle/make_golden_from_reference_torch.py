@@ -19,6 +19,9 @@ and runs the reference's module files unmodified, from where they lie:
   torch/blocks/dlrm.py      DLRMBlock END TO END (schema -> per-feature nn.Embedding tables -> bottom MLP over the
                             concatenated continuous features -> Stack -> DLRMInteraction -> [bottom | interactions]
                             -> top MLP), built from this repo's Schema shim standing in for merlin.schema
+  torch/models/ranking.py   DLRMModel and DCNModel END TO END including BinaryOutput (Linear(1) + sigmoid): the
+                            model-level outputs {target: (B, 1)} (pytorch_lightning.LightningModule is replaced by
+                            an empty torch.nn.Module subclass)
   torch/outputs/contrastive.py  ContrastiveOutput.contrastive_outputs ([positive | negatives] logits, one-hot
                             targets), rescore_false_negatives (accidental hits -> MIN_FLOAT)
   torch/outputs/sampling/in_batch.py   InBatchNegativeSampler
@@ -113,7 +116,12 @@ def install_stand_ins():
     tm = _ns("torchmetrics", None, Metric=_Inert, AUROC=_Inert, Accuracy=_Inert, Precision=_Inert, Recall=_Inert,
              MeanSquaredError=_Inert, MetricCollection=_Inert)
     tm.__getattr__ = lambda name: _Inert  # any other metric class (RetrievalHitRate, ...) is an inert placeholder
-    _ns("pytorch_lightning", None, LightningModule=object, Trainer=_Inert, LightningDataModule=object)
+    import torch
+
+    class LightningModule(torch.nn.Module):  # stand-in base of models/base.py Model(LightningModule, Block)
+        pass
+
+    _ns("pytorch_lightning", None, LightningModule=LightningModule, Trainer=_Inert, LightningDataModule=object)
     _ns("merlin.models", REF / "merlin" / "models")
     _ns("merlin.models.torch", REF / "merlin" / "models" / "torch")
     for sub in ("blocks", "inputs", "utils", "transforms", "outputs", "models"):
@@ -265,6 +273,57 @@ def main():
     np.savez(OUT / "ref_torch_dlrm_block.npz", kind="dlrm_block", cat_names=np.array([n for n, _ in cats]),
              cat_max=np.array([mx for _, mx in cats], dtype=np.int64), cont_names=np.array(conts), dim=np.int64(dim),
              out=out.detach().numpy(), **{f"batch_{k}": v for k, v in batch.items()}, **blobs)
+    # ---- 9. DLRMModel / DCNModel of the torch backend, BinaryOutput included ----------------------
+    ranking = importlib.import_module("merlin.models.torch.models.ranking")
+    target = S.ColumnSchema("click", tags=("target", "binary_classification"), dtype="int64")
+    mschema = S.Schema(cols + [target])
+    feed = {k: torch.from_numpy(v) for k, v in batch.items()}
+
+    def linears(module):
+        return [(n, m) for n, m in module.named_modules() if isinstance(m, torch.nn.Linear)]
+
+    def tables_of(module):
+        out = {}
+        for name, m in module.named_modules():
+            if isinstance(m, torch.nn.Embedding):
+                feat = [n for n, _ in cats if f".{n}." in f".{name}."][0]
+                out[f"table_{feat}"] = m.weight.detach().numpy().copy()
+        return out
+
+    def pack(tag, lins, act):
+        d = {}
+        for i, l in enumerate(lins):
+            d[f"{tag}_kernel_{i}"] = l.weight.detach().numpy().T.copy()
+            d[f"{tag}_bias_{i}"] = l.bias.detach().numpy().copy()
+            d[f"{tag}_act_{i}"] = np.array(act)
+        return d
+
+    torch.manual_seed(11)
+    dm = ranking.DLRMModel(mschema, dim=dim, bottom_block=mlpm.MLPBlock([32, dim]), top_block=mlpm.MLPBlock([24, 8]))
+    dout = dm(feed)["click"]
+    L = linears(dm)
+    assert len(L) == 5
+    np.savez(OUT / "ref_torch_dlrm_model.npz", kind="dlrm_model", cat_names=np.array([n for n, _ in cats]),
+             cat_max=np.array([mx for _, mx in cats], dtype=np.int64), cont_names=np.array(conts), dim=np.int64(dim),
+             out=dout.detach().numpy(), **{f"batch_{k}": v for k, v in batch.items()}, **tables_of(dm),
+             **pack("bottom", [m for n, m in L if ".continuous." in f".{n}."], "relu"),
+             **pack("top", [m for n, m in L if ".continuous." not in f".{n}."][:2], "relu"),
+             **pack("head", [L[-1][1]], "sigmoid"))
+
+    torch.manual_seed(12)
+    cm = ranking.DCNModel(mschema, depth=3, deep_block=mlpm.MLPBlock([32, 16]))
+    cout = cm(feed)["click"]
+    L = linears(cm)
+    tabs = tables_of(cm)
+    d_in = sum(t.shape[1] for t in tabs.values()) + len(conts)
+    cross_l = [m for n, m in L if m.in_features == d_in and m.out_features == d_in]
+    rest = [m for n, m in L if not (m.in_features == d_in and m.out_features == d_in)]
+    assert len(cross_l) == 3 and len(rest) == 3
+    np.savez(OUT / "ref_torch_dcn_model.npz", kind="dcn_model", cat_names=np.array([n for n, _ in cats]),
+             cat_max=np.array([mx for _, mx in cats], dtype=np.int64), cont_names=np.array(conts),
+             emb_dims=np.array([tabs[f"table_{n}"].shape[1] for n, _ in cats], dtype=np.int64), out=cout.detach().numpy(),
+             **{f"batch_{k}": v for k, v in batch.items()}, **tabs, **pack("cross", cross_l, "linear"),
+             **pack("deep", rest[:2], "relu"), **pack("head", [rest[2]], "sigmoid"))
     print("wrote", sorted(p.name for p in OUT.glob("ref_torch_*.npz")))
 
 

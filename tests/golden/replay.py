@@ -87,6 +87,20 @@ def check(path: Path) -> None:
         got = oracle.dlrm_forward(batch, tables, {n: n for n in cat}, [str(n) for n in z["cont_names"]],
                                   unpack_layers(z, "bottom"), unpack_layers(z, "top"), None)
         np.testing.assert_allclose(got, z["out"], rtol=1e-4, atol=1e-5)
+    elif kind in ("dlrm_model", "dcn_model"):
+        # the reference's torch DLRMModel / DCNModel executed end to end, BinaryOutput (Linear(1) + sigmoid) included
+        cat = [str(n) for n in z["cat_names"]]
+        batch = {k[len("batch_"):]: z[k] for k in z if k.startswith("batch_")}
+        tables = {n: z[f"table_{n}"] for n in cat}
+        cont = [str(n) for n in z["cont_names"]]
+        head = unpack_layers(z, "head")[0]
+        if kind == "dlrm_model":
+            got = oracle.dlrm_forward(batch, tables, {n: n for n in cat}, cont, unpack_layers(z, "bottom"),
+                                      unpack_layers(z, "top"), head)
+        else:
+            cross = [{"kernel": l["kernel"], "bias": l["bias"]} for l in unpack_layers(z, "cross")]
+            got = oracle.dcn_forward(batch, tables, {n: n for n in cat}, cont, cross, unpack_layers(z, "deep"), head)
+        np.testing.assert_allclose(got, z["out"], rtol=1e-4, atol=1e-5)
     elif kind == "oracle_model":
         spec = json.loads(str(z["spec"]))
         got = run_model_fixture(z, spec)

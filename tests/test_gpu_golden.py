@@ -204,3 +204,53 @@ def test_reference_torch_dlrm_block_end_to_end(device):
                 np.testing.assert_allclose(got, z["out"], rtol=2e-4, atol=2e-5)
         finally:
             blocks.set_dense_engine("auto")
+
+
+def _ref_schema(z, with_target=True):
+    from models_b200.schema import ColumnSchema, Schema
+
+    cols = [ColumnSchema(str(n), tags=("categorical",), dtype="int64", properties={"domain": {"min": 0, "max": int(mx), "name": str(n)}})
+            for n, mx in zip(z["cat_names"], z["cat_max"])]
+    cols += [ColumnSchema(str(n), tags=("continuous",), dtype="float32") for n in z["cont_names"]]
+    if with_target:
+        cols.append(ColumnSchema("click", tags=("target", "binary_classification"), dtype="int64"))
+    return Schema(cols)
+
+
+def test_reference_torch_dlrm_model_end_to_end(device):
+    """merlin.models.torch DLRMModel (DLRMBlock + BinaryOutput) executed in the build container -> mm.DLRMModel."""
+    z = replay.load(G / "ref_torch_dlrm_model.npz")
+    dim = int(z["dim"])
+    model = mm.DLRMModel(_ref_schema(z), embedding_dim=dim, bottom_block=mm.MLPBlock([32, dim]), top_block=mm.MLPBlock([24, 8]))
+    _set_tables(model.body.embeddings, z)
+    _set_mlp(model.body.bottom_block, replay.unpack_layers(z, "bottom"))
+    _set_mlp(model.body.top_block, replay.unpack_layers(z, "top"))
+    h = replay.unpack_layers(z, "head")[0]
+    model.prediction.to_call.set_weights(h["kernel"], h["bias"])
+    batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
+    for fused in (True, False):
+        model.body.fused = fused
+        got = model(batch).cpu().numpy()
+        np.testing.assert_allclose(got, z["out"], rtol=2e-4, atol=2e-6)
+    cf = model.compile({k: v.cpu().numpy() for k, v in batch.items()})  # the CUDA-graph runtime gives the same numbers
+    hb = mm.HostBatch.like({k: v.cpu().numpy() for k, v in batch.items()}, model.input_columns())
+    np.testing.assert_allclose(cf(hb).numpy(), z["out"], rtol=2e-4, atol=2e-6)
+
+
+def test_reference_torch_dcn_model_end_to_end(device):
+    """merlin.models.torch DCNModel (embeddings + continuous -> sorted concat -> CrossBlock(3) -> MLP -> BinaryOutput)."""
+    z = replay.load(G / "ref_torch_dcn_model.npz")
+    dims = {str(n): int(d) for n, d in zip(z["cat_names"], z["emb_dims"])}
+    model = mm.DCNModel(_ref_schema(z), depth=3, deep_block=mm.MLPBlock([32, 16]), dim=dims)
+    _set_tables(model.body.input_block.embeddings, z)
+    cross = replay.unpack_layers(z, "cross")
+    d = cross[0]["kernel"].shape[0]
+    assert d == sum(dims.values()) + len(z["cont_names"])
+    for l, w in zip(model.body.cross.cross_layers, cross):
+        l.build(d, device)
+        l.dense.set_weights(w["kernel"], w["bias"])
+    _set_mlp(model.body.deep, replay.unpack_layers(z, "deep"))
+    h = replay.unpack_layers(z, "head")[0]
+    model.prediction.to_call.set_weights(h["kernel"], h["bias"])
+    batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
+    np.testing.assert_allclose(model(batch).cpu().numpy(), z["out"], rtol=2e-4, atol=2e-6)
