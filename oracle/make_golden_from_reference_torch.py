@@ -22,6 +22,8 @@ and runs the reference's module files unmodified, from where they lie:
   torch/models/ranking.py   DLRMModel and DCNModel END TO END including BinaryOutput (Linear(1) + sigmoid): the
                             model-level outputs {target: (B, 1)} (pytorch_lightning.LightningModule is replaced by
                             an empty torch.nn.Module subclass)
+  torch/outputs/classification.py  EmbeddingTablePrediction (weight-tied catalog logits x @ E^T + bias) with the
+                            backend's default loss nn.CrossEntropyLoss evaluated on them
   torch/outputs/contrastive.py  ContrastiveOutput.contrastive_outputs ([positive | negatives] logits, one-hot
                             targets), rescore_false_negatives (accidental hits -> MIN_FLOAT)
   torch/outputs/sampling/in_batch.py   InBatchNegativeSampler
@@ -324,6 +326,23 @@ def main():
              emb_dims=np.array([tabs[f"table_{n}"].shape[1] for n, _ in cats], dtype=np.int64), out=cout.detach().numpy(),
              **{f"batch_{k}": v for k, v in batch.items()}, **tabs, **pack("cross", cross_l, "linear"),
              **pack("deep", rest[:2], "relu"), **pack("head", [rest[2]], "sigmoid"))
+    # ---- 10. weight-tied catalog logits (CategoricalOutput / EmbeddingTablePrediction) -------------
+    clsm = importlib.import_module("merlin.models.torch.outputs.classification")
+    item = S.ColumnSchema("item_id", tags=("categorical", "item_id"), dtype="int64",
+                          properties={"domain": {"min": 0, "max": 299, "name": "item_id"}})
+    torch.manual_seed(13)
+    etab = emb.EmbeddingTable(16, S.Schema([item]))
+    pred = clsm.EmbeddingTablePrediction(etab)
+    with torch.no_grad():
+        pred.bias.copy_(torch.from_numpy((rng.standard_normal(pred.num_classes) * 0.1).astype(np.float32)))
+    xq = rng.standard_normal((41, 16)).astype(np.float32)
+    tgt = rng.integers(0, 300, 41).astype(np.int64)
+    logits = pred(torch.from_numpy(xq))
+    ce = torch.nn.CrossEntropyLoss(reduction="none")(logits, torch.from_numpy(tgt))   # the backend's default loss
+    tk = torch.topk(logits, 10, dim=1)
+    np.savez(OUT / "ref_torch_catalog.npz", kind="catalog", table=pred.embeddings().detach().numpy().copy(),
+             bias=pred.bias.detach().numpy().copy(), x=xq, targets=tgt, logits=logits.detach().numpy(),
+             cross_entropy=ce.detach().numpy(), topk_scores=tk.values.detach().numpy(), topk_ids=tk.indices.numpy())
     print("wrote", sorted(p.name for p in OUT.glob("ref_torch_*.npz")))
 
 

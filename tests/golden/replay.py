@@ -87,6 +87,15 @@ def check(path: Path) -> None:
         got = oracle.dlrm_forward(batch, tables, {n: n for n in cat}, [str(n) for n in z["cont_names"]],
                                   unpack_layers(z, "bottom"), unpack_layers(z, "top"), None)
         np.testing.assert_allclose(got, z["out"], rtol=1e-4, atol=1e-5)
+    elif kind == "catalog":
+        # reference torch EmbeddingTablePrediction: logits = x @ E^T + bias; nn.CrossEntropyLoss on them; top-k
+        logits = oracle.catalog_logits(z["x"], z["table"], z["bias"])
+        np.testing.assert_allclose(logits, z["logits"], rtol=RTOL, atol=1e-5)
+        st = oracle.softmax_ce_stats(logits, z["targets"])
+        np.testing.assert_allclose(st[:, 1] - st[:, 2], z["cross_entropy"], rtol=1e-4, atol=1e-5)
+        s, ids = oracle.topk(logits, z["topk_scores"].shape[1])
+        np.testing.assert_allclose(s, z["topk_scores"], rtol=RTOL, atol=1e-5)
+        assert np.array_equal(ids, z["topk_ids"])
     elif kind in ("dlrm_model", "dcn_model"):
         # the reference's torch DLRMModel / DCNModel executed end to end, BinaryOutput (Linear(1) + sigmoid) included
         cat = [str(n) for n in z["cat_names"]]

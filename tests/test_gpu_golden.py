@@ -254,3 +254,27 @@ def test_reference_torch_dcn_model_end_to_end(device):
     model.prediction.to_call.set_weights(h["kernel"], h["bias"])
     batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
     np.testing.assert_allclose(model(batch).cpu().numpy(), z["out"], rtol=2e-4, atol=2e-6)
+
+
+def test_reference_torch_catalog_logits_ce_and_topk(device):
+    """merlin.models.torch EmbeddingTablePrediction (x @ E^T + bias) + the backend's nn.CrossEntropyLoss + top-k,
+    executed in the build container -> mm.CategoricalOutput: materialised logits, and the fused kernel's
+    log-sum-exp statistics / top-k that never materialise them."""
+    from models_b200.schema import ColumnSchema
+
+    z = replay.load(G / "ref_torch_catalog.npz")
+    n_items, D = z["table"].shape
+    col = ColumnSchema("item_id", tags=("categorical", "item_id"), dtype="int64",
+                       properties={"domain": {"min": 0, "max": n_items - 1, "name": "item_id"}})
+    table = mm.EmbeddingTable(D, col, embeddings_initializer=z["table"])
+    out = mm.CategoricalOutput(table)
+    out.build(device)
+    out.bias.copy_(dev(z["bias"], device))
+    x, t = dev(z["x"], device), dev(z["targets"], device)
+    np.testing.assert_allclose(out(x).cpu().numpy(), z["logits"], rtol=1e-4, atol=2e-4)
+    stats = out.softmax_ce_stats(x, t).cpu().numpy()           # (max, log-sum-exp, target logit) per row
+    np.testing.assert_allclose(stats[:, 1] - stats[:, 2], z["cross_entropy"], rtol=1e-4, atol=3e-4)
+    scores, ids = out.top_k(x, z["topk_scores"].shape[1])
+    np.testing.assert_allclose(scores.cpu().numpy(), z["topk_scores"], rtol=1e-4, atol=2e-4)
+    gap = np.abs(np.diff(z["topk_scores"], axis=1)).min(axis=1) > 1e-3
+    assert gap.any() and np.array_equal(ids.cpu().numpy()[gap], z["topk_ids"][gap])
