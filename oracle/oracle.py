@@ -21,7 +21,8 @@ PINNING STATUS
     (oracle/make_golden_from_reference_torch.py -> tests/golden/ref_torch_*.npz): sorted-name concat / stack
     order, DLRM interaction ordering/values and the [bottom | interactions] concat, the WHOLE DLRMBlock end to end
     (tables -> bottom MLP -> stack -> interaction -> top MLP; ref_torch_dlrm_block.npz) and the torch DLRMModel /
-    DCNModel with BinaryOutput (ref_torch_dlrm_model.npz, ref_torch_dcn_model.npz), embedding-bag combiners,
+    DCNModel with BinaryOutput (ref_torch_dlrm_model.npz, ref_torch_dcn_model.npz), weight-tied catalog logits +
+    cross-entropy + top-k (EmbeddingTablePrediction, ref_torch_catalog.npz), embedding-bag combiners,
     MLP, DCN-v2 cross, the [positive | negatives] logits layout with false-negative rescoring and one-hot
     targets (ContrastiveOutput.contrastive_outputs, rescore_false_negatives, InBatchNegativeSampler), the
     log-uniform sampling distribution (the torch backend is one class short of the TF formula and its
