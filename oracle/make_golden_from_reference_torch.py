@@ -326,6 +326,40 @@ def main():
              emb_dims=np.array([tabs[f"table_{n}"].shape[1] for n, _ in cats], dtype=np.int64), out=cout.detach().numpy(),
              **{f"batch_{k}": v for k, v in batch.items()}, **tabs, **pack("cross", cross_l, "linear"),
              **pack("deep", rest[:2], "relu"), **pack("head", [rest[2]], "sigmoid"))
+    # ---- 9b. DCNModel over a schema with a ragged multi-hot feature (name__values / name__offsets) ----
+    cats_mh = [("C1", 30), ("C10", 7), ("genres", 18)]
+    cols_mh = [S.ColumnSchema("C1", tags=("categorical",), dtype="int64", properties={"domain": {"min": 0, "max": 30, "name": "C1"}}),
+               S.ColumnSchema("C10", tags=("categorical",), dtype="int64", properties={"domain": {"min": 0, "max": 7, "name": "C10"}}),
+               S.ColumnSchema("genres", tags=("categorical",), dtype="int64", is_list=True, is_ragged=True,
+                              properties={"domain": {"min": 0, "max": 18, "name": "genres"}, "value_count": {"min": 1, "max": 4}}),
+               S.ColumnSchema("I1", tags=("continuous",), dtype="float32"), S.ColumnSchema("I2", tags=("continuous",), dtype="float32"),
+               target]
+    lens = rng.integers(1, 5, Bm)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    batch_mh = {"C1": rng.integers(0, 31, Bm).astype(np.int64), "C10": rng.integers(0, 8, Bm).astype(np.int64),
+                "genres__values": rng.integers(0, 19, int(offs[-1])).astype(np.int64), "genres__offsets": offs,
+                "I1": rng.random(Bm).astype(np.float32), "I2": rng.random(Bm).astype(np.float32)}
+    torch.manual_seed(14)
+    mh = ranking.DCNModel(S.Schema(cols_mh), depth=2, deep_block=mlpm.MLPBlock([16, 8]))
+    mh_out = mh({k: torch.from_numpy(v) for k, v in batch_mh.items()})["click"]
+    combiners = {getattr(m, "seq_combiner") for _, m in mh.named_modules() if isinstance(getattr(m, "seq_combiner", None), str)}
+    assert combiners == {"mean"}, combiners   # the default bag combiner of the backend
+    tabs = {}
+    for name, m in mh.named_modules():
+        if isinstance(m, torch.nn.Embedding):
+            feat = [n for n, _ in cats_mh if f".{n}." in f".{name}."][0]
+            tabs[f"table_{feat}"] = m.weight.detach().numpy().copy()
+    L = linears(mh)
+    d_in = sum(t.shape[1] for t in tabs.values()) + 2
+    cross_l = [m for n, m in L if m.in_features == d_in and m.out_features == d_in]
+    rest = [m for n, m in L if not (m.in_features == d_in and m.out_features == d_in)]
+    assert len(cross_l) == 2 and len(rest) == 3
+    np.savez(OUT / "ref_torch_dcn_multihot.npz", kind="dcn_model", cat_names=np.array([n for n, _ in cats_mh]),
+             cat_max=np.array([mx for _, mx in cats_mh], dtype=np.int64), cont_names=np.array(["I1", "I2"]),
+             list_names=np.array(["genres"]), emb_dims=np.array([tabs[f"table_{n}"].shape[1] for n, _ in cats_mh], dtype=np.int64),
+             out=mh_out.detach().numpy(), **{f"batch_{k}": v for k, v in batch_mh.items()}, **tabs,
+             **pack("cross", cross_l, "linear"), **pack("deep", rest[:2], "relu"), **pack("head", [rest[2]], "sigmoid"))
+
     # ---- 10. weight-tied catalog logits (CategoricalOutput / EmbeddingTablePrediction) -------------
     clsm = importlib.import_module("merlin.models.torch.outputs.classification")
     item = S.ColumnSchema("item_id", tags=("categorical", "item_id"), dtype="int64",

@@ -209,8 +209,14 @@ def test_reference_torch_dlrm_block_end_to_end(device):
 def _ref_schema(z, with_target=True):
     from models_b200.schema import ColumnSchema, Schema
 
-    cols = [ColumnSchema(str(n), tags=("categorical",), dtype="int64", properties={"domain": {"min": 0, "max": int(mx), "name": str(n)}})
-            for n, mx in zip(z["cat_names"], z["cat_max"])]
+    lists = {str(n) for n in z["list_names"]} if "list_names" in z else set()
+    cols = []
+    for n, mx in zip(z["cat_names"], z["cat_max"]):
+        n = str(n)
+        props = {"domain": {"min": 0, "max": int(mx), "name": n}}
+        if n in lists:
+            props["value_count"] = {"min": 1, "max": 4}
+        cols.append(ColumnSchema(n, tags=("categorical",), dtype="int64", is_list=n in lists, is_ragged=n in lists, properties=props))
     cols += [ColumnSchema(str(n), tags=("continuous",), dtype="float32") for n in z["cont_names"]]
     if with_target:
         cols.append(ColumnSchema("click", tags=("target", "binary_classification"), dtype="int64"))
@@ -278,3 +284,25 @@ def test_reference_torch_catalog_logits_ce_and_topk(device):
     np.testing.assert_allclose(scores.cpu().numpy(), z["topk_scores"], rtol=1e-4, atol=2e-4)
     gap = np.abs(np.diff(z["topk_scores"], axis=1)).min(axis=1) > 1e-3
     assert gap.any() and np.array_equal(ids.cpu().numpy()[gap], z["topk_ids"][gap])
+
+
+def test_reference_torch_dcn_with_ragged_multi_hot_feature(device):
+    """merlin.models.torch DCNModel over a schema with a list column fed as `genres__values` / `genres__offsets`
+    (the backend's default bag combiner is "mean"): pins the ragged input convention and the bag lookup in context."""
+    z = replay.load(G / "ref_torch_dcn_multihot.npz")
+    dims = {str(n): int(d) for n, d in zip(z["cat_names"], z["emb_dims"])}
+    model = mm.DCNModel(_ref_schema(z), depth=2, deep_block=mm.MLPBlock([16, 8]), dim=dims)
+    _set_tables(model.body.input_block.embeddings, z)
+    cross = replay.unpack_layers(z, "cross")
+    d = cross[0]["kernel"].shape[0]
+    for l, w in zip(model.body.cross.cross_layers, cross):
+        l.build(d, device)
+        l.dense.set_weights(w["kernel"], w["bias"])
+    _set_mlp(model.body.deep, replay.unpack_layers(z, "deep"))
+    h = replay.unpack_layers(z, "head")[0]
+    model.prediction.to_call.set_weights(h["kernel"], h["bias"])
+    batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
+    assert "genres__values" in batch and "genres__offsets" in batch
+    np.testing.assert_allclose(model(batch).cpu().numpy(), z["out"], rtol=2e-4, atol=2e-6)
+    batch32 = dict(batch, genres__offsets=batch["genres__offsets"].to(torch.int32))  # the loader's int32 offsets
+    np.testing.assert_allclose(model(batch32).cpu().numpy(), z["out"], rtol=2e-4, atol=2e-6)
