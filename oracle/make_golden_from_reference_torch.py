@@ -377,6 +377,23 @@ def main():
     np.savez(OUT / "ref_torch_catalog.npz", kind="catalog", table=pred.embeddings().detach().numpy().copy(),
              bias=pred.bias.detach().numpy().copy(), x=xq, targets=tgt, logits=logits.detach().numpy(),
              cross_entropy=ce.detach().numpy(), topk_scores=tk.values.detach().numpy(), topk_ids=tk.indices.numpy())
+    # ---- 11. MLPBlock with every activation the hot path offers (torch modules = Keras definitions:
+    #          GELU erf-based, SELU/ELU with the standard constants) -------------------------------
+    xa = (rng.standard_normal((Bm, 11)) * 2.5).astype(np.float32)
+    act_blobs = {}
+    for aname, amod in (("sigmoid", torch.nn.Sigmoid), ("tanh", torch.nn.Tanh), ("selu", torch.nn.SELU), ("elu", torch.nn.ELU),
+                        ("gelu", torch.nn.GELU), ("relu", torch.nn.ReLU)):
+        torch.manual_seed(21)
+        blk_a = mlpm.MLPBlock([24, 9], activation=amod)
+        ya = blk_a(torch.from_numpy(xa))
+        lins_a = [m for m in blk_a.modules() if isinstance(m, torch.nn.Linear)]
+        act_blobs[f"out_{aname}"] = ya.detach().numpy()
+        for i, l in enumerate(lins_a):  # same seed -> same weights for every activation; store once per name anyway
+            act_blobs[f"{aname}_kernel_{i}"] = l.weight.detach().numpy().T.copy()
+            act_blobs[f"{aname}_bias_{i}"] = l.bias.detach().numpy().copy()
+    np.savez(OUT / "ref_torch_mlp_activations.npz", kind="mlp_acts", x=xa,
+             names=np.array(["sigmoid", "tanh", "selu", "elu", "gelu", "relu"]), **act_blobs)
+
     print("wrote", sorted(p.name for p in OUT.glob("ref_torch_*.npz")))
 
 

@@ -87,6 +87,10 @@ def check(path: Path) -> None:
         got = oracle.dlrm_forward(batch, tables, {n: n for n in cat}, [str(n) for n in z["cont_names"]],
                                   unpack_layers(z, "bottom"), unpack_layers(z, "top"), None)
         np.testing.assert_allclose(got, z["out"], rtol=1e-4, atol=1e-5)
+    elif kind == "mlp_acts":
+        for name in [str(n) for n in z["names"]]:
+            layers = layers_from(z, prefix=f"{name}_", act=name)
+            np.testing.assert_allclose(oracle.mlp(z["x"], layers), z[f"out_{name}"], rtol=1e-4, atol=1e-5, err_msg=name)
     elif kind == "catalog":
         # reference torch EmbeddingTablePrediction: logits = x @ E^T + bias; nn.CrossEntropyLoss on them; top-k
         logits = oracle.catalog_logits(z["x"], z["table"], z["bias"])

@@ -306,3 +306,21 @@ def test_reference_torch_dcn_with_ragged_multi_hot_feature(device):
     np.testing.assert_allclose(model(batch).cpu().numpy(), z["out"], rtol=2e-4, atol=2e-6)
     batch32 = dict(batch, genres__offsets=batch["genres__offsets"].to(torch.int32))  # the loader's int32 offsets
     np.testing.assert_allclose(model(batch32).cpu().numpy(), z["out"], rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("engine", ["auto", "fp32"])
+def test_reference_torch_mlp_activations(device, engine):
+    """MLPBlock([24, 9], activation=nn.{Sigmoid,Tanh,SELU,ELU,GELU,ReLU}) of the torch backend -> mm.MLPBlock with the
+    same kernels: pins the activation definitions of the GEMM epilogues (erf GELU, SELU/ELU constants)."""
+    from models_b200 import blocks
+
+    z = replay.load(G / "ref_torch_mlp_activations.npz")
+    x = dev(z["x"], device)
+    blocks.set_dense_engine(engine)
+    try:
+        for name in [str(n) for n in z["names"]]:
+            mlp = mm.MLPBlock([24, 9], activation=name)
+            _set_mlp(mlp, replay.layers_from(z, prefix=f"{name}_", act=name))
+            np.testing.assert_allclose(mlp(x).cpu().numpy(), z[f"out_{name}"], rtol=2e-4, atol=2e-5, err_msg=name)
+    finally:
+        blocks.set_dense_engine("auto")
