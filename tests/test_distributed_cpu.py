@@ -88,3 +88,41 @@ def test_sharded_protocol_world2_gloo():
     result = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), result), nprocs=world, join=True)
     assert dict(result) == {0: True, 1: True}
+
+
+def _loader_worker(rank, world, port, result):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 1003
+        data = {"row": np.arange(n, dtype=np.int64), "x": np.arange(n, dtype=np.float32) * 0.5, "y": (np.arange(n) % 2).astype(np.int64)}
+        loader = mm.Loader(data, batch_size=100, shuffle=True, seed_fn=lambda: 99, label_names=["y"], device="cpu",
+                           global_size=dist.get_world_size(), global_rank=dist.get_rank())
+        rows = torch.cat([b[0]["row"] for b in loader]).to(torch.int64)
+        for inputs, targets in loader:  # features and targets stay aligned with their rows after the sharded shuffle
+            assert torch.equal(inputs["x"], inputs["row"].to(torch.float32) * 0.5)
+            assert torch.equal(targets, inputs["row"] % 2)
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([rows.numel()]))
+        pad = torch.full((int(max(s.item() for s in sizes)),), -1, dtype=torch.int64)
+        pad[: rows.numel()] = rows
+        gathered = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(gathered, pad)
+        allrows = torch.cat(gathered)
+        allrows = allrows[allrows >= 0]
+        ok = allrows.numel() == n and torch.equal(torch.sort(allrows).values, torch.arange(n))
+        ok = ok and abs(rows.numel() - n / world) <= 1 and len(loader) == (rows.numel() + 99) // 100
+        result[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loader_shards_partition_the_dataset_across_ranks():
+    """One Loader per process (as one rank per GPU): the ranks' shuffled shards are disjoint, equally sized (±1) and
+    together cover every row exactly once — checked with a gloo all_gather over world_size 2."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_loader_worker, args=(world, port, result), nprocs=world, join=True)
+    assert dict(result) == {0: True, 1: True}
