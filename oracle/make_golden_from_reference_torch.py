@@ -24,6 +24,8 @@ and runs the reference's module files unmodified, from where they lie:
                             an empty torch.nn.Module subclass)
   torch/outputs/classification.py  EmbeddingTablePrediction (weight-tied catalog logits x @ E^T + bias) with the
                             backend's default loss nn.CrossEntropyLoss evaluated on them
+  utils/schema_utils.py     infer_embedding_dim / get_embedding_size_from_cardinality (backend-independent host code,
+                            the default dims of InputBlockV2 / DCNModel: sum = 1024 on the bundled Criteo schema)
   torch/outputs/contrastive.py  ContrastiveOutput.contrastive_outputs ([positive | negatives] logits, one-hot
                             targets), rescore_false_negatives (accidental hits -> MIN_FLOAT)
   torch/outputs/sampling/in_batch.py   InBatchNegativeSampler
@@ -394,6 +396,18 @@ def main():
     np.savez(OUT / "ref_torch_mlp_activations.npz", kind="mlp_acts", x=xa,
              names=np.array(["sigmoid", "tanh", "selu", "elu", "gelu", "relu"]), **act_blobs)
 
+    # ---- 12. inferred embedding dims (merlin/models/utils/schema_utils.py:169-207) ------------------
+    su = importlib.import_module("merlin.models.utils.schema_utils")
+    from models_b200 import datasets as _ds
+
+    names = sorted(_ds.CRITEO_MAX)
+    maxes = np.array([_ds.CRITEO_MAX[n] for n in names] + [0, 1, 2, 15, 16, 255, 256, 4095, 10**6, 4 * 10**7], dtype=np.int64)
+    colsd = [S.ColumnSchema(f"f{i}", tags=("categorical",), dtype="int64", properties={"domain": {"min": 0, "max": int(m), "name": f"f{i}"}})
+             for i, m in enumerate(maxes)]
+    dims_default = np.array([su.infer_embedding_dim(c) for c in colsd], dtype=np.int64)                      # x2, multiple of 8
+    dims_plain = np.array([su.infer_embedding_dim(c, multiplier=3.0, ensure_multiple_of_8=False) for c in colsd], dtype=np.int64)
+    np.savez(OUT / "ref_torch_embedding_dims.npz", kind="embedding_dims", max_id=maxes, dims_default=dims_default,
+             dims_mult3_plain=dims_plain, n_criteo=np.int64(len(names)))
     print("wrote", sorted(p.name for p in OUT.glob("ref_torch_*.npz")))
 
 

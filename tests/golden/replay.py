@@ -91,6 +91,12 @@ def check(path: Path) -> None:
         for name in [str(n) for n in z["names"]]:
             layers = layers_from(z, prefix=f"{name}_", act=name)
             np.testing.assert_allclose(oracle.mlp(z["x"], layers), z[f"out_{name}"], rtol=1e-4, atol=1e-5, err_msg=name)
+    elif kind == "embedding_dims":
+        got = [oracle.infer_embedding_dim(int(m) + 1) for m in z["max_id"]]
+        assert got == z["dims_default"].tolist()
+        got3 = [oracle.infer_embedding_dim(int(m) + 1, multiplier=3.0, ensure_multiple_of_8=False) for m in z["max_id"]]
+        assert got3 == z["dims_mult3_plain"].tolist()
+        assert int(z["dims_default"][: int(z["n_criteo"])].sum()) == 1024  # d = 1024 + 13 for DCN
     elif kind == "catalog":
         # reference torch EmbeddingTablePrediction: logits = x @ E^T + bias; nn.CrossEntropyLoss on them; top-k
         logits = oracle.catalog_logits(z["x"], z["table"], z["bias"])

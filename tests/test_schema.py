@@ -93,3 +93,24 @@ def test_schema_json_writer_round_trips(tmp_path):
     mm.save_merlin_metadata(tmp_path, datasets.criteo_schema(), None)
     inp, out = mm.load_merlin_metadata(tmp_path)
     assert inp.column_names == datasets.criteo_schema().column_names and out is None
+
+
+def test_inferred_embedding_dims_match_the_reference_utility():
+    """mm.infer_embedding_dim (host logic of Embeddings / InputBlockV2 / DCNModel defaults) against the outputs of the
+    reference's own merlin/models/utils/schema_utils.py:169-207 executed in the build container
+    (tests/golden/ref_torch_embedding_dims.npz)."""
+    from pathlib import Path
+
+    import numpy as np
+
+    import models_b200 as mm
+
+    z = np.load(Path(__file__).parent / "golden" / "ref_torch_embedding_dims.npz")
+    cols = [ColumnSchema(f"f{i}", tags=(Tags.CATEGORICAL,), dtype="int64", properties={"domain": {"min": 0, "max": int(m), "name": f"f{i}"}})
+            for i, m in enumerate(z["max_id"])]
+    assert [mm.infer_embedding_dim(c) for c in cols] == z["dims_default"].tolist()
+    assert [mm.infer_embedding_dim(c, multiplier=3.0, ensure_multiple_of_8=False) for c in cols] == z["dims_mult3_plain"].tolist()
+    # the bundled Criteo schema: default DCN input width = 1024 + 13
+    schema = datasets.criteo_schema()
+    cat = schema.select_by_tag(Tags.CATEGORICAL)
+    assert sum(mm.infer_embedding_dim(c) for c in cat) == 1024
