@@ -230,7 +230,11 @@ def main():
     scores2 = (q @ neg2.T).astype(np.float32)
     resc, valid = con.rescore_false_negatives(torch.from_numpy(ids), torch.from_numpy(neg2_ids), torch.from_numpy(scores2),
                                               MINF)
+    bias_mod = importlib.import_module("merlin.models.torch.transforms.bias")
+    TEMP = 0.37
+    out_scaled = bias_mod.LogitsTemperatureScaler(TEMP)(out_ds)   # applied after the rescoring: MIN_FLOAT / T on hits
     np.savez(OUT / "ref_torch_contrastive.npz", kind="contrastive", query=q, positive=pos, ids=ids,
+             temperature=np.float32(TEMP), out_scaled=out_scaled.numpy(),
              negative=neg_t.numpy(), negative_ids=neg_id_t.numpy(), out_downscored=out_ds.numpy(), out_plain=out_plain.numpy(),
              target=target, min_float=np.float32(MINF), min_float_as_imported=np.float32(con.MIN_FLOAT), neg2=neg2, neg2_ids=neg2_ids, scores2=scores2,
              rescored2=resc.numpy(), valid2=valid.numpy())

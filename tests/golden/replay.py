@@ -60,6 +60,10 @@ def check(path: Path) -> None:
         np.testing.assert_allclose(out, z["out_downscored"], rtol=RTOL, atol=ATOL)
         assert np.array_equal(out == np.float32(z["min_float"]), z["out_downscored"] == np.float32(z["min_float"]))
         assert np.array_equal(tgt, z["target"])
+        if "out_scaled" in z:  # LogitsTemperatureScaler after the rescoring (transforms/bias.py): logits / T
+            scaled, _ = oracle.contrastive_logits(z["query"], z["positive"], z["negative"], z["ids"], z["negative_ids"], True,
+                                                  float(z["min_float"]), temperature=float(z["temperature"]))
+            np.testing.assert_allclose(scaled, z["out_scaled"], rtol=RTOL, atol=ATOL)
         plain, _ = oracle.contrastive_logits(z["query"], z["positive"], z["negative"], None, None, False, float(z["min_float"]))
         np.testing.assert_allclose(plain, z["out_plain"], rtol=RTOL, atol=ATOL)
         resc, valid = oracle.rescore_false_negatives(z["ids"], z["neg2_ids"], z["scores2"], float(z["min_float"]))

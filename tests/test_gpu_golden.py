@@ -151,6 +151,12 @@ def test_reference_torch_contrastive_logits(device):
     assert np.array_equal(got == np.float32(fns), hit)            # the mask is exact (integer compare)
     np.testing.assert_allclose(got[~hit], z["out_downscored"][~hit], rtol=RTOL, atol=2e-4)
     assert np.array_equal(out.targets.cpu().numpy(), z["target"])
+    # LogitsTemperatureScaler applied after the rescoring: every logit (accidental hits included) divided by T
+    T = float(z["temperature"])
+    scaled = mm.ContrastiveOutput(negative_samplers="in-batch", false_negative_score=fns, logits_temperature=T)(
+        {"query": q, "candidate": pos}, candidate_ids=ids, training=True).outputs.cpu().numpy()
+    np.testing.assert_allclose(scaled[hit], z["out_scaled"][hit], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(scaled[~hit], z["out_scaled"][~hit], rtol=RTOL, atol=2e-4 / T)
     # exact-fp32 engine and a separate negative set (N != B)
     B, N = z["scores2"].shape
     buf = torch.empty((B, 1 + N), dtype=torch.float32, device=device)
