@@ -112,3 +112,14 @@ def test_model_plans_follow_the_reference_ordering_rules():
     # inferred dims (utils/schema_utils.py:169-207)
     assert mm.infer_embedding_dim(schema["C1"]) == 120 and mm.infer_embedding_dim(schema["C6"]) == 8
     assert model.input_columns()[0] == "C21" and len(model.input_columns()) == 39
+
+
+def test_integration_doc_lists_every_exported_symbol():
+    """INTEGRATION.md is the maintainer-facing table of the C ABI: it must mention every symbol of include/mm_b200.h."""
+    from pathlib import Path
+
+    from models_b200 import _cabi
+
+    doc = (Path(__file__).resolve().parent.parent / "INTEGRATION.md").read_text()
+    missing = [s for s in sorted(_cabi.declared_symbols()) if s not in doc]
+    assert not missing, f"INTEGRATION.md does not mention: {missing}"
