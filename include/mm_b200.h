@@ -160,6 +160,36 @@ int mm_dlrm_gather_interact(const mm_gather_table* tables_host, int n_tables, in
                             int bottom_slot, float* out, int64_t out_stride, void* out_split,
                             int out_Kp, int32_t* oob_count, void* stream);
 
+/* Second-generation fused lookup + interaction (same result as mm_dlrm_gather_interact), with a richer
+ * table descriptor:
+ *   - per-table id width: idx_bytes = 1, 2, 3 (unsigned little-endian — what a loader ships when the
+ *     table has <= 2^8 / 2^16 / 2^24 rows), 4 (int32) or 8 (int64).  Narrow arrays need no alignment;
+ *     the kernel reads the aligned 32-bit words that contain an id, so the array must be readable up
+ *     to the next 4-byte boundary after its last id.  (loader hand-off: merlin/models/tf/loader.py:135-420)
+ *   - placement: peer_weights_host == NULL: `weights` is the whole (rows, D) table (replicated);
+ *     otherwise the table is ROW-SHARDED over `world` GPUs of one NVLink domain — global row r lives on
+ *     rank r % world at local row r / world — `weights` is this rank's shard and peer_weights_host[k]
+ *     the shard of rank k as mapped into this process (peer access / symmetric memory;
+ *     peer_weights_host[rank] == weights).  A row owned by another rank is read over NVLink straight
+ *     into the consuming SM's shared memory: the distributed lookup (SOK `lookup_sparse` on a distributed
+ *     variable, merlin/models/tf/distributed/embedding.py:75-84,144-148: all-to-all of keys, local
+ *     lookup, all-to-all of vectors) is part of the same kernel as the interaction.  No collective,
+ *     no barrier: tables are read-only in the forward pass.
+ * `rows` is always the GLOBAL row count; ids outside [0, rows) give a zero row and bump *oob_count.
+ * F = n_tables + (bottom ? 1 : 0) <= 32, D in {16, 32, 64, 128}, world <= 8. */
+typedef struct {
+  const float* weights;
+  const void* indices; /* (B,) ids of this feature, idx_bytes each */
+  int64_t rows;
+  int32_t slot;      /* position of this feature in the sorted (B,F,D) stack */
+  int32_t idx_bytes; /* 1, 2, 3, 4, 8 */
+  const float* const* peer_weights_host; /* NULL, or `world` shard pointers (host array) */
+} mm_lookup_table;
+
+int mm_dlrm_lookup_interact(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, int rank, int world,
+                            const float* bottom, int64_t bottom_stride, int bottom_slot, float* out,
+                            int64_t out_stride, void* out_split, int out_Kp, int32_t* oob_count, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K4  Dense layer, exact fp32 on CUDA cores:  out = act(x @ W + bias).
  * Replaces tf.keras.layers.Dense (blocks/mlp.py:275-280); W is the Keras kernel (K, N).

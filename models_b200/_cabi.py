@@ -34,6 +34,19 @@ class GatherTable(C.Structure):
     ]
 
 
+class LookupTable(C.Structure):
+    """mm_lookup_table (include/mm_b200.h)."""
+
+    _fields_ = [
+        ("weights", C.c_void_p),
+        ("indices", C.c_void_p),
+        ("rows", C.c_int64),
+        ("slot", C.c_int32),
+        ("idx_bytes", C.c_int32),
+        ("peer_weights_host", C.POINTER(C.c_void_p)),
+    ]
+
+
 class ConcatPiece(C.Structure):
     """mm_concat_piece (include/mm_b200.h)."""
 
@@ -64,6 +77,7 @@ SIGNATURES = {
     "mm_l2_normalize": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp]),
     "mm_dot_interaction": (_i, [_vp, _i64, _i, _i, _i64, _vp, _i, _i64, _i, _vp, _i64, _vp, _i, _vp]),
     "mm_dlrm_gather_interact": (_i, [_tables, _i, _i, _i64, _i, _vp, _i64, _i, _vp, _i64, _vp, _i, _vp, _vp]),
+    "mm_dlrm_lookup_interact": (_i, [C.POINTER(LookupTable), _i, _i64, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i, _vp, _vp]),
     "mm_dense_fp32": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64, _vp]),
     "mm_tc_padded_k": (_i, [_i]),
     "mm_tc_padded_n": (_i, [_i]),

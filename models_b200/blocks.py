@@ -490,7 +490,7 @@ class DLRM(Block):
     def can_emit_split(self) -> bool:
         """True when the tensor-core interaction kernel applies (F <= 32, D % 16 == 0)."""
         F = len(self.embeddings.feature_names) + (1 if self.bottom_block is not None else 0)
-        return 2 <= F <= 32 and self.embedding_dim % 16 == 0 and self.embedding_dim <= 256
+        return 2 <= F <= 32 and self.embedding_dim in (16, 32, 64, 128)
 
     def bottom_forward(self, inputs: TabularData) -> Optional[torch.Tensor]:
         if self.bottom_block is None:
@@ -519,9 +519,15 @@ class DLRM(Block):
         from .inputs import _as_index, _raise_on_oob
 
         if self.sharded is not None:
-            # row-sharded tables: index all-gather + owner-computes NVLink push + barrier rebuild the
-            # (B,F,D) stack of the local samples; the interaction then reads it like the staged path
             oob = emb.counter(dev)
+            if with_prefix == (bottom is not None) and self.can_emit_split():
+                # row-sharded tables, product path: the lookup is part of the interaction kernel — rows owned
+                # by other ranks are read over NVLink straight into shared memory (no exchange, no barrier)
+                self.sharded.lookup_interact(inputs, slots, bottom, out, oob)
+                emb.finish_check(oob)
+                return out
+            # staged protocol (index all-gather + owner-computes NVLink push + barrier) rebuilds the (B,F,D)
+            # stack of the local samples; the interaction then reads it like the staged path
             stack = self.sharded.lookup_stack(inputs, slots, F, oob)
             emb.finish_check(oob)
             if bottom is not None:
@@ -530,11 +536,19 @@ class DLRM(Block):
         all_onehot = all(emb.feature_to_table[f].lookup_kind(get_feature(inputs, f)) == "onehot" for f in feats)
         if self.fused and all_onehot and with_prefix == (bottom is not None):
             oob = emb.counter(dev)
-            idx = [_as_index(get_feature(inputs, f)).reshape(-1) for f in feats]
-            if len({i.dtype for i in idx}) > 1:
-                idx = [i.to(torch.int64) for i in idx]
-            ops.dlrm_gather_interact([emb.feature_to_table[f].table for f in feats], idx, [slots[f] for f in feats], D,
-                                     bottom, slots.get("bottom_block", -1), out, oob)
+            raw = [get_feature(inputs, f) for f in feats]
+            if self.can_emit_split():
+                # ids travel at their own width (packed uint8 / uint16 / 24-bit host batches, int32, int64)
+                idx = [i if i.dtype in (torch.uint8, torch.uint16) else _as_index(i).reshape(-1) for i in raw]
+                tabs = [emb.feature_to_table[f].table for f in feats]
+                ops.dlrm_lookup_interact(tabs, idx, [slots[f] for f in feats], [t.shape[0] for t in tabs], D, bottom,
+                                         slots.get("bottom_block", -1), out, oob)
+            else:
+                idx = [_as_index(i).reshape(-1) for i in raw]
+                if len({i.dtype for i in idx}) > 1:
+                    idx = [i.to(torch.int64) for i in idx]
+                ops.dlrm_gather_interact([emb.feature_to_table[f].table for f in feats], idx, [slots[f] for f in feats], D,
+                                         bottom, slots.get("bottom_block", -1), out, oob)
             emb.finish_check(oob)
             return out
         # staged path: one fused gather into the (B,F,D) stack, then the interaction kernel

@@ -10,11 +10,19 @@
 
 namespace mm {
 
+bool use_imma_v1();
+
 namespace itc {  // interaction_tc.cu: tcgen05 path, four samples per 128x128 tile (F <= 32, D == 64)
 template <int MODE, typename IdxT>
 int launch(const float* x, int64_t x_stride, const GatherParams& gp, const float* prefix, int64_t prefix_stride,
            int P, int bottom_slot, int64_t B, int F, int D, float* out_f32, int64_t out_stride, void* out_split,
            int out_Kp, int32_t* oob, cudaStream_t st, const char* who);
+}
+namespace imma2 {  // interaction_v2.cu: second-generation warp-per-sample kernel (packed ids, sharded tables)
+template <int MODE>
+int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float* prefix, int64_t prefix_stride, int P,
+           int bottom_slot, int64_t B, int F, int D, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
+           int32_t* oob, cudaStream_t st, const char* who);
 }
 namespace imma {  // interaction_mma.cu: warp-level mma.sync path (F <= 32, D in {16,32,64,128})
 template <int MODE, typename IdxT>
@@ -220,9 +228,77 @@ static int launch_interact(const float* x, int64_t x_stride, const GatherParams&
   return check_launch(who);
 }
 
+bool use_imma_v1() {  // MM_IMMA_V1=1: first-generation kernel (interaction_mma.cu), kept for A/B measurements
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MM_IMMA_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 }  // namespace mm
 
 extern "C" {
+
+int mm_dlrm_lookup_interact(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, int rank, int world,
+                            const float* bottom, int64_t bottom_stride, int bottom_slot, float* out,
+                            int64_t out_stride, void* out_split, int out_Kp, int32_t* oob_count, void* stream) {
+  const char* who = "mm_dlrm_lookup_interact";
+  MM_REQUIRE(tables_host && n_tables > 0 && (out || out_split) && B >= 0, MM_ERR_ARG, "%s: bad table list / null out / B<0", who);
+  MM_REQUIRE(!(out && out_split), MM_ERR_ARG, "%s: give either out or out_split", who);
+  MM_REQUIRE(D == 16 || D == 32 || D == 64 || D == 128, MM_ERR_UNSUPPORTED, "%s: D must be 16, 32, 64 or 128", who);
+  MM_REQUIRE(world >= 1 && world <= mm::MM_LOOKUP_MAX_WORLD && rank >= 0 && rank < world, MM_ERR_ARG,
+             "%s: world must be 1..%d and 0 <= rank < world", who, mm::MM_LOOKUP_MAX_WORLD);
+  const int F = n_tables + (bottom ? 1 : 0);
+  MM_REQUIRE(F >= 2 && F <= mm::MM_LOOKUP_MAX_ROWS, MM_ERR_UNSUPPORTED, "%s: 2..%d feature slots", who, mm::MM_LOOKUP_MAX_ROWS);
+  MM_REQUIRE(!bottom || (bottom_slot >= 0 && bottom_slot < F && bottom_stride >= D && bottom_stride % 4 == 0 &&
+                         ((uintptr_t)bottom % 16) == 0),
+             MM_ERR_ARG, "%s: bad bottom slot / stride / alignment", who);
+  mm::LookupParams lk;
+  memset(&lk, 0, sizeof(lk));
+  lk.world = world;
+  lk.log2_world = -1;
+  for (int b = 0; b < 4; ++b)
+    if ((1 << b) == world) lk.log2_world = b;
+  unsigned seen = bottom ? (1u << bottom_slot) : 0u;
+  for (int t = 0; t < n_tables; ++t) {
+    const mm_lookup_table& tb = tables_host[t];
+    const int r = tb.slot;
+    MM_REQUIRE(tb.weights && tb.indices && tb.rows > 0 && r >= 0 && r < F && ((uintptr_t)tb.weights % 16) == 0, MM_ERR_ARG,
+               "%s: table %d: null pointer, rows <= 0, bad slot or misaligned weights", who, t);
+    MM_REQUIRE(!(seen & (1u << r)), MM_ERR_ARG, "%s: slot %d used twice", who, r);
+    seen |= 1u << r;
+    const int w = tb.idx_bytes;
+    MM_REQUIRE(w == 1 || w == 2 || w == 3 || w == 4 || w == 8, MM_ERR_ARG, "%s: table %d: idx_bytes must be 1, 2, 3, 4 or 8", who, t);
+    MM_REQUIRE(w >= 4 || tb.rows <= (1ll << (8 * w)), MM_ERR_ARG, "%s: table %d: %lld rows do not fit %d-byte ids", who, t,
+               (long long)tb.rows, w);
+    MM_REQUIRE((w != 4 && w != 8) || ((uintptr_t)tb.indices % w) == 0, MM_ERR_ALIGN, "%s: table %d: misaligned ids", who, t);
+    lk.weights[r] = tb.weights;
+    lk.indices[r] = tb.indices;
+    lk.rows[r] = tb.rows;
+    lk.idx_bytes[r] = (unsigned char)w;
+    if (tb.peer_weights_host) {
+      MM_REQUIRE(world > 1, MM_ERR_ARG, "%s: table %d is sharded but world == 1", who, t);
+      lk.sharded[r] = 1;
+      for (int k = 0; k < world; ++k) {
+        MM_REQUIRE(tb.peer_weights_host[k] && ((uintptr_t)tb.peer_weights_host[k] % 16) == 0, MM_ERR_ARG,
+                   "%s: table %d: null / misaligned shard pointer of rank %d", who, t, k);
+        lk.peers[r * world + k] = tb.peer_weights_host[k];
+      }
+      MM_REQUIRE(tb.peer_weights_host[rank] == tb.weights, MM_ERR_ARG, "%s: table %d: peer_weights_host[rank] != weights", who, t);
+    }
+  }
+  const int P = bottom ? D : 0;
+  MM_REQUIRE(!out || out_stride >= P + F * (F - 1) / 2, MM_ERR_ARG, "%s: out_stride too small", who);
+  MM_REQUIRE(!out_split || (out_Kp % 64 == 0 && out_Kp >= P + F * (F - 1) / 2 && ((uintptr_t)out_split % 16) == 0), MM_ERR_ARG,
+             "%s: out_Kp must be a multiple of 64 >= the row width, out_split 16-B aligned", who);
+  if (B == 0) return MM_OK;
+  const int rc = mm::imma2::launch<1>(nullptr, 0, lk, bottom, bottom_stride, P, bottom ? bottom_slot : -1, B, F, D, out,
+                                      out_stride, out_split, out_Kp, oob_count, (cudaStream_t)stream, who);
+  MM_REQUIRE(rc != MM_ERR_UNSUPPORTED, MM_ERR_UNSUPPORTED, "%s: shape outside the fused kernel (F=%d, D=%d)", who, F, D);
+  return rc;
+}
 
 int mm_dot_interaction(const float* x, int64_t B, int F, int D, int64_t x_stride,
                        const float* prefix, int P, int64_t prefix_stride, int self_interaction,
@@ -243,6 +319,14 @@ int mm_dot_interaction(const float* x, int64_t B, int F, int D, int64_t x_stride
   if (B == 0) return MM_OK;
   mm::GatherParams p;
   memset(&p, 0, sizeof(p));
+  if (!self_interaction && !mm::use_imma_v1()) {
+    mm::LookupParams lk;
+    memset(&lk, 0, sizeof(lk));
+    lk.world = 1;
+    const int rc2 = mm::imma2::launch<0>(x, x_stride, lk, prefix, prefix_stride, P, -1, B, F, D, out, out_stride, out_split,
+                                         out_Kp, nullptr, (cudaStream_t)stream, "mm_dot_interaction");
+    if (rc2 != MM_ERR_UNSUPPORTED) return rc2;
+  }
   if (!self_interaction) {
     const int rc0 = mm::itc::launch<0, int32_t>(x, x_stride, p, prefix, prefix_stride, P, -1, B, F, D, out, out_stride,
                                                 out_split, out_Kp, nullptr, (cudaStream_t)stream, "mm_dot_interaction");
@@ -295,6 +379,21 @@ int mm_dlrm_gather_interact(const mm_gather_table* tables_host, int n_tables, in
   p.n_tables = n_tables;
   for (int t = 0; t < n_tables; ++t) p.t[t] = tables_host[t];
   cudaStream_t st = (cudaStream_t)stream;
+  if (!mm::use_imma_v1() && F <= mm::MM_LOOKUP_MAX_ROWS) {
+    mm::LookupParams lk;
+    memset(&lk, 0, sizeof(lk));
+    lk.world = 1;
+    for (int t = 0; t < n_tables; ++t) {
+      const int r = tables_host[t].out_col / D;
+      lk.weights[r] = tables_host[t].weights;
+      lk.indices[r] = tables_host[t].indices;
+      lk.rows[r] = tables_host[t].rows;
+      lk.idx_bytes[r] = idx_dtype == MM_I32 ? 4 : 8;
+    }
+    const int rc2 = mm::imma2::launch<1>(nullptr, 0, lk, bottom, bottom_stride, P, bottom ? bottom_slot : -1, B, F, D, out,
+                                         out_stride, out_split, out_Kp, oob_count, st, "mm_dlrm_gather_interact");
+    if (rc2 != MM_ERR_UNSUPPORTED) return rc2;
+  }
   {
     const int bs = bottom ? bottom_slot : -1;
     const int rc0 = idx_dtype == MM_I32

@@ -1,0 +1,462 @@
+// DLRM lookup + pairwise interaction, one warp per sample (second generation of interaction_mma.cu).
+//
+// What changed against the first kernel (profiles/r01_notes.md §h: 1 155 warp instructions per sample,
+// 436 of them in the row-copy loop, issue-bound at 12 warps per SM):
+//   * copy loop: 8 lanes move one 128-byte half row per LDGSTS, 4 rows per instruction.  Staged row r is
+//     owned by lane r (tables arrive sorted by slot, so row == slot), a row's source pointer travels
+//     with two shuffles, and because row = 4*i + lane/8 the XOR swizzle of a lane's destination does
+//     not depend on i: every destination is `lane constant + immediate`.  7 iterations x (2 SHFL +
+//     2 IADD + 2 LDGSTS) per sample instead of 14 x 23 instructions.  Bad ids read a zero row in global
+//     memory (no zero-fill operand, no predicates).
+//   * fragment loads: the k index of a 16-wide k-step is permuted (lane t takes floats 4t..4t+3 and
+//     calls them k = 2t, 2t+1, 2t+8, 2t+9).  A and B fragments are the same registers (B = X^T), so the
+//     permutation cancels in the dot products and one LDS.128 replaces two LDS.64.
+//   * the fp32 output row is staged INSIDE the sample buffer that was just consumed (the prefix row is
+//     lifted into registers first), so a warp needs 2 x rows x D x 4 bytes and 16 warps fit in 227 KB.
+//   * index arrays may be 1, 2, 3 (unsigned), 4 or 8 (signed) bytes wide PER TABLE — a host batch ships
+//     52-60 B of ids per Criteo sample instead of 104 (PCIe is the end-to-end bound).
+//   * a table may be ROW-SHARDED over the GPUs of an NVLink domain: row r lives on rank r % world at
+//     local row r / world, and the owner lane takes the row's address from that rank's peer-mapped
+//     shard — the cp.async reads the row over NVLink straight into this SM's shared memory.  Lookup,
+//     all-to-all and interaction are ONE kernel: no index exchange, no send/receive buffers, no barrier
+//     (tables are read-only in the forward pass).
+//
+// Replaces: T x Embedding lookups (inputs/embedding.py:401-471) or SOK's distributed lookup
+// (distributed/embedding.py:75-84,144-148) + StackFeatures (core/aggregation.py:101-108) +
+// DotProductInteraction (blocks/interaction.py:86-116) + shortcut concat (blocks/dlrm.py:126-130).
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "mm_common.cuh"
+
+namespace mm {
+namespace imma2 {
+
+__device__ __align__(16) float g_zero_row[128];  // zero-initialised: source of rows for out-of-range ids
+
+struct Params {
+  const float* x;  // MODE 0: stacked input
+  long long x_stride;
+  const float* prefix;  // bottom vector (P == 0 or P == D)
+  long long prefix_stride;
+  int P;
+  int bottom_slot;  // MODE 1: staged row of the bottom vector (-1: none)
+  long long B;
+  int F, D;
+  int rows;  // rows staged per sample (F, or F+1 when MODE 0 carries a separate prefix row)
+  float* out_f32;
+  long long out_stride;
+  __nv_bfloat16* out_split;
+  int out_Kp;
+  int* oob_count;
+  int n_warps;
+  unsigned buf_bytes;   // one sample buffer (>= rows*D*4 and >= the staged output row)
+  unsigned stage_cols;  // floats of the staged output row (out_Kp, or OW rounded up to 4)
+  unsigned peer_off;    // byte offset of the peer pointer table in shared memory
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// predicated form: no branch / reconvergence bookkeeping around the copy
+__device__ __forceinline__ void cp_async16_if(bool pred, uint32_t dst, const void* src) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst),
+      "l"(src), "r"((uint32_t)pred)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// (x, y) -> packed bf16x2 hi (x in the low half) and the bf16x2 of the residuals
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x - xh, y - yh);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+struct RawIdx {
+  uint32_t a, b;
+};
+
+template <int MODE, int KD /* embedding dim: 16, 32, 64, 128 */, int NWARPS /* launch bound */>
+__global__ void __launch_bounds__(32 * NWARPS, 1)
+interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int NBUF = 2;
+  constexpr int D = KD, KS = KD / 16;
+  constexpr int C = KD / 4;           // 16-byte chunks per row
+  constexpr int L = C < 8 ? C : 8;    // lanes per row in the copy loop
+  constexpr int J = C / L;            // copies per lane and row
+  constexpr int R = 32 / L;           // rows per copy instruction
+  constexpr int IMAX = 32 / R;        // copy iterations for 32 rows
+  constexpr bool SWZ = KD >= 32;      // chunk index XOR 4 on odd rows (bank-conflict-free LDS.128 of two rows)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int F = p.F;
+  const int nw = p.n_warps;
+  const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)warp * (NBUF * p.buf_bytes);
+
+  // ---- samples of this CTA: a contiguous range, interleaved over its warps (neighbouring warps read
+  // neighbouring ids: the 32-byte index sectors are shared through L1 instead of being fetched 8 times)
+  const long long begin = (long long)blockIdx.x * p.B / gridDim.x;
+  const long long end = (long long)(blockIdx.x + 1) * p.B / gridDim.x;
+  const long long first = begin + warp;
+  const long long n_mine = first < end ? (end - first + nw - 1) / nw : 0;
+
+  // ---- owner role: lane r owns staged row r (MODE 1: a table, or the bottom vector)
+  const bool is_table = MODE == 1 && lane < p.rows && lane != p.bottom_slot;
+  const uint8_t* my_idx = is_table ? reinterpret_cast<const uint8_t*>(lk.indices[lane]) : nullptr;
+  const float* my_base = is_table ? lk.weights[lane] : nullptr;
+  const long long my_rows = is_table ? lk.rows[lane] : 0;
+  const int my_w = is_table ? lk.idx_bytes[lane] : 4;
+  const bool my_sharded = is_table && lk.sharded[lane];
+  const float* const* peers = reinterpret_cast<const float* const*>(smem_raw + p.peer_off);
+  if (MODE == 1 && lk.world > 1) {  // peer shard pointers: kernel parameters -> shared memory (indexed by lane AND owner)
+    float const** dst = reinterpret_cast<float const**>(smem_raw + p.peer_off);
+    for (int i = threadIdx.x; i < p.rows * lk.world; i += blockDim.x) dst[i] = lk.peers[i];
+    __syncthreads();
+  }
+
+  auto load_raw = [&](long long it) -> RawIdx {
+    RawIdx r{0u, 0u};
+    if (MODE == 1 && is_table && it < n_mine) {
+      const long long s = first + it * nw;
+      if (my_w == 4) {
+        r.a = __ldg(reinterpret_cast<const uint32_t*>(my_idx) + s);
+      } else if (my_w == 8) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(my_idx) + s);
+        r.a = v.x;
+        r.b = v.y;
+      } else {  // 1..3 bytes: the aligned word(s) holding the value
+        const uintptr_t a = reinterpret_cast<uintptr_t>(my_idx) + (uintptr_t)s * my_w;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        r.a = __ldg(wp);
+        if ((int)(a & 3) + my_w > 4) r.b = __ldg(wp + 1);
+      }
+    }
+    return r;
+  };
+  auto decode = [&](RawIdx r, long long s) -> long long {
+    if (my_w == 4) return (long long)(int)r.a;
+    if (my_w == 8) return (long long)(((unsigned long long)r.b << 32) | r.a);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(my_idx) + (uintptr_t)s * my_w;
+    const uint32_t v = __funnelshift_r(r.a, r.b, 8u * (uint32_t)(a & 3));
+    return (long long)(v & (0xffffffffu >> (32 - 8 * my_w)));
+  };
+
+  // ---- copy-loop constants of this lane
+  const int cl = lane & (L - 1), rl = lane / L;
+  const uint32_t src_lane_off = (uint32_t)cl * 16u;
+  const uint32_t dst_lane_off =
+      (uint32_t)rl * (D * 4) + (uint32_t)((SWZ ? (cl ^ ((rl & 1) << 2)) : cl) * 16);
+
+  auto issue = [&](long long it, RawIdx raw) {
+    // The shuffles run unconditionally (no divergent-branch handling around them); past the end of this
+    // warp's samples the row count is 0 and nothing is copied.
+    const int live_rows = it < n_mine ? p.rows : 0;
+    const long long s = first + it * nw;
+    const uint32_t xs = wbase + (uint32_t)(it & (NBUF - 1)) * p.buf_bytes + dst_lane_off;
+    if (MODE == 1) {
+      const float* my_src = g_zero_row;
+      if (is_table && live_rows) {
+        const long long idx = decode(raw, s);
+        if (idx >= 0 && idx < my_rows) {
+          if (my_sharded) {
+            long long lrow;
+            int owner;
+            if (lk.log2_world >= 0) {
+              owner = (int)(idx & (lk.world - 1));
+              lrow = idx >> lk.log2_world;
+            } else {
+              lrow = idx / lk.world;
+              owner = (int)(idx - lrow * lk.world);
+            }
+            my_src = peers[lane * lk.world + owner] + lrow * D;
+          } else {
+            my_src = my_base + idx * D;
+          }
+        } else if (p.oob_count) {
+          atomicAdd(p.oob_count, 1);
+        }
+      } else if (lane == p.bottom_slot && live_rows) {
+        my_src = p.prefix + s * p.prefix_stride;
+      }
+      const uint32_t src_lo = (uint32_t)(uintptr_t)my_src, src_hi = (uint32_t)((uintptr_t)my_src >> 32);
+#pragma unroll
+      for (int i = 0; i < IMAX; ++i) {
+        if (i * R < p.rows) {  // kernel parameter: uniform branch
+          const int row = i * R + rl;
+          const uint32_t lo = __shfl_sync(0xffffffffu, src_lo, row);
+          const uint32_t hi = __shfl_sync(0xffffffffu, src_hi, row);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(((uintptr_t)hi << 32) | lo) + src_lane_off;
+          const bool on = row < live_rows;
+#pragma unroll
+          for (int j = 0; j < J; ++j) cp_async16_if(on, xs + (uint32_t)(i * R * D * 4 + j * L * 16), src + j * L * 16);
+        }
+      }
+    } else {
+      const uint8_t* xrow = reinterpret_cast<const uint8_t*>(p.x + s * p.x_stride) + (size_t)rl * (D * 4) + src_lane_off;
+      const uint8_t* prow = reinterpret_cast<const uint8_t*>(p.prefix + s * p.prefix_stride) + src_lane_off;
+#pragma unroll
+      for (int i = 0; i < IMAX; ++i) {
+        if (i * R < p.rows) {
+          const int row = i * R + rl;
+          const uint8_t* src = row < F ? xrow + (size_t)i * (R * D * 4) : prow;
+          const bool on = row < live_rows;
+#pragma unroll
+          for (int j = 0; j < J; ++j) cp_async16_if(on, xs + (uint32_t)(i * R * D * 4 + j * L * 16), src + j * L * 16);
+        }
+      }
+    }
+    cp_async_commit();  // one group per sample (empty past the end keeps the group count in step)
+  };
+
+  // ---- fragment-load constants: rows q*8 + g (q = 0..3), clamped to staged rows; this lane reads floats
+  // 4t..4t+3 of every 16-wide k-step.  Even k-steps sit at pe + 64*ks, odd ones at po + 64*ks (the XOR
+  // swizzle of odd rows swaps neighbouring k-steps).
+  uint32_t pe[4], po[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = min(8 * q + g, F - 1);
+    const uint32_t base = (uint32_t)r * (D * 4) + (uint32_t)t * 16u;
+    const uint32_t sb = (SWZ && (r & 1)) ? 64u : 0u;
+    pe[q] = base + sb;
+    po[q] = base - sb;
+  }
+  // ---- output constants: accumulator (i, j) with i = 8*qi + g, j = 8*nt + 2t + e lands at
+  // P + i(2F-i-1)/2 + (j-i-1) = rb[qi] + 8*nt + e   (floats); valid iff i < j < F
+  int rb[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = 8 * q + g;
+    rb[q] = (p.P + i * (2 * F - i - 1) / 2 - i - 1 + 2 * t) * 4;  // bytes
+  }
+  const int jlim = F - 2 * t;        // j < F  <=>  8*nt + e < jlim
+  const bool dg0 = g < 2 * t, dg1 = g < 2 * t + 1;  // diagonal tiles: i < j  <=>  g < 2t + e
+  const int npairs = F * (F - 1) / 2;
+  const int OW = p.P + npairs;
+  const int prow = MODE == 1 ? p.bottom_slot : F;  // staged row holding the prefix
+  const uint32_t pfx_off = (uint32_t)prow * (D * 4) + (uint32_t)((SWZ ? (lane ^ ((prow & 1) << 2)) : lane) * 16);
+
+  // ---- software pipeline: one sample in flight behind the one being computed; ids one iteration ahead
+  RawIdx raw_pref = load_raw(0);
+  {
+    const RawIdx cur = raw_pref;
+    raw_pref = load_raw(1);
+    issue(0, cur);
+  }
+  for (long long it = 0; it < n_mine; ++it) {
+    {
+      const RawIdx cur = raw_pref;
+      raw_pref = load_raw(it + 2);
+      issue(it + 1, cur);  // refills the buffer consumed (and used as output stage) in the previous iteration
+    }
+    const long long s = first + it * nw;
+    const uint32_t xs = wbase + (uint32_t)(it & (NBUF - 1)) * p.buf_bytes;
+    cp_async_wait<NBUF - 1>();
+    __syncwarp();
+
+    float acc[6][4];
+#pragma unroll
+    for (int ti = 0; ti < 6; ++ti)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[ti][c] = 0.0f;
+
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t h[4][2], l[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = lds128(xs + ((ks & 1) ? po[q] : pe[q]) + 64u * ks);
+        split_pair(v.x, v.y, h[q][0], l[q][0]);
+        split_pair(v.z, v.w, h[q][1], l[q][1]);
+      }
+      // tile (mt, nt): A = rows q = 2mt, 2mt+1; B (n-tile nt = rows 8nt + g) = the registers of q = nt.
+      // Pass-major order: six independent accumulators between dependent MMAs.
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti) {
+        const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+        mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], l[nt][0], l[nt][1]);
+      }
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti) {
+        const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+        mma_bf16_16816(acc[ti], l[2 * mt][0], l[2 * mt + 1][0], l[2 * mt][1], l[2 * mt + 1][1], h[nt][0], h[nt][1]);
+      }
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti) {
+        const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+        mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], h[nt][0], h[nt][1]);
+      }
+    }
+
+    // ---- the prefix row leaves the buffer before the buffer becomes the output stage
+    float4 pfx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.P > 0 && lane < C) pfx = lds128(xs + pfx_off);
+    __syncwarp();  // every lane is done reading the sample
+    if (p.P > 0 && lane < C)
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(xs + lane * 16u), "f"(pfx.x), "f"(pfx.y), "f"(pfx.z),
+                   "f"(pfx.w)
+                   : "memory");
+#pragma unroll
+    for (int ti = 0; ti < 6; ++ti) {
+      const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int qi = 2 * mt + (c >> 1), e = c & 1;
+        if (qi > nt) continue;  // below the diagonal: never stored
+        bool ok = (8 * nt + e) < jlim;
+        if (qi == nt) ok = ok && (e ? dg1 : dg0);
+        if (ok) sts32(xs + (uint32_t)(rb[qi] + (8 * nt + e) * 4), acc[ti][c]);
+      }
+    }
+    for (int e = OW + lane; e < (int)p.stage_cols; e += 32) sts32(xs + (uint32_t)e * 4u, 0.0f);  // zero padding
+    __syncwarp();
+
+    // ---- coalesced row store
+    if (p.out_split) {
+      __nv_bfloat16* drow = p.out_split + s * (2ll * p.out_Kp);
+      const int groups = p.out_Kp >> 3;  // 8 columns = one 16-byte bf16 store for hi and one for lo
+      for (int gi = lane; gi < groups; gi += 32) {
+        const float4 a = lds128(xs + (uint32_t)gi * 32u), b = lds128(xs + (uint32_t)gi * 32u + 16u);
+        uint32_t hh[4], ll[4];
+        split_pair(a.x, a.y, hh[0], ll[0]);
+        split_pair(a.z, a.w, hh[1], ll[1]);
+        split_pair(b.x, b.y, hh[2], ll[2]);
+        split_pair(b.z, b.w, hh[3], ll[3]);
+        *reinterpret_cast<uint4*>(drow + 8 * gi) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        *reinterpret_cast<uint4*>(drow + p.out_Kp + 8 * gi) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+      }
+    } else {
+      float* dst = p.out_f32 + s * p.out_stride;
+      if (((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0)) {
+        const int n4 = OW >> 2;
+        for (int e = lane; e < n4; e += 32) reinterpret_cast<float4*>(dst)[e] = lds128(xs + (uint32_t)e * 16u);
+        for (int e = (n4 << 2) + lane; e < OW; e += 32) {
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (uint32_t)e * 4u));
+          dst[e] = v;
+        }
+      } else {
+        for (int e = lane; e < OW; e += 32) {
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (uint32_t)e * 4u));
+          dst[e] = v;
+        }
+      }
+    }
+    __syncwarp();  // the buffer may be refilled by the next iteration's copies
+  }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+template <int MODE, int KD, int NWARPS>
+static int launch_kd(const LookupParams& lk, const Params& p, size_t smem, unsigned grid, cudaStream_t st, const char* who) {
+  auto kern = interact_v2_kernel<MODE, KD, NWARPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, 32 * p.n_warps, smem, st>>>(lk, p);
+  return check_launch(who);
+}
+
+// Returns MM_ERR_UNSUPPORTED (without touching the error text) when the fast path does not apply.
+// MODE 1: `lk` lists the tables BY STAGED ROW (= slot); the bottom row's entries are null.
+template <int MODE>
+int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float* prefix, int64_t prefix_stride, int P,
+           int bottom_slot, int64_t B, int F, int D, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
+           int32_t* oob, cudaStream_t st, const char* who) {
+  if (F < 2 || F > 32 || (D != 16 && D != 32 && D != 64 && D != 128)) return MM_ERR_UNSUPPORTED;
+  if (P != 0 && P != D) return MM_ERR_UNSUPPORTED;
+  if (out_f32 && out_split) return MM_ERR_UNSUPPORTED;
+  const int rows = (MODE == 0 && P > 0) ? F + 1 : F;
+  if (rows > 32) return MM_ERR_UNSUPPORTED;
+  if (MODE == 0 && (((uintptr_t)x & 15) || (x_stride & 3))) return MM_ERR_UNSUPPORTED;
+  if (P > 0 && (((uintptr_t)prefix & 15) || (prefix_stride & 3))) return MM_ERR_UNSUPPORTED;
+  const int OW = P + F * (F - 1) / 2;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x;
+  p.x_stride = x_stride;
+  p.prefix = prefix;
+  p.prefix_stride = prefix_stride;
+  p.P = P;
+  p.bottom_slot = bottom_slot;
+  p.B = B;
+  p.F = F;
+  p.D = D;
+  p.rows = rows;
+  p.out_f32 = out_f32;
+  p.out_stride = out_stride;
+  p.out_split = (__nv_bfloat16*)out_split;
+  p.out_Kp = out_Kp;
+  p.oob_count = oob;
+  p.stage_cols = out_split ? (unsigned)out_Kp : (unsigned)((OW + 3) & ~3);
+  const unsigned in_bytes = (unsigned)(rows * D * 4), stage_bytes = p.stage_cols * 4u;
+  p.buf_bytes = ((in_bytes > stage_bytes ? in_bytes : stage_bytes) + 127u) & ~127u;
+  const unsigned per_warp = 2u * p.buf_bytes;
+  const unsigned peer_bytes = (MODE == 1 && lk.world > 1) ? (unsigned)(rows * lk.world * 8) : 0u;
+  const unsigned budget = 227u * 1024u - peer_bytes;
+  static int warps_env = -2;
+  if (warps_env == -2) warps_env = env_int("MM_IMMA_WARPS", 0);
+  const int want_warps = warps_env > 0 ? warps_env : 16;
+  int warps = (int)(budget / per_warp);
+  if (warps > want_warps) warps = want_warps;
+  if (warps > 16) warps = 16;
+  if (warps < 2) return MM_ERR_UNSUPPORTED;
+  p.n_warps = warps;
+  p.peer_off = (unsigned)warps * per_warp;
+  const size_t smem = (size_t)p.peer_off + peer_bytes;
+  const long long sms = sm_count();
+  long long want = (B + warps - 1) / warps;
+  const unsigned grid = (unsigned)(want < sms ? want : sms);
+#define MM_V2_LAUNCH(KD)                                                                 \
+  (warps > 12 ? launch_kd<MODE, KD, 16>(lk, p, smem, grid, st, who) : launch_kd<MODE, KD, 12>(lk, p, smem, grid, st, who))
+  switch (D) {
+    case 16: return MM_V2_LAUNCH(16);
+    case 32: return MM_V2_LAUNCH(32);
+    case 64: return MM_V2_LAUNCH(64);
+    default: return MM_V2_LAUNCH(128);
+  }
+#undef MM_V2_LAUNCH
+}
+
+template int launch<0>(const float*, int64_t, const LookupParams&, const float*, int64_t, int, int, int64_t, int, int,
+                       float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*);
+template int launch<1>(const float*, int64_t, const LookupParams&, const float*, int64_t, int, int, int64_t, int, int,
+                       float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*);
+
+}  // namespace imma2
+}  // namespace mm

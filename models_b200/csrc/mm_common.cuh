@@ -76,6 +76,20 @@ struct GatherParams {
   int n_tables;
 };
 
+// Lookup descriptor of the fused lookup + interaction kernel (interaction_v2.cu), indexed by STAGED ROW
+// (= feature slot); passed by value in kernel parameter space (2.9 KB)
+constexpr int MM_LOOKUP_MAX_ROWS = 32;
+constexpr int MM_LOOKUP_MAX_WORLD = 8;
+struct LookupParams {
+  const float* weights[MM_LOOKUP_MAX_ROWS];  // full table (replicated) or this rank's shard; null: not a table row
+  const void* indices[MM_LOOKUP_MAX_ROWS];
+  long long rows[MM_LOOKUP_MAX_ROWS];  // GLOBAL row count
+  const float* peers[MM_LOOKUP_MAX_ROWS * MM_LOOKUP_MAX_WORLD];  // [row * world + rank] shard pointers (sharded rows)
+  unsigned char idx_bytes[MM_LOOKUP_MAX_ROWS];  // 1, 2, 3 (unsigned), 4, 8 (signed)
+  unsigned char sharded[MM_LOOKUP_MAX_ROWS];
+  int world, log2_world;  // log2_world = -1: world is not a power of two
+};
+
 template <typename T>
 __device__ __forceinline__ long long load_index(const void* p, long long i) {
   return (long long)reinterpret_cast<const T*>(p)[i];

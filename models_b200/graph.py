@@ -38,18 +38,40 @@ class HostBatch:
                                                  for name, (shp, dt) in self.spec.items()}
 
     @classmethod
-    def like(cls, batch: Dict[str, np.ndarray], names=None) -> "HostBatch":
+    def like(cls, batch: Dict[str, np.ndarray], names=None, id_bytes: Optional[Dict[str, int]] = None) -> "HostBatch":
+        """Layout for batches shaped like `batch`.  `id_bytes` (`Model.id_bytes()`): integer id columns listed
+        there travel packed — 1 -> uint8 (B,), 2 -> uint16 (B,), 3 -> uint8 (B,3) little-endian — instead
+        of int32/int64; `fill` narrows them (ids must lie in [0, 2^(8*width)))."""
         names = list(batch) if names is None else list(names)
-        hb = cls({k: (np.asarray(batch[k]).shape, np.asarray(batch[k]).dtype) for k in names})
+        spec = {}
+        for k in names:
+            a = np.asarray(batch[k])
+            w = (id_bytes or {}).get(k)
+            if w in (1, 2, 3) and a.dtype.kind in "iu" and (a.ndim == 1 or (a.ndim == 2 and a.shape[1] == 1)):
+                spec[k] = ((a.shape[0],), np.uint8) if w == 1 else ((a.shape[0],), np.uint16) if w == 2 else ((a.shape[0], 3), np.uint8)
+            else:
+                spec[k] = (a.shape, a.dtype)
+        hb = cls(spec)
         hb.fill(batch)
         return hb
 
     def fill(self, batch: Dict[str, np.ndarray]) -> "HostBatch":
         for name, (shp, dt) in self.spec.items():
             src = np.asarray(batch[name])
-            if src.shape != shp or src.dtype != dt:
+            dst = self.columns[name].numpy()
+            if src.shape == shp and src.dtype == dt:
+                dst[...] = src
+                continue
+            width = {(1, 1): 1, (1, 2): 2, (2, 1): 3}.get((len(shp), dt.itemsize)) if dt.kind == "u" else None
+            if width is None or src.dtype.kind not in "iu" or src.size != shp[0]:
                 raise ValueError(f"column {name!r}: expected {shp} {dt}, got {src.shape} {src.dtype}")
-            self.columns[name].numpy()[...] = src
+            flat = src.reshape(-1)
+            if flat.size and (int(flat.min()) < 0 or int(flat.max()) >= (1 << (8 * width))):
+                raise ValueError(f"column {name!r}: ids outside [0, 2^{8 * width}) cannot travel as {width}-byte ids")
+            if width == 3:
+                dst[...] = flat.astype("<u4").view(np.uint8).reshape(-1, 4)[:, :3]
+            else:
+                dst[...] = flat.astype(dt)
         return self
 
     def payload_bytes(self) -> int:

@@ -132,6 +132,8 @@ class EmbeddingTable(Block):
     def lookup_kind(self, feat) -> str:
         if isinstance(feat, tuple):
             return "bag"
+        if feat.dtype == torch.uint8 and feat.dim() == 2 and feat.shape[1] == 3:
+            return "onehot"  # packed 24-bit ids (graph.HostBatch id_bytes)
         if feat.dim() == 1 or (feat.dim() == 2 and feat.shape[1] == 1):
             return "onehot"
         if feat.dim() == 2 or (feat.dim() == 3 and feat.shape[2] == 1):
@@ -178,6 +180,8 @@ class EmbeddingTable(Block):
 def _as_index(t: torch.Tensor) -> torch.Tensor:
     if t.dtype in (torch.int32, torch.int64):
         return t
+    if t.dtype in (torch.uint8, torch.uint16):  # packed host-batch ids (graph.HostBatch id_bytes)
+        return ops.widen_index(t)
     return t.to(torch.int32)  # reference casts non-int ids to int32 (inputs/embedding.py:1127-1129)
 
 

@@ -182,6 +182,74 @@ def dlrm_gather_interact(weights, indices, slots, D: int, bottom: Optional[torch
     return out
 
 
+def index_bytes_of(t: torch.Tensor) -> int:
+    """Width in bytes of the ids a categorical column carries: int32 -> 4, int64 -> 8, and the packed
+    host-batch forms uint8 (B,) -> 1, uint16 (B,) -> 2, uint8 (B, 3) -> 3 (little-endian 24-bit)."""
+    if t.dtype == torch.int32:
+        return 4
+    if t.dtype == torch.int64:
+        return 8
+    if t.dtype == torch.uint16:
+        return 2
+    if t.dtype == torch.uint8:
+        return 3 if (t.dim() == 2 and t.shape[1] == 3) else 1
+    raise TypeError(f"ids must be int32, int64, uint16, uint8 or uint8 (B,3), got {t.dtype} {tuple(t.shape)}")
+
+
+def widen_index(t: torch.Tensor) -> torch.Tensor:
+    """Packed ids -> int32 (torch ops; only the paths that do not take packed ids natively use this)."""
+    w = index_bytes_of(t)
+    if w >= 4:
+        return t
+    if w == 3:
+        b = t.to(torch.int32)
+        return b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+    return t.reshape(-1).to(torch.int32)
+
+
+def dlrm_lookup_interact(weights, indices, slots, rows, D: int, bottom: Optional[torch.Tensor], bottom_slot: int,
+                         out: torch.Tensor, oob: Optional[torch.Tensor] = None, peers=None, rank: int = 0,
+                         world: int = 1) -> torch.Tensor:
+    """Fused lookup + interaction with per-table id widths and optional row-sharded tables
+    (mm_dlrm_lookup_interact).  weights[t]: the (rows, D) table or this rank's shard; indices[t]: (B,) ids
+    (any width, see index_bytes_of); rows[t]: GLOBAL row count; peers[t]: None (replicated) or the `world`
+    device pointers of the shards as mapped in this process."""
+    _dev(out, "out")
+    B = out.shape[0]
+    n = len(weights)
+    if not (len(indices) == n and len(slots) == n and len(rows) == n):
+        raise ValueError("weights / indices / slots / rows length mismatch")
+    arr = (_cabi.LookupTable * n)()
+    keep = []
+    for t in range(n):
+        w = _dev(weights[t], f"weights[{t}]", torch.float32)
+        ix = _dev(indices[t], f"indices[{t}]")
+        if w.dim() != 2 or w.shape[1] != D or not w.is_contiguous():
+            raise ValueError(f"weights[{t}] must be a contiguous (rows, {D}) matrix")
+        wb = index_bytes_of(ix)
+        if ix.numel() != B * (3 if wb == 3 else 1) or not ix.is_contiguous():
+            raise ValueError(f"indices[{t}] must be contiguous with {B} ids, got {tuple(ix.shape)}")
+        arr[t].weights = w.data_ptr()
+        arr[t].indices = ix.data_ptr()
+        arr[t].rows = int(rows[t])
+        arr[t].slot = int(slots[t])
+        arr[t].idx_bytes = wb
+        pt = None if peers is None else peers[t]
+        if pt is not None:
+            if len(pt) != world:
+                raise ValueError(f"peers[{t}] must list {world} shard pointers")
+            pa = (C.c_void_p * world)(*[int(x) for x in pt])
+            keep.append(pa)
+            arr[t].peer_weights_host = C.cast(pa, C.POINTER(C.c_void_p))
+    o32, ostride, osplit, okp = _split_out_args(out)
+    _cabi.check(
+        _lib().mm_dlrm_lookup_interact(arr, n, B, D, rank, world, _ptr(bottom),
+                                       0 if bottom is None else _row_stride(_dev(bottom, "bottom", torch.float32), "bottom"),
+                                       bottom_slot, o32, ostride, osplit, okp, _ptr(oob), _stream()),
+        "mm_dlrm_lookup_interact")
+    return out
+
+
 def dense_fp32(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], act: Optional[str],
                out: torch.Tensor, x0: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = act(x @ W + bias)   or, with x0, the DCN-v2 cross  out = x0 * (x @ W + bias) + x."""

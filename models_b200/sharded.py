@@ -1,22 +1,29 @@
 """Row-sharded embedding tables across the GPUs of one box (BASELINE config 4).
 
-Partitioning: row r of every table lives on rank `r % world` at local row `r // world` (balanced
-under skew, keeps tiny tables from pinning to one GPU).  Dense / MLP / interaction weights are
-replicated; the batch is sharded data-parallel.
+Partitioning: row r of every sharded table lives on rank `r % world` at local row `r // world`
+(balanced under skew, keeps tiny tables from pinning to one GPU).  Tables with fewer than
+`replicate_below_rows` rows may be kept whole on every rank ("replicate tables with
+<= 64 k rows and shard only the big ones"); the default 0 shards everything.  Dense / MLP /
+interaction weights are replicated; the batch is sharded data-parallel.
 
-Forward of the lookup on every rank (one process per GPU, `torch.distributed`):
-  1. all-gather of the local index arrays -> GLOBAL indices (T, world*B_local) on every rank
-     (4 B per feature per sample: tiny next to the 256-B rows);
-  2. ONE kernel, `mm_shard_gather_push`: for the rows this rank owns it reads the row from its
-     local shard and stores it straight into the destination rank's (B_local, F, D) stack through
-     NVLink peer-mapped memory (torch symmetric memory) — gather and all-to-all fused, no pack /
-     unpack buffers and no size exchange;
-  3. a stream-ordered cross-rank barrier; everything downstream (interaction, MLPs) is replica-local.
+Forward (one process per GPU): all shards live in ONE symmetric-memory arena per rank
+(`torch.distributed._symmetric_memory`: every rank maps every other rank's arena over NVLink, same
+offsets everywhere).  The lookup is then part of the interaction kernel itself
+(`mm_dlrm_lookup_interact`, csrc/interaction_v2.cu): for each (sample, table) the owning lane derives
+owner = id % world, local row = id // world, and the cp.async that stages the row into shared memory
+reads it from that rank's shard — local HBM or a peer's HBM over NVLink.  There is no index exchange,
+no send/receive buffer, no collective and no barrier on the data path (tables are read-only in the
+forward pass), so the sharded step is the same 4 launches as the replicated one and captures into a
+CUDA graph like it.
 
 The reference's counterpart is SOK's distributed variable + `sok.lookup_sparse`
-(merlin/models/tf/distributed/embedding.py:75-84,144-148).  Host logic here (ownership maths,
-index all-gather, stack layout) is backend-agnostic and covered by world-size-2 gloo tests on CPU;
-the device step needs CUDA + peer access.
+(merlin/models/tf/distributed/embedding.py:75-84,144-148: all-to-all of keys, local lookup, all-to-all
+of vectors).  The round-1 protocol — all-gather of the ids, owner-computes push into the
+destination rank's (B_local, F, D) stack (`mm_shard_gather_push`), barrier — is kept as
+`lookup_stack` (it is what a NCCL-style exchange looks like on the same shards and serves as the
+baseline the fused kernel is measured against).  Host logic here (ownership maths, index all-gather,
+stack layout) is backend-agnostic and covered by world-size-2 gloo tests on CPU; the device step
+needs CUDA + peer access.
 """
 from __future__ import annotations
 
@@ -52,57 +59,127 @@ def shard_of(full: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 
 
 class ShardedEmbeddings:
-    """Local shards of every table of an EmbeddingsBlock + the exchange that rebuilds, on every
-    rank, the (B_local, F, D) feature stack of its own samples."""
+    """Local shards of every table of an EmbeddingsBlock inside one symmetric-memory arena, the peer
+    pointers of every other rank's arena, and the fused lookup + interaction launch."""
 
-    def __init__(self, embeddings: EmbeddingsBlock, group=None, device=None):
+    def __init__(self, embeddings: EmbeddingsBlock, group=None, device=None, replicate_below_rows: int = 0):
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.embeddings = embeddings
         self.device = device
+        self.replicate_below_rows = int(replicate_below_rows)
         self.feature_names: List[str] = embeddings.feature_names
         dims = set(embeddings.output_dims().values())
         if len(dims) != 1:
             raise ValueError("sharded lookup needs one embedding dimension for all tables")
         self.D = dims.pop()
-        self.shards: Dict[str, torch.Tensor] = {}
+        self.shards: Dict[str, torch.Tensor] = {}     # table name -> local shard (or the whole table if replicated)
+        self.peer_ptrs: Dict[str, Optional[List[int]]] = {}  # table name -> device pointers of every rank's shard (None: replicated)
         self.global_rows: Dict[str, int] = {n: t.input_dim for n, t in embeddings.tables.items()}
+        self.arena = None
+        self._arena_hdl = None
         self._symm = None
         self._symm_key = None
 
+    def is_sharded(self, table_name: str) -> bool:
+        return self.world > 1 and self.global_rows[table_name] >= self.replicate_below_rows
+
     # ---- shard construction -------------------------------------------------------------------------
-    def build(self, device) -> "ShardedEmbeddings":
-        """Create the local shard of every table directly (never materialising a full table)."""
+    def _allocate(self, device):
+        """One arena for all sharded tables (same offsets on every rank) + plain tensors for replicated ones."""
+        if self.shards:
+            return
         self.device = device
+        D = self.D
+        off, offsets = 0, {}
         for name, table in self.embeddings.tables.items():
-            if name in self.shards:
-                continue
-            lrows = local_row_count(table.input_dim, self.rank, self.world)
+            if self.is_sharded(name):
+                offsets[name] = off
+                lrows_max = (table.input_dim + self.world - 1) // self.world  # same on every rank
+                off += ((max(lrows_max, 1) * D + 63) // 64) * 64  # 256-B aligned shards
+        arena_ptrs = None
+        if off and device.type == "cuda":
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.arena = symm_mem.empty((off,), dtype=torch.float32, device=device)
+            self._arena_hdl = symm_mem.rendezvous(self.arena, group=self.group)
+            arena_ptrs = [int(p) for p in self._arena_hdl.buffer_ptrs]
+        elif off:
+            self.arena = torch.empty((off,), dtype=torch.float32, device=device)  # CPU (gloo tests): no peer mapping
+        for name, table in self.embeddings.tables.items():
+            if name in offsets:
+                lrows = local_row_count(table.input_dim, self.rank, self.world)
+                o = offsets[name]
+                self.shards[name] = self.arena[o: o + max(lrows, 1) * D].view(max(lrows, 1), D)
+                self.peer_ptrs[name] = None if arena_ptrs is None else [p + 4 * o for p in arena_ptrs]
+            else:
+                self.shards[name] = torch.empty((table.input_dim, D), dtype=torch.float32, device=device)
+                self.peer_ptrs[name] = None
+
+    def _publish(self):
+        """Shards are written once; every rank must see every other rank's rows before the first lookup."""
+        if self.device is not None and self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def build(self, device) -> "ShardedEmbeddings":
+        """Create the local shard of every table directly (never materialising a full sharded table)."""
+        if self.shards:
+            return self
+        self._allocate(device)
+        for name, table in self.embeddings.tables.items():
+            w = self.shards[name]
             init = table.embeddings_initializer
-            w = torch.empty((max(lrows, 1), table.dim), dtype=torch.float32, device=device)
+            shd = self.is_sharded(name)
+            lrows = local_row_count(table.input_dim, self.rank, self.world) if shd else table.input_dim
             if isinstance(init, dict) and "hash_seed" in init:
                 _cabi.check(_cabi.load().mm_init_uniform_hash_rows(
                     w.data_ptr(), lrows, table.dim, init["hash_seed"] & (2**64 - 1), init.get("lo", -0.05),
-                    init.get("hi", 0.05), self.rank, self.world, torch.cuda.current_stream().cuda_stream),
-                    "mm_init_uniform_hash_rows")
+                    init.get("hi", 0.05), self.rank if shd else 0, self.world if shd else 1,
+                    torch.cuda.current_stream().cuda_stream), "mm_init_uniform_hash_rows")
             elif isinstance(init, (torch.Tensor,)) or hasattr(init, "shape"):
                 full = torch.as_tensor(init, dtype=torch.float32)
-                w = shard_of(full, self.rank, self.world).to(device)
+                w[:lrows].copy_(shard_of(full, self.rank, self.world) if shd else full)
             else:
-                # seeded generators are rank-independent: build the full table row block by row block
+                # seeded generators are rank-independent: build the full table, keep this rank's rows
                 full = create_variable((table.input_dim, table.dim), init, device, f"{table.table_name}/embeddings")
-                w = shard_of(full, self.rank, self.world)
+                w[:lrows].copy_(shard_of(full, self.rank, self.world) if shd else full)
                 del full
-            self.shards[name] = w
+        self._publish()
         return self
 
     def load_full_tables(self, full: Dict[str, torch.Tensor], device) -> "ShardedEmbeddings":
         """Shard explicitly given full tables (tests, checkpoints)."""
-        self.device = device
+        self._allocate(device)
         for name in self.embeddings.tables:
-            self.shards[name] = shard_of(torch.as_tensor(full[name], dtype=torch.float32), self.rank, self.world).to(device)
+            src = torch.as_tensor(full[name], dtype=torch.float32)
+            if self.is_sharded(name):
+                mine = shard_of(src, self.rank, self.world)
+                self.shards[name][: mine.shape[0]].copy_(mine)
+                self.shards[name] = self.shards[name][: max(mine.shape[0], 1)]
+            else:
+                self.shards[name].copy_(src)
+        self._publish()
         return self
+
+    # ---- the product path: lookup fused into the interaction kernel ----------------------------------
+    def lookup_interact(self, local_inputs: Dict[str, torch.Tensor], slots: Dict[str, int], bottom: Optional[torch.Tensor],
+                        out: torch.Tensor, oob: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """out = [bottom | pairwise dots] of this rank's samples; rows owned by other ranks are read over
+        NVLink inside the kernel (mm_dlrm_lookup_interact)."""
+        if not self.shards:
+            raise RuntimeError("ShardedEmbeddings.build(device) must be called first")
+        from .core import get_feature
+
+        names = [self.embeddings.feature_to_table[f].table_name for f in self.feature_names]
+        idx = [get_feature(local_inputs, f) for f in self.feature_names]
+        idx = [i if i.dtype in (torch.uint8, torch.uint16) else _as_index(i).reshape(-1) for i in idx]
+        return ops.dlrm_lookup_interact(
+            [self.shards[n] for n in names], idx, [slots[f] for f in self.feature_names], [self.global_rows[n] for n in names],
+            self.D, bottom, slots.get("bottom_block", -1), out, oob,
+            peers=[self.peer_ptrs[n] if self.is_sharded(n) else None for n in names], rank=self.rank, world=self.world)
 
     # ---- step 1: replicate the indices ----------------------------------------------------------------
     def gather_indices(self, local_inputs: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -133,6 +210,8 @@ class ShardedEmbeddings:
         """(B_local, n_slots*D) stack with feature f at slot slots[f] (other slots untouched)."""
         if not self.shards:
             raise RuntimeError("ShardedEmbeddings.build(device) must be called first")
+        if any(not self.is_sharded(n) for n in self.shards) and self.world > 1:
+            raise NotImplementedError("lookup_stack (push protocol) needs every table sharded (replicate_below_rows=0)")
         g_idx = self.gather_indices(local_inputs)
         T, Bg = g_idx.shape
         Bl = Bg // self.world
@@ -158,9 +237,10 @@ class ShardedEmbeddings:
         return buf
 
 
-def shard_model(model, group=None):
+def shard_model(model, group=None, replicate_below_rows: int = 0):
     """Row-shard the embedding tables of a DLRM model over `group` (call before the first forward;
-    every rank then holds 1/world of each table).  Returns the model."""
+    every rank then holds 1/world of each sharded table; tables with fewer than `replicate_below_rows`
+    rows stay whole on every rank).  Returns the model."""
     from .blocks import DLRM
 
     body = getattr(model, "body", model)
@@ -168,5 +248,5 @@ def shard_model(model, group=None):
         raise NotImplementedError("shard_model supports DLRM bodies")
     if any(t.table is not None for t in body.embeddings.tables.values()):
         raise RuntimeError("shard_model must be called before the tables are built")
-    body.sharded = ShardedEmbeddings(body.embeddings, group)
+    body.sharded = ShardedEmbeddings(body.embeddings, group, replicate_below_rows=replicate_below_rows)
     return model

@@ -71,7 +71,7 @@ def main():
         print(json.dumps(r), flush=True)
         res.append(r)
 
-    if only & {"gather", "interact", "fused"}:
+    if only & {"gather", "interact", "fused", "fused2"}:
         schema = datasets.criteo_schema()
         cat = schema.select_by_tag(mm.Tags.CATEGORICAL)
         emb = mm.Embeddings(cat, dim=D, embeddings_initializer={"hash_seed": 4321})
@@ -99,6 +99,31 @@ def main():
             m, mn = timeit(lambda i: ops.dlrm_gather_interact(tables, idx[i % nb], [slots[n] for n in names], D, bottom,
                                                               slots["bottom_block"], out[i % 2]), args.iters)
             report("mm_dlrm_gather_interact", m, mn, bytes_=B * (T * D * 4 + T * 4 + D * 4 + (D + 351) * 4), law=args.law)
+
+    if "fused2" in only:
+        # the real step's launch: split-bf16 output row (B, 2*448); ids as int32 and packed (1/2/3-byte)
+        Kp = ops.tc_padded_k(D + F * (F - 1) // 2)
+        osplit = [torch.empty((B, 2 * Kp), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        rows = [t.shape[0] for t in tables]
+        sl = [slots[n] for n in names]
+        m, mn = timeit(lambda i: ops.dlrm_lookup_interact(tables, idx[i % nb], sl, rows, D, bottom, slots["bottom_block"], osplit[i % 2]), args.iters)
+        report("mm_dlrm_lookup_interact (int32 ids, split out)", m, mn, bytes_=B * (T * D * 4 + T * 4 + D * 4 + (D + 351) * 4), law=args.law)
+        def narrow(t, r):
+            h = t.cpu().numpy()
+            if r <= 256:
+                h = h.astype(np.uint8)
+            elif r <= 65536:
+                h = h.astype(np.uint16)
+            elif r <= (1 << 24):
+                h = h.astype("<u4").view(np.uint8).reshape(-1, 4)[:, :3].copy()
+            return torch.from_numpy(h).to(dev)
+        pidx = [[narrow(t, r) for t, r in zip(b_, rows)] for b_ in idx]
+        idb = sum(ops.index_bytes_of(t) for t in pidx[0])
+        m, mn = timeit(lambda i: ops.dlrm_lookup_interact(tables, pidx[i % nb], sl, rows, D, bottom, slots["bottom_block"], osplit[i % 2]), args.iters)
+        report(f"mm_dlrm_lookup_interact (packed ids {idb} B/sample, split out)", m, mn,
+               bytes_=B * (T * D * 4 + idb + D * 4 + (D + 351) * 4), law=args.law)
+        m, mn = timeit(lambda i: ops.dlrm_gather_interact(tables, idx[i % nb], sl, D, bottom, slots["bottom_block"], osplit[i % 2]), args.iters)
+        report("mm_dlrm_gather_interact (legacy entry, split out)", m, mn, bytes_=B * (T * D * 4 + T * 4 + D * 4 + (D + 351) * 4), law=args.law)
 
     if "dense" in only:
         for (K, N) in [(13, 128), (128, 64), (415, 128), (128, 64), (64, 32), (32, 1), (1037, 1037), (1024, 1024)]:
