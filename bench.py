@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200 hot path (BASELINE.json: DLRM fwd samples/s).
+"""bench.py — headline benchmark of the B200 hot path (BASELINE.json: DLRM & TwoTower fwd samples/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload dlrm|dlrm-sharded|twotower|dcn] [--batch B]
+                    [--workload all|dlrm|dlrm-sharded|twotower|dcn] [--batch B]
 
-N=1 workload = BASELINE.json configs[1]: mm.DLRMModel, Criteo shape (26 cat, 13 dense, emb 64,
+Headline workload = BASELINE.json configs[1]: mm.DLRMModel, Criteo shape (26 cat, 13 dense, emb 64,
 bundled cardinalities = 45.6 M rows / 11.7 GB of tables), batch 65 536, README MLP dims.
 A step = one forward pass over one batch of synthetic input.  N>1 (torchrun): one replica per
 GPU on disjoint batches, no data-path collective (the forward is replica-local),
 weak scaling.
 
 Prints ONE JSON line (contract in the task statement): value = device-resident samples/s,
-e2e = the same metric through the public host-buffer call (pinned H2D + forward + D2H inside the
-timed region), roofline = dominant kernel vs measured HBM peak, cpu_baseline = CPU restatement
-of the reference op sequence on this box's host cores (rank 0, N=1 only).
-`--impl reference` times that CPU restatement alone (TensorFlow is not installable: no network).
-`--workload twotower` (configs[2]: 10 M-item catalog, in-batch negatives, batch 16 384) and `--workload dcn`
-(configs[4]: DCN-v2 depth 3 + MLP[256,128], batch 65 536) print the same kind of line for the other
-single-GPU configurations; `--workload dlrm-sharded` is configs[3] (row-sharded tables, torchrun).
+e2e = the same metric through the public host-buffer call (pinned H2D of a PACKED batch — ids at 1/2/3
+bytes — + forward + D2H inside the timed region), roofline = dominant kernel vs measured HBM peak (both
+the algorithmic-bytes fraction and the DRAM-traffic fraction), cpu_baseline = CPU restatement of the
+reference op sequence on this box's host cores (rank 0, N=1 only).
+The default `--workload all` adds to the same line:
+  "secondary": {"twotower": {...}, "dcn": {...}} — configs[2] (10 M-item catalog, in-batch negatives,
+      batch 16 384) and configs[4] (DCN-v2 depth 3 + MLP[256,128], batch 65 536), each with its own value,
+      e2e and roofline (the other half of BASELINE.json's metric), replicas under torchrun;
+  "sharded": {...} (N > 1 only) — configs[3]: Criteo-TB-shape tables row-sharded over the N GPUs, lookup
+      fused into the interaction kernel over NVLink peer memory, checked bit-exact against the unsharded
+      model on the same box, with ms/step, NVLink GB/s per GPU and the staged (all-gather + push + barrier)
+      protocol timed beside it.
+`--impl reference` times the CPU restatement alone on the SAME 65 536-sample step (TensorFlow is not
+installable: no network).  `--workload dlrm|twotower|dcn|dlrm-sharded` print a line for that workload only.
 """
 from __future__ import annotations
 
@@ -143,11 +150,15 @@ def ncu_traffic_bytes(summary: Path):
         return None
 
 
-def dlrm_bytes_per_sample(T=26, D=64, idx_bytes=4, P=64):
+def dlrm_bytes_per_sample(T=26, D=64, id_bytes_total=104, P=64):
+    """rows read + ids + bottom vector + output row = 8 676 B with int32 ids."""
     F = T + 1
-    fused = T * D * 4 + T * idx_bytes + D * 4 + (P + F * (F - 1) // 2) * 4  # 8 676 B
-    gather = 2 * T * D * 4 + T * idx_bytes  # standalone gather: 13 416 B
+    fused = T * D * 4 + id_bytes_total + D * 4 + (P + F * (F - 1) // 2) * 4
+    gather = 2 * T * D * 4 + id_bytes_total  # standalone gather: 13 416 B
     return fused, gather
+
+
+NCU_FUSED_SUMMARY = "profiles/r02_ncu_fused_v2.txt"  # `ncu --set full` summary of THIS round's dominant kernel
 
 
 def cpu_baseline_dlrm(model, feats_host, sample_rows, threads):
@@ -174,18 +185,265 @@ def cpu_baseline_dlrm(model, feats_host, sample_rows, threads):
     return run
 
 
+
+class Ctx:
+    """Process-wide handles shared by the workload functions."""
+
+    def __init__(self, args, mm, datasets, ops, dev, rank, local_rank, world):
+        self.args, self.mm, self.datasets, self.ops = args, mm, datasets, ops
+        self.dev, self.rank, self.local_rank, self.world = dev, rank, local_rank, world
+
+    def barrier(self):
+        import torch
+
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(device_ids=[self.local_rank])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        import torch
+
+        if self.world == 1:
+            return [float(v) for v in vals]
+        import torch.distributed as dist
+
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum_over_ranks(self, v):
+        import torch
+
+        if self.world == 1:
+            return int(v)
+        import torch.distributed as dist
+
+        t = torch.tensor([int(v)], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+
+def timed_replay(ctx, pf, packed_dev, steps, warmup):
+    """K device-resident steps through model.pipeline (graph replays on `depth` streams): CUDA events on the
+    submitting stream, barrier + synchronize on both sides, clocks sampled during the region."""
+    import torch
+
+    n_bufs = len(packed_dev)
+    pf.n = 0
+    for i in range(warmup):
+        pf.submit_device(packed_dev[i % n_bufs])
+    pf.join()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        pf.submit_device(packed_dev[i % n_bufs])
+    pf.join()
+    t1.record()
+    ctx.barrier()
+    clocks = sampler.stop()
+    return t0.elapsed_time(t1), clocks
+
+
+def timed_serial(cf, packed_dev, steps):
+    import torch
+
+    n_bufs = len(packed_dev)
+    for i in range(3):
+        cf.load_device(packed_dev[i % n_bufs])
+        cf.replay()
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(steps):
+        cf.load_device(packed_dev[i % n_bufs])
+        cf.replay()
+    s1.record()
+    torch.cuda.synchronize()
+    return s0.elapsed_time(s1) / steps
+
+
+def timed_e2e(ctx, pf, hbs, steps, depth):
+    """Public host-buffer call: per step ONE pinned H2D of the packed batch + graph + D2H of the predictions,
+    `depth` steps in flight; wall clock from first submit to last result on the host."""
+    import torch
+
+    n_bufs = len(hbs)
+
+    def loop(n):
+        tickets, res = [], None
+        for i in range(n):
+            tickets.append(pf.submit(hbs[i % n_bufs]))
+            if len(tickets) == depth:
+                res = pf.result(tickets.pop(0))
+        while tickets:
+            res = pf.result(tickets.pop(0))
+        return res
+
+    pf.n = 0
+    loop(depth + 1)
+    ctx.barrier()
+    pf.n = 0
+    w0 = time.perf_counter()
+    res = loop(steps)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - w0) * 1e3
+    ctx.barrier()
+    return ms, res
+
+
+def event_times(fn, n, warmup=3):
+    """Mean duration of `fn(i)` launched back to back, one CUDA-event pair per launch."""
+    import torch
+
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    evs = []
+    for i in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(i)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+# ---------------------------------------------------------------------------------------------
+# headline: DLRM replicas
+# ---------------------------------------------------------------------------------------------
+def dlrm_record(ctx):
+    import torch
+
+    args, mm, datasets, ops, dev, world = ctx.args, ctx.mm, ctx.datasets, ctx.ops, ctx.dev, ctx.world
+    B = args.batch or 65536
+    schema, model = build_dlrm(mm, datasets)
+    model.build(dev)
+    n_bufs = 4
+    hosts = host_batches(datasets, schema, B, n_bufs, seed0=1234 + 1000 * ctx.rank)
+    widths = model.id_bytes()
+    # packed pinned host batches (one allocation each, ids at 1/2/3 bytes) and their device-resident copies
+    hbs = [mm.HostBatch.like(h, model.input_columns(), id_bytes=widths) for h in hosts]
+    packed_dev = [hb.buffer.to(dev) for hb in hbs]
+    devs = [{k: torch.from_numpy(v).to(dev) for k, v in h.items()} for h in hosts]
+    torch.cuda.synchronize()
+
+    # the public serving call: forward captured into a CUDA graph over static buffers
+    cf = model.compile(hbs[0])
+    ref_out = model(devs[0])  # int32 ids through the eager path
+    cf.load_device(packed_dev[0])
+    assert torch.equal(ref_out, cf.replay()), "graph replay on packed ids diverges from model.__call__ on int32 ids"
+
+    # Steps are independent forward passes; `depth` graph instances on as many streams let the small kernels
+    # of step i+1 (bottom MLP, narrow top layers) fill SMs that step i leaves idle — the same runtime
+    # the host-buffer path uses.  K steps are still exactly K forward passes over K batches.
+    depth = args.pipeline_depth
+    pf = model.pipeline(hbs[0], depth=depth)
+    pf.submit_device(packed_dev[1])
+    pf.join()
+    torch.cuda.synchronize()
+    assert torch.equal(model(devs[1]), pf.output(0)), "pipelined replay diverges from model.__call__"
+
+    elapsed_ms, clocks = timed_replay(ctx, pf, packed_dev, args.steps, args.warmup)
+    launches = cf.launches_per_replay * args.steps
+    serial_ms = timed_serial(cf, packed_dev, args.steps)
+
+    # ---- roofline of the dominant kernel: launched back to back on the same rotating (packed) inputs with a
+    # CUDA-event pair around every launch (graph nodes cannot be bracketed individually)
+    body = model.body
+    slots = body.slots()
+    names = body.embeddings.feature_names
+    tables = [body.embeddings.feature_to_table[f].table for f in names]
+    rows = [t.shape[0] for t in tables]
+    slot_list = [slots[f] for f in names]
+    bottoms = [body.bottom_forward(d) for d in devs]
+    width = body.output_width_before_top()
+    a_out = torch.empty((B, 2 * ops.tc_padded_k(width)), dtype=torch.bfloat16, device=dev)
+    # packed id views of the device-resident batches (same layout the graph reads)
+    from models_b200.graph import _view
+
+    idx_lists = [[_view(pd, hbs[0].offsets[f], *hbs[0].spec[f]) for f in names] for pd in packed_dev]
+    id_bytes_total = sum(ops.index_bytes_of(t) for t in idx_lists[0])
+
+    def dominant(i):
+        ops.dlrm_lookup_interact(tables, idx_lists[i % n_bufs], slot_list, rows, 64, bottoms[i % n_bufs],
+                                 slots["bottom_block"], a_out)
+
+    kern_ms = event_times(dominant, args.steps, args.warmup)
+
+    e2e_steps = max(5, args.steps)
+    e2e_ms, res = timed_e2e(ctx, pf, hbs, e2e_steps, depth)
+    ref_host = cf(hbs[(e2e_steps - 1) % n_bufs]).clone()
+    assert torch.equal(res, ref_host), "pipelined e2e result differs from the serial graph call"
+    h2d = int(hbs[0].payload_bytes())
+    d2h = int(res.numel() * res.element_size())
+
+    elapsed_ms, e2e_ms, kern_ms = ctx.max_over_ranks(elapsed_ms, e2e_ms, kern_ms)
+    launches = ctx.sum_over_ranks(launches)
+    peak, peak_src = measured_peaks()
+    fused_b, _ = dlrm_bytes_per_sample(id_bytes_total=id_bytes_total)
+    achieved = fused_b * B / (kern_ms * 1e-3) / 1e9
+    traffic = ncu_traffic_bytes(ROOT / NCU_FUSED_SUMMARY) if B == 65536 else None
+    line = {
+        "metric": "DLRM fwd samples/sec (Criteo shape, batch 65536/GPU)",
+        "value": world * B * args.steps / (elapsed_ms * 1e-3),
+        "unit": "samples/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "fp32 I/O; GEMM-shaped work as split-bf16 x3 (hi*hi + hi*lo + lo*hi, fp32 accumulate, |err| ~ 2^-16)",
+        "data": "synthetic (uniform indices over bundled Criteo cardinalities; hash-initialised tables, random-init MLPs)",
+        "config": {
+            "workload": "mm.DLRMModel Criteo-shape (26 cat, 13 dense, emb_dim 64), bottom [128,64], top [128,64,32]",
+            "batch_per_gpu": B, "global_batch": B * world,
+            "index_dtype": f"packed per table (8 x u8, 10 x u16, 8 x u24 = {id_bytes_total} B/sample; Model.id_bytes())",
+            "table_rows": 45621194,
+            "table_gb": 11.68, "parallelism": f"replicas x{world} (no data-path collective)",
+            "l2": f"inputs larger than L2: 11.7 GB of tables, {n_bufs} rotating input batches, no flush",
+            "runtime": f"CUDA graph replay, {depth} graph instances on {depth} streams (model.pipeline): independent steps overlap; "
+                       "input refresh = one D2D copy of the packed batch per step",
+            "ms_per_step_single_stream": serial_ms,
+            "dense_engine": mm.dense_engine(),
+        },
+        "clocks": clocks,
+        "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "h2d_gbs_per_gpu": h2d * e2e_steps / (e2e_ms * 1e-3) / 1e9},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "interact_v2_kernel<lookup-fused> (mm_dlrm_lookup_interact)",
+                     "timing": "CUDA events around each of K back-to-back launches on the same rotating inputs (graph nodes cannot be bracketed)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": fused_b * B,
+                     "kernel_ms": kern_ms,
+                     "traffic": traffic,
+                     "dram_frac": None if traffic is None else traffic / (kern_ms * 1e-3) / 1e9 / peak,
+                     "traffic_source": f"{NCU_FUSED_SUMMARY} (ncu --set full of this round's kernel, one launch, B=65536; the 19 "
+                                       "small tables are L2-resident, so DRAM traffic < algorithmic bytes)"},
+    }
+    return line, model, hosts
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dlrm", choices=["dlrm", "dlrm-sharded", "twotower", "dcn"])
+    ap.add_argument("--workload", default="all", choices=["all", "dlrm", "dlrm-sharded", "twotower", "dcn"])
     ap.add_argument("--batch", type=int, default=None)
-    ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--cpu-sample", type=int, default=None, help="samples per CPU pass (default: the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline-depth", type=int, default=3,
-                    help="graph instances / streams of model.pipeline (3: one more pinned H2D in flight than 2 — e2e 288 -> 337 M samples/s)")
+                    help="graph instances / streams of model.pipeline (3: one more pinned H2D in flight than 2)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -198,11 +456,7 @@ def main():
 
     import models_b200 as mm
     from models_b200 import datasets, ops
-    from models_b200.blocks import run_dense_chain
 
-    if args.batch is None:
-        args.batch = 16384 if args.workload == "twotower" else 65536
-    B = args.batch
     cores = usable_cores()
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -216,200 +470,63 @@ def main():
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
+    import torch.distributed as dist
 
+    if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx(args, mm, datasets, ops, dev, rank, local_rank, world)
+
+    def finish(line):
+        if rank == 0:
+            print(json.dumps(line))
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return 0
 
     if args.workload == "dlrm-sharded":
-        return sharded_arm(args, mm, datasets, ops, dev, rank, local_rank, world)
+        rec = sharded_record(ctx)
+        rec.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "unit": "samples/s"})
+        return finish(rec)
     if args.workload in ("twotower", "dcn"):
-        return secondary_arm(args, mm, datasets, ops, dev, rank, local_rank, world)
+        rec = secondary_record(ctx, args.workload)
+        rec.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None})
+        return finish(rec)
 
-    schema, model = build_dlrm(mm, datasets)
-    model.build(dev)
-    n_bufs = 4
-    hosts = host_batches(datasets, schema, B, n_bufs, seed0=1234 + 1000 * rank)
-    # packed pinned host batches (one allocation each) and their device-resident copies
-    hbs = [mm.HostBatch.like(h, model.input_columns()) for h in hosts]
-    packed_dev = [hb.buffer.to(dev) for hb in hbs]
-    devs = [{k: torch.from_numpy(v).to(dev) for k, v in h.items()} for h in hosts]
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize()
-
-    # the public serving call: forward captured into a CUDA graph over static buffers
-    cf = model.compile(hbs[0])
-    ref_out = model(devs[0])
-    cf.load_device(packed_dev[0])
-    assert torch.equal(ref_out, cf.replay()), "graph replay diverges from model.__call__"
-
-    # Steps are independent forward passes; two graph instances on two streams let the small kernels
-    # of step i+1 (bottom MLP, narrow top layers) fill SMs that step i leaves idle — the same runtime
-    # the host-buffer path uses.  K steps are still exactly K forward passes over K batches.
-    pf = model.pipeline(hbs[0], depth=args.pipeline_depth)
-    pf.submit_device(packed_dev[1])
-    pf.join()
-    torch.cuda.synchronize()
-    assert torch.equal(model(devs[1]), pf.output(0)), "pipelined replay diverges from model.__call__"
-    pf.n = 0
-
-    def step(i):
-        return pf.submit_device(packed_dev[i % n_bufs])
-
-    for i in range(args.warmup):
-        step(i)
-    pf.join()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for i in range(args.steps):
-        step(i)
-    pf.join()
-    t1.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = cf.launches_per_replay * args.steps
-    elapsed_ms = t0.elapsed_time(t1)
-    # serial single-stream figure for reference (no overlap between steps)
-    for i in range(3):
-        cf.load_device(packed_dev[i % n_bufs]); cf.replay()
-    torch.cuda.synchronize()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for i in range(args.steps):
-        cf.load_device(packed_dev[i % n_bufs])
-        cf.replay()
-    s1.record()
-    torch.cuda.synchronize()
-    serial_ms = s0.elapsed_time(s1) / args.steps
-
-    # ---- roofline of the dominant kernel: launched back to back on the same rotating inputs with a
-    # CUDA-event pair around every launch (the host runs ahead of the GPU, so each pair brackets
-    # exactly one kernel execution; graph nodes cannot be bracketed individually)
-    body = model.body
-    slots = body.slots()
-    feats_names = body.embeddings.feature_names
-    tables = [body.embeddings.feature_to_table[f].table for f in feats_names]
-    slot_list = [slots[f] for f in feats_names]
-    bottoms = [body.bottom_forward(d) for d in devs]
-    width = body.output_width_before_top()
-    a_out = torch.empty((B, 2 * ops.tc_padded_k(width)), dtype=torch.bfloat16, device=dev)
-    idx_lists = [[d[f] for f in feats_names] for d in devs]
-
-    def dominant(i):
-        ops.dlrm_gather_interact(tables, idx_lists[i % n_bufs], slot_list, 64, bottoms[i % n_bufs],
-                                 slots["bottom_block"], a_out)
-
-    for i in range(args.warmup):
-        dominant(i)
-    torch.cuda.synchronize()
-    kev = []
-    for i in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dominant(i)
-        e1.record()
-        kev.append((e0, e1))
-    torch.cuda.synchronize()
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-
-    # ---- e2e: public host-buffer call; ONE pinned H2D + graph + D2H per step inside the region
-    # model.pipeline: two graph instances on two streams; the pinned H2D copy of step i+1 overlaps the
-    # forward of step i.  Every step still copies its own inputs in and its own predictions out.
-    e2e_steps = max(5, args.steps)
-
-    def e2e_loop(n):
-        tickets = []
-        res = None
-        for i in range(n):
-            tickets.append(pf.submit(hbs[i % n_bufs]))
-            if len(tickets) == args.pipeline_depth:
-                res = pf.result(tickets.pop(0))
-        while tickets:
-            res = pf.result(tickets.pop(0))
-        return res
-
-    e2e_loop(4)
-    barrier()
-    w0 = time.perf_counter()
-    res = e2e_loop(e2e_steps)  # ends with the last result on the host (event-synchronised)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - w0) * 1e3
-    barrier()
-    ref_host = cf(hbs[(e2e_steps - 1) % n_bufs]).clone()
-    assert torch.equal(res, ref_host), "pipelined e2e result differs from the serial graph call"
-    h2d = int(hbs[0].payload_bytes())
-    d2h = int(res.numel() * res.element_size())
-
-    if world > 1:
-        import torch.distributed as dist
-
-        t = torch.tensor([elapsed_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, kern_ms = (float(x) for x in t.tolist())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        fused_b, gather_b = dlrm_bytes_per_sample()
-        achieved = fused_b * B / (kern_ms * 1e-3) / 1e9
-        line = {
-            "metric": "DLRM fwd samples/sec (Criteo shape, batch 65536/GPU)",
-            "value": world * B * args.steps / (elapsed_ms * 1e-3),
-            "unit": "samples/s",
-            "n_gpus": world,
-            "steps": args.steps,
-            "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True,
-            "scaling": "weak",
-            "vs_baseline": None,
-            "dtype": "fp32",
-            "data": "synthetic (uniform indices over bundled Criteo cardinalities; hash-initialised tables, random-init MLPs)",
-            "config": {
-                "workload": "mm.DLRMModel Criteo-shape (26 cat, 13 dense, emb_dim 64), bottom [128,64], top [128,64,32]",
-                "batch_per_gpu": B, "global_batch": B * world, "index_dtype": "int32", "table_rows": 45621194,
-                "table_gb": 11.68, "parallelism": f"replicas x{world} (no data-path collective)",
-                "l2": f"inputs larger than L2: 11.7 GB of tables, {n_bufs} rotating input batches, no flush",
-                "runtime": f"CUDA graph replay, {args.pipeline_depth} graph instances on {args.pipeline_depth} streams (model.pipeline): independent steps overlap; "
-                           "input refresh = one D2D copy of the packed batch per step",
-                "ms_per_step_single_stream": serial_ms,
-                "dense_engine": mm.dense_engine(),
-            },
-            "clocks": clocks,
-            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "samples/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "interact_mma_kernel<gather-fused> (mm_dlrm_gather_interact)",
-                         "timing": "CUDA events around each of K back-to-back launches on the same rotating inputs (graph nodes cannot be bracketed)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": fused_b * B,
-                         "kernel_ms": kern_ms,
-                         "traffic": ncu_traffic_bytes(ROOT / "profiles" / "r01_ncu_fused_m.txt") if B == 65536 else None,
-                         "traffic_source": "profiles/r01_ncu_fused_m.txt (ncu --set full, one launch, B=65536; the 19 "
-                                           "small tables are L2-resident, so DRAM traffic < algorithmic bytes)"},
-        }
-        if world == 1 and not args.no_cpu_baseline:
+    line, model, hosts = dlrm_record(ctx)
+    if world == 1 and not args.no_cpu_baseline and rank == 0:
+        try:
+            line["cpu_baseline"] = time_cpu_baseline(model, hosts[0], min(args.cpu_sample or 16384, args.batch or 65536), cores)
+        except Exception as e:  # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    del model, hosts
+    free_device_memory()
+    if args.workload == "all":
+        line["secondary"] = {}
+        for kind in ("twotower", "dcn"):
             try:
-                line["cpu_baseline"] = time_cpu_baseline(model, hosts[0], min(args.cpu_sample, B), cores)
-            except Exception as e:  # the baseline must never take the bench line down
-                line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
-        print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
+                line["secondary"][kind] = secondary_record(ctx, kind)
+            except Exception as e:  # a secondary record must never take the headline down
+                line["secondary"][kind] = {"error": f"{type(e).__name__}: {e}"}
+            free_device_memory()
+        if world > 1:
+            try:
+                line["sharded"] = sharded_record(ctx)
+            except Exception as e:
+                line["sharded"] = {"error": f"{type(e).__name__}: {e}"}
+            free_device_memory()
+    return finish(line)
 
-        dist.destroy_process_group()
-    return 0
+
+def free_device_memory():
+    import gc
+
+    import torch
+
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
 
 
 def usable_cores() -> int:
@@ -438,79 +555,163 @@ def pick_threads(run, cores):
     return best
 
 
-def sharded_arm(args, mm, datasets, ops, dev, rank, local_rank, world):
-    """BASELINE config 4: Criteo-TB-shape tables (204 M rows x 64 fp32 = 52 GB) row-sharded over the
-    ranks (row r on rank r % world), batch 65 536 per GPU, data-parallel MLPs.  One step = index
-    all-gather + owner-computes NVLink push (mm_shard_gather_push) + barrier + interaction + MLPs."""
+
+# ---------------------------------------------------------------------------------------------
+# configs[3]: row-sharded tables (N > 1)
+# ---------------------------------------------------------------------------------------------
+def sharded_record(ctx):
+    """BASELINE config 4: Criteo-TB-shape tables (204 M rows x 64 fp32 = 52 GB) row-sharded over the ranks (row r on
+    rank r % world), batch 65 536 per GPU, data-parallel MLPs.  The lookup is part of the interaction kernel: rows
+    owned by other ranks are read over NVLink peer memory straight into shared memory (no exchange step, no barrier),
+    so the step is graph-captured like the replicated one.  Two placements are reported: every table sharded, and
+    big tables sharded + tables under 65 536 rows replicated.  Parity: the sharded logits must be bit-identical to
+    the unsharded model's on the same batch, on every rank.  The staged protocol of round 1 (NCCL all-gather of the
+    ids + owner-computes push + symmetric-memory barriers, eager) is timed beside it as the baseline."""
     import torch
     import torch.distributed as dist
 
-    if world == 1:
+    args, mm, datasets, ops, dev, world, rank = ctx.args, ctx.mm, ctx.datasets, ctx.ops, ctx.dev, ctx.world, ctx.rank
+    if not dist.is_initialized():
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1, device_id=dev)
-    B = args.batch
+    B = args.batch or 65536
+    steps = args.steps
     schema = datasets.criteo_tb_schema()
-    model = mm.DLRMModel(schema, embedding_dim=64, bottom_block=mm.MLPBlock([128, 64]), top_block=mm.MLPBlock([128, 64, 32]),
+    rows_total = sum(datasets.CRITEO_TB_ROWS)
+
+    def make(shard_below=None):
+        mm.set_seed(4)
+        m = mm.DLRMModel(schema, embedding_dim=64, bottom_block=mm.MLPBlock([128, 64]), top_block=mm.MLPBlock([128, 64, 32]),
                          embedding_options=mm.EmbeddingOptions(embeddings_initializers={"hash_seed": 4321}))
-    mm.shard_model(model)
-    model.build(dev)
+        if shard_below is not None:
+            mm.shard_model(m, replicate_below_rows=shard_below)
+        m.build(dev)
+        return m
+
     n_bufs = 3
-    devs = []
+    hosts = []
     for i in range(n_bufs):
-        b, _ = datasets.split_targets(schema, datasets.generate_batch(schema, B, seed=4000 + 100 * rank + i, index_law="uniform"))
-        devs.append({k: torch.from_numpy(v).to(dev) for k, v in b.items()})
-    torch.cuda.synchronize()
+        b, _ = datasets.split_targets(schema, datasets.generate_batch(schema, B, seed=4000 + 100 * rank + i, index_law="uniform",
+                                                                      index_dtype=np.int32))
+        hosts.append(b)
+    devs = [{k: torch.from_numpy(v).to(dev) for k, v in h.items()} for h in hosts]
 
-    def barrier():
-        dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize()
+    # unsharded model of the same shape (52 GB of tables on this GPU) -> the logits every placement must reproduce
+    full = make()
+    want = full(devs[0]).clone()
+    del full
+    free_device_memory()
 
-    for i in range(args.warmup):
-        model(devs[i % n_bufs])
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = ops.launch_count()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for i in range(args.steps):
-        out = model(devs[i % n_bufs])
-    t1.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = ops.launch_count() - l0
-    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-    dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(t.item())
-    if rank == 0:
-        rows = sum(datasets.CRITEO_TB_ROWS)
-        nv_bytes = B * 26 * 64 * 4 * (world - 1) / world  # payload each GPU sends (and receives) per step
-        print(json.dumps({
-            "metric": "DLRM fwd samples/sec (Criteo-TB shape, row-sharded tables, batch 65536/GPU)",
-            "value": world * B * args.steps / (elapsed_ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32", "data": "synthetic (uniform indices; hash-initialised shards)",
-            "config": {"workload": "mm.DLRMModel Criteo-TB-shape, tables row-sharded (row r on rank r % world), "
-                                   "index all-gather + owner-computes NVLink push + barrier",
-                       "batch_per_gpu": B, "global_batch": B * world, "table_rows": rows, "table_gb": rows * 256 / 1e9,
-                       "shard_gb_per_gpu": rows * 256 / 1e9 / world, "parallelism": f"tables row-sharded x{world}, MLPs dp{world}",
-                       "nvlink_payload_bytes_per_gpu_per_step": nv_bytes, "runtime": "eager (symmetric-memory barriers)"},
-            "clocks": clocks, "gpu_launches": int(lt.item()),
-        }))
-    dist.destroy_process_group()
-    return 0
+    rec = {
+        "metric": "DLRM fwd samples/sec (Criteo-TB shape, row-sharded tables, batch 65536/GPU)",
+        "data": "synthetic (uniform indices; hash-initialised shards)", "dtype": "fp32 I/O; split-bf16 x3 GEMM work",
+        "config": {"workload": "mm.DLRMModel Criteo-TB-shape (MLPerf DLRM-DCNv2 capped cardinalities), tables row-sharded "
+                               "(row r on rank r % world at local row r / world), MLPs data-parallel",
+                   "batch_per_gpu": B, "global_batch": B * world, "table_rows": rows_total, "table_gb": rows_total * 256 / 1e9,
+                   "parallelism": f"tables row-sharded x{world}, MLPs dp{world}",
+                   "exchange": "none as a separate step: mm_dlrm_lookup_interact reads remote rows over NVLink peer memory "
+                               "(cp.async from the owner's shard into the consuming SM's shared memory)",
+                   "runtime": f"CUDA graph replay, {args.pipeline_depth} graph instances (no collective, no barrier in the graph)"},
+        "placements": {},
+    }
+    link_ref = 770.0  # GB/s per direction per GPU: measured peer copy (B200_PROFILING.md); nominal 900
+    for label, below in (("all_tables_sharded", 0), ("big_sharded_small_replicated", 65536)):
+        model = make(below)
+        se = model.body.sharded
+        got = model(devs[0])
+        ok = int(torch.equal(got, want))
+        flag = torch.tensor([ok], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        widths = model.id_bytes()
+        hbs = [mm.HostBatch.like(h, model.input_columns(), id_bytes=widths) for h in hosts]
+        packed_dev = [hb.buffer.to(dev) for hb in hbs]
+        cf = model.compile(hbs[0])
+        cf.load_device(packed_dev[0])
+        graph_ok = int(torch.equal(cf.replay(), want))
+        pf = model.pipeline(hbs[0], depth=args.pipeline_depth)
+        elapsed_ms, clocks = timed_replay(ctx, pf, packed_dev, steps, args.warmup)
+        serial_ms = timed_serial(cf, packed_dev, steps)
+        # the fused lookup + interaction kernel alone
+        body = model.body
+        bottoms = [body.bottom_forward(d) for d in devs]
+        kern_ms = event_times(lambda i: body.interaction_forward(devs[i % n_bufs], bottoms[i % n_bufs], as_split=True),
+                              max(5, steps // 2))
+        e2e_steps = max(5, min(steps, 20))
+        e2e_ms, _ = timed_e2e(ctx, pf, hbs, e2e_steps, args.pipeline_depth)
+        # exact NVLink payload of this rank's batch 0: rows whose owner is another rank
+        remote = 0
+        n_sharded = 0
+        for f in se.feature_names:
+            name = body.embeddings.feature_to_table[f].table_name
+            if se.is_sharded(name):
+                n_sharded += 1
+                remote += int((hosts[0][f].astype(np.int64) % world != rank).sum())
+        remote_bytes = remote * 256
+        elapsed_ms, serial_ms, kern_ms, e2e_ms, remote_b = ctx.max_over_ranks(elapsed_ms, serial_ms, kern_ms, e2e_ms, remote_bytes)
+        rec["placements"][label] = {
+            "replicate_below_rows": below, "tables_sharded": n_sharded, "tables_replicated": 26 - n_sharded,
+            "shard_gb_per_gpu": float(se.arena.numel() * 4 / 1e9) if se.arena is not None else 0.0,
+            "parity": "bit-exact vs the unsharded model on every rank" if int(flag.item()) == 1 else "MISMATCH",
+            "graph_replay_parity": bool(graph_ok),
+            "value": world * B * steps / (elapsed_ms * 1e-3), "unit": "samples/s", "ms_per_step": elapsed_ms / steps,
+            "ms_per_step_single_stream": serial_ms,
+            "lookup_interact_kernel_ms": kern_ms,
+            "nvlink_bytes_in_per_gpu_per_step": remote_b,
+            "nvlink_gbs_per_gpu_kernel": remote_b / (kern_ms * 1e-3) / 1e9,
+            "nvlink_gbs_per_gpu_step": remote_b / (elapsed_ms / steps * 1e-3) / 1e9,
+            "nvlink_ref_gbs": link_ref, "nvlink_frac_kernel": remote_b / (kern_ms * 1e-3) / 1e9 / link_ref,
+            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": int(hbs[0].payload_bytes()), "d2h_bytes_per_step": B * 4},
+            "gpu_launches": ctx.sum_over_ranks(cf.launches_per_replay * steps), "clocks": clocks,
+        }
+        if below == 0 and world > 1:
+            # staged baseline on the same shards: ids all-gathered by NCCL, owner-computes push into the destination
+            # rank's (B,F,D) stack, barriers, interaction from the stack — eager, as in round 1
+            slots = body.slots()
+            F = len(slots)
+            out = torch.empty((B, 2 * ops.tc_padded_k(body.output_width_before_top())), dtype=torch.bfloat16, device=dev)
+
+            def staged(i):
+                d = devs[i % n_bufs]
+                stack = se.lookup_stack(d, slots, F)
+                ops.concat_columns([bottoms[i % n_bufs]], stack, [slots["bottom_block"] * 64])
+                ops.dot_interaction(stack.view(B, F, 64), out, prefix=bottoms[i % n_bufs])
+
+            for i in range(3):
+                staged(i)
+            ctx.barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_st = max(5, min(steps, 10))
+            t0.record()
+            for i in range(n_st):
+                staged(i)
+            t1.record()
+            ctx.barrier()
+            (st_ms,) = ctx.max_over_ranks(t0.elapsed_time(t1) / n_st)
+            rec["placements"][label]["staged_protocol_ms"] = st_ms
+            rec["placements"][label]["staged_protocol"] = ("NCCL all-gather of ids + mm_shard_gather_push + symmetric-memory "
+                                                           "barriers + interaction from the stack (eager; same shards)")
+        del cf, pf, model, se, body, bottoms
+        free_device_memory()
+    best = rec["placements"]["all_tables_sharded"]
+    rec["value"], rec["ms_per_step"] = best["value"], best["ms_per_step"]
+    return rec
 
 
-def secondary_arm(args, mm, datasets, ops, dev, rank, local_rank, world):
+# ---------------------------------------------------------------------------------------------
+# configs[2] and configs[4]: two-tower and DCN-v2 (replicas under torchrun)
+# ---------------------------------------------------------------------------------------------
+def secondary_record(ctx, kind):
     """BASELINE configs[2] (two-tower, 10 M-item catalog, in-batch negatives, B = 16 384) and configs[4]
     (DCN-v2, depth 3, deep [256,128], B = 65 536): same timing protocol as the DLRM arm (graph replay on two
     streams for `value`, packed pinned host batches for `e2e`, CUDA events, clocks), replicas under torchrun."""
     import torch
 
-    B = args.batch
+    args, mm, datasets, ops, dev, world, rank = ctx.args, ctx.mm, ctx.datasets, ctx.ops, ctx.dev, ctx.world, ctx.rank
+    steps = args.steps
     mm.set_seed(1)
-    if args.workload == "twotower":
+    if kind == "twotower":
+        B = args.batch if (args.batch and args.workload == "twotower") else 16384
         schema = datasets.retrieval_10m_schema()
         model = mm.TwoTowerModel(schema, query_tower=mm.MLPBlock([256, 128]),
                                  embedding_options=mm.EmbeddingOptions(embeddings_initializers={"hash_seed": 5}))
@@ -519,6 +720,7 @@ def secondary_arm(args, mm, datasets, ops, dev, rank, local_rank, world):
         label = "mm.TwoTowerModel 10M-item catalog, towers [256,128], in-batch sampled softmax (train-mode forward: (B, 1+B) logits)"
         metric = "TwoTower fwd samples/sec (10M-item catalog, in-batch negatives, batch 16384/GPU)"
     else:
+        B = args.batch if (args.batch and args.workload == "dcn") else 65536
         schema = datasets.criteo_schema()
         model = mm.DCNModel(schema, depth=3, deep_block=mm.MLPBlock([256, 128]), embeddings_initializer={"hash_seed": 99})
         call_kwargs = {}
@@ -533,42 +735,13 @@ def secondary_arm(args, mm, datasets, ops, dev, rank, local_rank, world):
     model.build(dev)
     hbs = [mm.HostBatch.like(h, model.input_columns()) for h in hosts]
     packed_dev = [hb.buffer.to(dev) for hb in hbs]
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize()
-
     cf = model.compile(hbs[0], **call_kwargs)
     pf = model.pipeline(hbs[0], depth=2, **call_kwargs)
-    for i in range(args.warmup):
-        pf.submit_device(packed_dev[i % n_bufs])
-    pf.join()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for i in range(args.steps):
-        pf.submit_device(packed_dev[i % n_bufs])
-    pf.join()
-    t1.record()
-    barrier()
-    clocks = sampler.stop()
-    elapsed_ms = t0.elapsed_time(t1)
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for i in range(args.steps):
-        cf.load_device(packed_dev[i % n_bufs])
-        cf.replay()
-    s1.record()
-    torch.cuda.synchronize()
-    serial_ms = s0.elapsed_time(s1) / args.steps
+    elapsed_ms, clocks = timed_replay(ctx, pf, packed_dev, steps, args.warmup)
+    serial_ms = timed_serial(cf, packed_dev, steps)
 
     # dominant kernel, one launch per CUDA-event pair
-    if args.workload == "twotower":
+    if kind == "twotower":
         D = 128
         q = torch.randn((B, D), device=dev)
         it = torch.randn((B, D), device=dev)
@@ -600,77 +773,40 @@ def secondary_arm(args, mm, datasets, ops, dev, rank, local_rank, world):
         algo = 2.0 * B * d * d
         roof = {"bound": "tensor", "kernel": "dense_tc_kernel<cross epilogue> (mm_dense_tc, one of the 3 cross layers)",
                 "unit": "TFLOP/s", "note": "algorithmic fp32 FLOPs; 3 bf16 passes are issued for fp32 parity (x3 tensor work)"}
-    for i in range(3):
-        dominant(i)
-    torch.cuda.synchronize()
-    kev = []
-    for i in range(max(5, args.steps // 2)):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dominant(i)
-        e1.record()
-        kev.append((e0, e1))
-    torch.cuda.synchronize()
-    kern_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in kev]))
+    kern_ms = event_times(dominant, max(5, steps // 2))
 
     # e2e: pinned packed host batch in, predictions (logits for the two-tower) out, pipelined
-    e2e_steps = max(5, min(args.steps, 20))
-
-    def e2e_loop(n):
-        tickets, res = [], None
-        for i in range(n):
-            tickets.append(pf.submit(hbs[i % n_bufs]))
-            if len(tickets) == 2:
-                res = pf.result(tickets.pop(0))
-        while tickets:
-            res = pf.result(tickets.pop(0))
-        return res
-
-    e2e_loop(3)
-    barrier()
-    w0 = time.perf_counter()
-    res = e2e_loop(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - w0) * 1e3
-    barrier()
-    if world > 1:
-        import torch.distributed as dist
-
-        t = torch.tensor([elapsed_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, kern_ms = (float(v) for v in t.tolist())
-    if rank == 0:
-        hbm, hbm_src = measured_peaks()
-        tf_peak = None
-        pth = ROOT / "MEASURED_PEAKS.json"
-        if pth.exists():
-            tf_peak = json.loads(pth.read_text()).get("bf16_tflops")
-        if roof["bound"] == "hbm":
-            achieved, peak, src = algo / (kern_ms * 1e-3) / 1e9, hbm, hbm_src
-        else:
-            achieved, peak, src = algo / (kern_ms * 1e-3) / 1e12, tf_peak or 1590.0, "measured (MEASURED_PEAKS.json)" if tf_peak else "fallback (B200_PROFILING.md)"
-        roof.update({"achieved": achieved, "peak": peak, "frac": achieved / peak, "peak_source": src, "kernel_ms": kern_ms,
-                     "algorithmic_per_launch": algo, "traffic": None})
-        print(json.dumps({
-            "metric": metric, "value": world * B * args.steps / (elapsed_ms * 1e-3), "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-            "data": f"synthetic ({law} indices; hash-initialised tables, random-init towers)",
-            "config": {"workload": label, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"replicas x{world} (no data-path collective)",
-                       "l2": f"{n_bufs} rotating input batches; tables and the (B,1+B) logits exceed L2",
-                       "runtime": "CUDA graph replay, 2 graph instances on 2 streams", "ms_per_step_single_stream": serial_ms},
-            "clocks": clocks,
-            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "samples/s",
-                    "h2d_bytes_per_step": int(hbs[0].payload_bytes()), "d2h_bytes_per_step": int(res.numel() * res.element_size()),
-                    "steps": e2e_steps},
-            "gpu_launches": cf.launches_per_replay * args.steps * world, "roofline": roof,
-        }))
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.destroy_process_group()
-    return 0
+    e2e_steps = max(5, min(steps, 20))
+    e2e_ms, res = timed_e2e(ctx, pf, hbs, e2e_steps, 2)
+    elapsed_ms, e2e_ms, kern_ms = ctx.max_over_ranks(elapsed_ms, e2e_ms, kern_ms)
+    hbm, hbm_src = measured_peaks()
+    tf_peak = None
+    pth = ROOT / "MEASURED_PEAKS.json"
+    if pth.exists():
+        tf_peak = json.loads(pth.read_text()).get("bf16_tflops")
+    if roof["bound"] == "hbm":
+        achieved, peak, src = algo / (kern_ms * 1e-3) / 1e9, hbm, hbm_src
+    else:
+        achieved, peak, src = algo / (kern_ms * 1e-3) / 1e12, tf_peak or 1590.0, "measured (MEASURED_PEAKS.json)" if tf_peak else "fallback (B200_PROFILING.md)"
+    roof.update({"achieved": achieved, "peak": peak, "frac": achieved / peak, "peak_source": src, "kernel_ms": kern_ms,
+                 "algorithmic_per_launch": algo, "traffic": None})
+    rec = {
+        "metric": metric, "value": world * B * steps / (elapsed_ms * 1e-3), "unit": "samples/s",
+        "ms_per_step": elapsed_ms / steps,
+        "dtype": "fp32 I/O; split-bf16 x3 GEMM work",
+        "data": f"synthetic ({law} indices; hash-initialised tables, random-init towers)",
+        "config": {"workload": label, "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"replicas x{world} (no data-path collective)",
+                   "l2": f"{n_bufs} rotating input batches; tables and the (B,1+B) logits exceed L2",
+                   "runtime": "CUDA graph replay, 2 graph instances on 2 streams", "ms_per_step_single_stream": serial_ms},
+        "clocks": clocks,
+        "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": int(hbs[0].payload_bytes()), "d2h_bytes_per_step": int(res.numel() * res.element_size()),
+                "steps": e2e_steps},
+        "gpu_launches": cf.launches_per_replay * steps * world, "roofline": roof,
+    }
+    del cf, pf, model
+    return rec
 
 
 def time_cpu_baseline(model, feats_host, sample_rows, cores, budget_s=20.0):

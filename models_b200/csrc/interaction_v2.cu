@@ -97,10 +97,20 @@ __device__ __forceinline__ void sts32(uint32_t addr, float v) {
 }
 
 struct RawIdx {
-  uint32_t a, b;
+  uint32_t a, b, sh;  // the aligned word(s) holding an id, and the bit offset of the id inside `a`
 };
 
-template <int MODE, int KD /* embedding dim: 16, 32, 64, 128 */, int NWARPS /* launch bound */>
+__device__ __forceinline__ void mma_bf16_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+
+// K8: issue the Gram matrix as m16n8k8 MMAs.  With k16 every bf16x2 register must sit both in an A quad
+// {X[g],X[g+8]} x {k-lo,k-hi} and in a B pair {k-lo,k-hi} of one row — two incompatible adjacencies, which
+// cost 180 register moves per sample (ncu, r2a).  k8 operands are an A pair and a single B register: no
+// moves, twice the (half-size) MMAs.
+template <int MODE, int KD /* embedding dim: 16, 32, 64, 128 */, int NWARPS /* launch bound */, bool K8>
 __global__ void __launch_bounds__(32 * NWARPS, 1)
 interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -119,51 +129,48 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
   const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)warp * (NBUF * p.buf_bytes);
 
   // ---- samples of this CTA: a contiguous range, interleaved over its warps (neighbouring warps read
-  // neighbouring ids: the 32-byte index sectors are shared through L1 instead of being fetched 8 times)
+  // neighbouring ids: the 32-byte index sectors are shared through L1 instead of being fetched 8 times).
+  // Every warp runs the SAME number of iterations (a function of blockIdx only, so the loop and the shuffles
+  // inside it are provably convergent); a warp whose last sample does not exist skips the work, not the loop.
   const long long begin = (long long)blockIdx.x * p.B / gridDim.x;
-  const long long end = (long long)(blockIdx.x + 1) * p.B / gridDim.x;
-  const long long first = begin + warp;
-  const long long n_mine = first < end ? (end - first + nw - 1) / nw : 0;
+  const int n_cta = (int)((long long)(blockIdx.x + 1) * p.B / gridDim.x - begin);
+  const int n_iter = (n_cta + nw - 1) / nw;
+  const long long s0 = begin + warp;  // first sample of this warp
 
   // ---- owner role: lane r owns staged row r (MODE 1: a table, or the bottom vector)
   const bool is_table = MODE == 1 && lane < p.rows && lane != p.bottom_slot;
-  const uint8_t* my_idx = is_table ? reinterpret_cast<const uint8_t*>(lk.indices[lane]) : nullptr;
   const float* my_base = is_table ? lk.weights[lane] : nullptr;
-  const long long my_rows = is_table ? lk.rows[lane] : 0;
+  const unsigned long long my_rows = is_table ? (unsigned long long)lk.rows[lane] : 0ull;
   const int my_w = is_table ? lk.idx_bytes[lane] : 4;
   const bool my_sharded = is_table && lk.sharded[lane];
+  const bool my_64 = my_w == 8;
+  const uint32_t my_mask = my_w >= 4 ? 0xffffffffu : (0xffffffffu >> (32 - 8 * my_w));
+  const uint8_t* id_ptr = is_table ? reinterpret_cast<const uint8_t*>(lk.indices[lane]) + (size_t)s0 * my_w : nullptr;
+  const int id_step = nw * my_w;
   const float* const* peers = reinterpret_cast<const float* const*>(smem_raw + p.peer_off);
   if (MODE == 1 && lk.world > 1) {  // peer shard pointers: kernel parameters -> shared memory (indexed by lane AND owner)
     float const** dst = reinterpret_cast<float const**>(smem_raw + p.peer_off);
     for (int i = threadIdx.x; i < p.rows * lk.world; i += blockDim.x) dst[i] = lk.peers[i];
     __syncthreads();
   }
+  // running source pointers of the non-table rows
+  const uint8_t* pfx_ptr = p.prefix ? reinterpret_cast<const uint8_t*>(p.prefix + s0 * p.prefix_stride) : nullptr;
+  const long long pfx_step = (long long)nw * p.prefix_stride * 4;
 
-  auto load_raw = [&](long long it) -> RawIdx {
-    RawIdx r{0u, 0u};
-    if (MODE == 1 && is_table && it < n_mine) {
-      const long long s = first + it * nw;
-      if (my_w == 4) {
-        r.a = __ldg(reinterpret_cast<const uint32_t*>(my_idx) + s);
-      } else if (my_w == 8) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(my_idx) + s);
-        r.a = v.x;
-        r.b = v.y;
-      } else {  // 1..3 bytes: the aligned word(s) holding the value
-        const uintptr_t a = reinterpret_cast<uintptr_t>(my_idx) + (uintptr_t)s * my_w;
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        r.a = __ldg(wp);
-        if ((int)(a & 3) + my_w > 4) r.b = __ldg(wp + 1);
-      }
+  // ids are fetched as the aligned 32-bit word(s) that contain them, one iteration before they are decoded
+  int k_load = warp;  // index (inside the CTA's range) of the sample whose id is loaded next
+  auto load_raw = [&]() -> RawIdx {
+    RawIdx r{0u, 0u, 0u};
+    if (MODE == 1 && is_table && k_load < n_cta) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(id_ptr);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+      r.sh = 8u * (uint32_t)(a & 3);
+      r.a = __ldg(wp);
+      if (my_64 || (int)(a & 3) + my_w > 4) r.b = __ldg(wp + 1);
     }
+    id_ptr += id_step;
+    k_load += nw;
     return r;
-  };
-  auto decode = [&](RawIdx r, long long s) -> long long {
-    if (my_w == 4) return (long long)(int)r.a;
-    if (my_w == 8) return (long long)(((unsigned long long)r.b << 32) | r.a);
-    const uintptr_t a = reinterpret_cast<uintptr_t>(my_idx) + (uintptr_t)s * my_w;
-    const uint32_t v = __funnelshift_r(r.a, r.b, 8u * (uint32_t)(a & 3));
-    return (long long)(v & (0xffffffffu >> (32 - 8 * my_w)));
   };
 
   // ---- copy-loop constants of this lane
@@ -171,37 +178,42 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
   const uint32_t src_lane_off = (uint32_t)cl * 16u;
   const uint32_t dst_lane_off =
       (uint32_t)rl * (D * 4) + (uint32_t)((SWZ ? (cl ^ ((rl & 1) << 2)) : cl) * 16);
+  const uint8_t* x_ptr = MODE == 0 ? reinterpret_cast<const uint8_t*>(p.x + s0 * p.x_stride) + (size_t)rl * (D * 4) + src_lane_off
+                                   : nullptr;
+  const long long x_step = (long long)nw * p.x_stride * 4;
 
-  auto issue = [&](long long it, RawIdx raw) {
-    // The shuffles run unconditionally (no divergent-branch handling around them); past the end of this
-    // warp's samples the row count is 0 and nothing is copied.
-    const int live_rows = it < n_mine ? p.rows : 0;
-    const long long s = first + it * nw;
-    const uint32_t xs = wbase + (uint32_t)(it & (NBUF - 1)) * p.buf_bytes + dst_lane_off;
+  int k_issue = warp;
+  uint32_t buf_issue = 0;  // byte offset (0 / buf_bytes) of the buffer the next sample is staged in
+  auto issue = [&](RawIdx raw) {
+    // The shuffles run unconditionally; past the end of this warp's samples the row count is 0 and nothing is copied.
+    const int live_rows = k_issue < n_cta ? p.rows : 0;
+    const uint32_t xs = wbase + buf_issue + dst_lane_off;
     if (MODE == 1) {
       const float* my_src = g_zero_row;
-      if (is_table && live_rows) {
-        const long long idx = decode(raw, s);
-        if (idx >= 0 && idx < my_rows) {
+      if (is_table) {
+        const uint32_t v = __funnelshift_r(raw.a, raw.b, raw.sh) & my_mask;
+        const uint32_t hi = my_64 ? raw.b : (uint32_t)((int)v >> 31);
+        const unsigned long long idx = ((unsigned long long)hi << 32) | v;
+        if (idx < my_rows) {  // unsigned: negative ids are out of range too
           if (my_sharded) {
-            long long lrow;
+            unsigned long long lrow;
             int owner;
             if (lk.log2_world >= 0) {
-              owner = (int)(idx & (lk.world - 1));
+              owner = (int)(idx & (unsigned)(lk.world - 1));
               lrow = idx >> lk.log2_world;
             } else {
-              lrow = idx / lk.world;
-              owner = (int)(idx - lrow * lk.world);
+              lrow = idx / (unsigned)lk.world;
+              owner = (int)(idx - lrow * (unsigned)lk.world);
             }
             my_src = peers[lane * lk.world + owner] + lrow * D;
           } else {
             my_src = my_base + idx * D;
           }
-        } else if (p.oob_count) {
+        } else if (live_rows && p.oob_count) {
           atomicAdd(p.oob_count, 1);
         }
-      } else if (lane == p.bottom_slot && live_rows) {
-        my_src = p.prefix + s * p.prefix_stride;
+      } else if (lane == p.bottom_slot) {
+        my_src = reinterpret_cast<const float*>(pfx_ptr);
       }
       const uint32_t src_lo = (uint32_t)(uintptr_t)my_src, src_hi = (uint32_t)((uintptr_t)my_src >> 32);
 #pragma unroll
@@ -217,19 +229,21 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
         }
       }
     } else {
-      const uint8_t* xrow = reinterpret_cast<const uint8_t*>(p.x + s * p.x_stride) + (size_t)rl * (D * 4) + src_lane_off;
-      const uint8_t* prow = reinterpret_cast<const uint8_t*>(p.prefix + s * p.prefix_stride) + src_lane_off;
 #pragma unroll
       for (int i = 0; i < IMAX; ++i) {
         if (i * R < p.rows) {
           const int row = i * R + rl;
-          const uint8_t* src = row < F ? xrow + (size_t)i * (R * D * 4) : prow;
+          const uint8_t* src = row < F ? x_ptr + (size_t)i * (R * D * 4) : pfx_ptr + src_lane_off;
           const bool on = row < live_rows;
 #pragma unroll
           for (int j = 0; j < J; ++j) cp_async16_if(on, xs + (uint32_t)(i * R * D * 4 + j * L * 16), src + j * L * 16);
         }
       }
+      x_ptr += x_step;
     }
+    pfx_ptr += pfx_step;
+    k_issue += nw;
+    buf_issue ^= p.buf_bytes;  // NBUF == 2 (buf_bytes is a power-of-two-free toggle: 0 <-> buf_bytes)
     cp_async_commit();  // one group per sample (empty past the end keeps the group count in step)
   };
 
@@ -259,114 +273,143 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
   const int OW = p.P + npairs;
   const int prow = MODE == 1 ? p.bottom_slot : F;  // staged row holding the prefix
   const uint32_t pfx_off = (uint32_t)prow * (D * 4) + (uint32_t)((SWZ ? (lane ^ ((prow & 1) << 2)) : lane) * 16);
+  // running output pointers
+  __nv_bfloat16* osplit = p.out_split ? p.out_split + s0 * (2ll * p.out_Kp) : nullptr;
+  float* of32 = p.out_f32 ? p.out_f32 + s0 * p.out_stride : nullptr;
+  const bool f32_vec = ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
 
   // ---- software pipeline: one sample in flight behind the one being computed; ids one iteration ahead
-  RawIdx raw_pref = load_raw(0);
+  RawIdx raw_pref = load_raw();
   {
     const RawIdx cur = raw_pref;
-    raw_pref = load_raw(1);
-    issue(0, cur);
+    raw_pref = load_raw();
+    issue(cur);
   }
-  for (long long it = 0; it < n_mine; ++it) {
+  int k_cmp = warp;
+  uint32_t buf_cmp = 0;
+  for (int it = 0; it < n_iter; ++it) {
     {
       const RawIdx cur = raw_pref;
-      raw_pref = load_raw(it + 2);
-      issue(it + 1, cur);  // refills the buffer consumed (and used as output stage) in the previous iteration
+      raw_pref = load_raw();
+      issue(cur);  // refills the buffer consumed (and used as output stage) in the previous iteration
     }
-    const long long s = first + it * nw;
-    const uint32_t xs = wbase + (uint32_t)(it & (NBUF - 1)) * p.buf_bytes;
+    const uint32_t xs = wbase + buf_cmp;
+    buf_cmp ^= p.buf_bytes;
     cp_async_wait<NBUF - 1>();
     __syncwarp();
+    if (k_cmp < n_cta) {
+      float acc[6][4];
+#pragma unroll
+      for (int ti = 0; ti < 6; ++ti)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[ti][c] = 0.0f;
 
-    float acc[6][4];
 #pragma unroll
-    for (int ti = 0; ti < 6; ++ti)
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t h[4][2], l[4][2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[ti][c] = 0.0f;
-
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = lds128(xs + ((ks & 1) ? po[q] : pe[q]) + 64u * ks);
+          split_pair(v.x, v.y, h[q][0], l[q][0]);
+          split_pair(v.z, v.w, h[q][1], l[q][1]);
+        }
+        // tile (mt, nt): A = rows q = 2mt, 2mt+1; B (n-tile nt = rows 8nt + g) = the registers of q = nt.
+        // Pass-major order: six independent accumulators between dependent MMAs.
+        if (K8) {
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      uint32_t h[4][2], l[4][2];
+          for (int kh = 0; kh < 2; ++kh) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = lds128(xs + ((ks & 1) ? po[q] : pe[q]) + 64u * ks);
-        split_pair(v.x, v.y, h[q][0], l[q][0]);
-        split_pair(v.z, v.w, h[q][1], l[q][1]);
+            for (int ti = 0; ti < 6; ++ti) {
+              const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+              mma_bf16_1688(acc[ti], h[2 * mt][kh], h[2 * mt + 1][kh], l[nt][kh]);
+            }
+#pragma unroll
+            for (int ti = 0; ti < 6; ++ti) {
+              const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+              mma_bf16_1688(acc[ti], l[2 * mt][kh], l[2 * mt + 1][kh], h[nt][kh]);
+            }
+#pragma unroll
+            for (int ti = 0; ti < 6; ++ti) {
+              const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+              mma_bf16_1688(acc[ti], h[2 * mt][kh], h[2 * mt + 1][kh], h[nt][kh]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int ti = 0; ti < 6; ++ti) {
+            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+            mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], l[nt][0], l[nt][1]);
+          }
+#pragma unroll
+          for (int ti = 0; ti < 6; ++ti) {
+            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+            mma_bf16_16816(acc[ti], l[2 * mt][0], l[2 * mt + 1][0], l[2 * mt][1], l[2 * mt + 1][1], h[nt][0], h[nt][1]);
+          }
+#pragma unroll
+          for (int ti = 0; ti < 6; ++ti) {
+            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+            mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], h[nt][0], h[nt][1]);
+          }
+        }
       }
-      // tile (mt, nt): A = rows q = 2mt, 2mt+1; B (n-tile nt = rows 8nt + g) = the registers of q = nt.
-      // Pass-major order: six independent accumulators between dependent MMAs.
+
+      // ---- the prefix row leaves the buffer before the buffer becomes the output stage
+      float4 pfx = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.P > 0 && lane < C) pfx = lds128(xs + pfx_off);
+      __syncwarp();  // every lane is done reading the sample
+      if (p.P > 0 && lane < C)
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(xs + lane * 16u), "f"(pfx.x), "f"(pfx.y), "f"(pfx.z),
+                     "f"(pfx.w)
+                     : "memory");
 #pragma unroll
       for (int ti = 0; ti < 6; ++ti) {
         const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-        mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], l[nt][0], l[nt][1]);
-      }
 #pragma unroll
-      for (int ti = 0; ti < 6; ++ti) {
-        const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-        mma_bf16_16816(acc[ti], l[2 * mt][0], l[2 * mt + 1][0], l[2 * mt][1], l[2 * mt + 1][1], h[nt][0], h[nt][1]);
+        for (int c = 0; c < 4; ++c) {
+          const int qi = 2 * mt + (c >> 1), e = c & 1;
+          if (qi > nt) continue;  // below the diagonal: never stored
+          bool ok = (8 * nt + e) < jlim;
+          if (qi == nt) ok = ok && (e ? dg1 : dg0);
+          if (ok) sts32(xs + (uint32_t)(rb[qi] + (8 * nt + e) * 4), acc[ti][c]);
+        }
       }
-#pragma unroll
-      for (int ti = 0; ti < 6; ++ti) {
-        const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-        mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], h[nt][0], h[nt][1]);
-      }
-    }
+      for (int e = OW + lane; e < (int)p.stage_cols; e += 32) sts32(xs + (uint32_t)e * 4u, 0.0f);  // zero padding
+      __syncwarp();
 
-    // ---- the prefix row leaves the buffer before the buffer becomes the output stage
-    float4 pfx = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.P > 0 && lane < C) pfx = lds128(xs + pfx_off);
-    __syncwarp();  // every lane is done reading the sample
-    if (p.P > 0 && lane < C)
-      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(xs + lane * 16u), "f"(pfx.x), "f"(pfx.y), "f"(pfx.z),
-                   "f"(pfx.w)
-                   : "memory");
-#pragma unroll
-    for (int ti = 0; ti < 6; ++ti) {
-      const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int qi = 2 * mt + (c >> 1), e = c & 1;
-        if (qi > nt) continue;  // below the diagonal: never stored
-        bool ok = (8 * nt + e) < jlim;
-        if (qi == nt) ok = ok && (e ? dg1 : dg0);
-        if (ok) sts32(xs + (uint32_t)(rb[qi] + (8 * nt + e) * 4), acc[ti][c]);
-      }
-    }
-    for (int e = OW + lane; e < (int)p.stage_cols; e += 32) sts32(xs + (uint32_t)e * 4u, 0.0f);  // zero padding
-    __syncwarp();
-
-    // ---- coalesced row store
-    if (p.out_split) {
-      __nv_bfloat16* drow = p.out_split + s * (2ll * p.out_Kp);
-      const int groups = p.out_Kp >> 3;  // 8 columns = one 16-byte bf16 store for hi and one for lo
-      for (int gi = lane; gi < groups; gi += 32) {
-        const float4 a = lds128(xs + (uint32_t)gi * 32u), b = lds128(xs + (uint32_t)gi * 32u + 16u);
-        uint32_t hh[4], ll[4];
-        split_pair(a.x, a.y, hh[0], ll[0]);
-        split_pair(a.z, a.w, hh[1], ll[1]);
-        split_pair(b.x, b.y, hh[2], ll[2]);
-        split_pair(b.z, b.w, hh[3], ll[3]);
-        *reinterpret_cast<uint4*>(drow + 8 * gi) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-        *reinterpret_cast<uint4*>(drow + p.out_Kp + 8 * gi) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-      }
-    } else {
-      float* dst = p.out_f32 + s * p.out_stride;
-      if (((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0)) {
-        const int n4 = OW >> 2;
-        for (int e = lane; e < n4; e += 32) reinterpret_cast<float4*>(dst)[e] = lds128(xs + (uint32_t)e * 16u);
-        for (int e = (n4 << 2) + lane; e < OW; e += 32) {
-          float v;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (uint32_t)e * 4u));
-          dst[e] = v;
+      // ---- coalesced row store
+      if (p.out_split) {
+        const int groups = p.out_Kp >> 3;  // 8 columns = one 16-byte bf16 store for hi and one for lo
+        for (int gi = lane; gi < groups; gi += 32) {
+          const float4 a = lds128(xs + (uint32_t)gi * 32u), b = lds128(xs + (uint32_t)gi * 32u + 16u);
+          uint32_t hh[4], ll[4];
+          split_pair(a.x, a.y, hh[0], ll[0]);
+          split_pair(a.z, a.w, hh[1], ll[1]);
+          split_pair(b.x, b.y, hh[2], ll[2]);
+          split_pair(b.z, b.w, hh[3], ll[3]);
+          *reinterpret_cast<uint4*>(osplit + 8 * gi) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(osplit + p.out_Kp + 8 * gi) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
         }
       } else {
-        for (int e = lane; e < OW; e += 32) {
-          float v;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (uint32_t)e * 4u));
-          dst[e] = v;
+        if (f32_vec) {
+          const int n4 = OW >> 2;
+          for (int e = lane; e < n4; e += 32) reinterpret_cast<float4*>(of32)[e] = lds128(xs + (uint32_t)e * 16u);
+          for (int e = (n4 << 2) + lane; e < OW; e += 32) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (uint32_t)e * 4u));
+            of32[e] = v;
+          }
+        } else {
+          for (int e = lane; e < OW; e += 32) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (uint32_t)e * 4u));
+            of32[e] = v;
+          }
         }
       }
     }
+    k_cmp += nw;
+    if (osplit) osplit += (long long)nw * 2 * p.out_Kp;
+    if (of32) of32 += (long long)nw * p.out_stride;
     __syncwarp();  // the buffer may be refilled by the next iteration's copies
   }
 }
@@ -376,9 +419,9 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int MODE, int KD, int NWARPS>
+template <int MODE, int KD, int NWARPS, bool K8>
 static int launch_kd(const LookupParams& lk, const Params& p, size_t smem, unsigned grid, cudaStream_t st, const char* who) {
-  auto kern = interact_v2_kernel<MODE, KD, NWARPS>;
+  auto kern = interact_v2_kernel<MODE, KD, NWARPS, K8>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -442,8 +485,14 @@ int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float
   const long long sms = sm_count();
   long long want = (B + warps - 1) / warps;
   const unsigned grid = (unsigned)(want < sms ? want : sms);
-#define MM_V2_LAUNCH(KD)                                                                 \
-  (warps > 12 ? launch_kd<MODE, KD, 16>(lk, p, smem, grid, st, who) : launch_kd<MODE, KD, 12>(lk, p, smem, grid, st, who))
+  static int k8_env = -2;
+  if (k8_env == -2) k8_env = env_int("MM_IMMA_K8", 0);
+  const bool k8 = k8_env != 0;
+#define MM_V2_LAUNCH(KD)                                                                                        \
+  (warps > 12 ? (k8 ? launch_kd<MODE, KD, 16, true>(lk, p, smem, grid, st, who)                                 \
+                    : launch_kd<MODE, KD, 16, false>(lk, p, smem, grid, st, who))                               \
+              : (k8 ? launch_kd<MODE, KD, 12, true>(lk, p, smem, grid, st, who)                                 \
+                    : launch_kd<MODE, KD, 12, false>(lk, p, smem, grid, st, who)))
   switch (D) {
     case 16: return MM_V2_LAUNCH(16);
     case 32: return MM_V2_LAUNCH(32);

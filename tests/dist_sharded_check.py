@@ -34,29 +34,46 @@ def main():
     full = make()
     full.build(dev)
     tables = {n: t.embeddings.clone() for n, t in full.body.embeddings.tables.items()}
-    sharded = mm.shard_model(make())
-    sharded.body.sharded.load_full_tables(tables, dev)
-    sharded.build(dev)
-    for name, t in tables.items():
-        assert torch.equal(sharded.body.sharded.shards[name], t[rank::world])
     ok = True
-    for step in range(3):
-        B = 512
-        b, _ = datasets.split_targets(schema, datasets.generate_batch(schema, B, seed=100 * rank + step, index_law="uniform"))
-        if step == 2:
-            b["C2"] = b["C2"].copy()
-            b["C2"][:] = b["C2"][0]  # skew: every sample hits the same row (one owner)
-        d = {k: torch.from_numpy(v).to(dev) for k, v in b.items()}
-        want = full(d)
-        got = sharded(d)
-        ok &= bool(torch.equal(want, got))
-        # stack bit-exactness
-        slots = sharded.body.slots()
-        stack = sharded.body.sharded.lookup_stack(d, slots, len(slots)).clone()
-        ref = torch.zeros_like(stack)
-        full.body.embeddings.lookup_all_into(d, ref, {f: slots[f] * 64 for f in full.body.embeddings.feature_names})
-        cols = [c for f in full.body.embeddings.feature_names for c in range(slots[f] * 64, slots[f] * 64 + 64)]
-        ok &= bool(torch.equal(stack[:, cols], ref[:, cols]))
+    # two placements: every table row-sharded; and big tables sharded + small tables replicated
+    for replicate_below in (0, 2000):
+        sharded = mm.shard_model(make(), replicate_below_rows=replicate_below)
+        se = sharded.body.sharded
+        se.load_full_tables(tables, dev)
+        sharded.build(dev)
+        for name, t in tables.items():
+            want_rows = t[rank::world] if se.is_sharded(name) else t
+            assert torch.equal(se.shards[name], want_rows), name
+        batches = []
+        for step in range(3):
+            B = 512
+            b, _ = datasets.split_targets(schema, datasets.generate_batch(schema, B, seed=100 * rank + step, index_law="uniform",
+                                                                          index_dtype=np.int32))
+            if step == 2:
+                b["C2"] = b["C2"].copy()
+                b["C2"][:] = b["C2"][0]  # skew: every sample hits the same row (one owner)
+            batches.append(b)
+            d = {k: torch.from_numpy(v).to(dev) for k, v in b.items()}
+            want = full(d)
+            got = sharded(d)  # product path: lookup over NVLink inside the interaction kernel
+            ok &= bool(torch.equal(want, got))
+            if replicate_below == 0:
+                # staged protocol (index all-gather + push + barrier): stack bit-exactness
+                slots = sharded.body.slots()
+                stack = se.lookup_stack(d, slots, len(slots)).clone()
+                ref = torch.zeros_like(stack)
+                full.body.embeddings.lookup_all_into(d, ref, {f: slots[f] * 64 for f in full.body.embeddings.feature_names})
+                cols = [c for f in full.body.embeddings.feature_names for c in range(slots[f] * 64, slots[f] * 64 + 64)]
+                ok &= bool(torch.equal(stack[:, cols], ref[:, cols]))
+        # the sharded forward captures into a CUDA graph like the replicated one (no collective inside);
+        # host batches with packed ids go through the same graph
+        hb = [mm.HostBatch.like(b, sharded.input_columns(), id_bytes=sharded.id_bytes()) for b in batches]
+        cf = sharded.compile(hb[0])
+        for i, b in enumerate(batches):
+            d = {k: torch.from_numpy(v).to(dev) for k, v in b.items()}
+            ok &= bool(torch.equal(cf(hb[i]).to(dev), full(d)))
+        dist.barrier()
+        del cf
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
