@@ -135,6 +135,18 @@ int mm_concat_split(const mm_concat_piece* pieces_host, int n_pieces, int64_t B,
 int mm_l2_normalize(const float* x, int64_t B, int D, int64_t x_stride, float* out,
                     int64_t out_stride, void* stream);
 
+/* BatchNormalization at inference (MLPBlock(normalization="batch_norm"), blocks/mlp.py:131-135; Keras epsilon 1e-3):
+ * out = x * scale + shift per column, scale = gamma / sqrt(moving_var + eps), shift = beta - moving_mean * scale.
+ * The host folds every normalization that is followed by a Dense into that Dense's kernel and bias; this entry
+ * point serves the one at the end of a block.  In place ok. */
+int mm_scale_shift(const float* x, int64_t B, int D, int64_t x_stride, const float* scale, const float* shift,
+                   float* out, int64_t out_stride, void* stream);
+
+/* DCN-v2 cross combine out = x0 * proj + x (blocks/cross.py:196-198) for projections that do not come out of a
+ * GEMM with the fused cross epilogue (CrossBlock(low_rank_dim=...) on the exact-fp32 engine). */
+int mm_cross_combine(const float* x0, const float* proj, const float* x, int64_t B, int D, int64_t x0_stride,
+                     int64_t proj_stride, int64_t x_stride, float* out, int64_t out_stride, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K6 (+K3)  Pairwise dot-product interaction.
  * Replaces tf.matmul(x, x, transpose_b=True) + band_part + boolean_mask

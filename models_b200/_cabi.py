@@ -75,6 +75,8 @@ SIGNATURES = {
     "mm_concat_columns": (_i, [C.POINTER(ConcatPiece), _i, _i64, _vp, _i64, _vp]),
     "mm_concat_split": (_i, [C.POINTER(ConcatPiece), _i, _i64, _vp, _i, _vp]),
     "mm_l2_normalize": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp]),
+    "mm_scale_shift": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "mm_cross_combine": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _i64, _vp, _i64, _vp]),
     "mm_dot_interaction": (_i, [_vp, _i64, _i, _i, _i64, _vp, _i, _i64, _i, _vp, _i64, _vp, _i, _vp]),
     "mm_dlrm_gather_interact": (_i, [_tables, _i, _i, _i64, _i, _vp, _i64, _i, _vp, _i64, _vp, _i, _vp, _vp]),
     "mm_dlrm_lookup_interact": (_i, [C.POINTER(LookupTable), _i, _i64, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i, _vp, _vp]),

@@ -143,9 +143,14 @@ class _Dense(Block):
     _TRANSIENT = {"_w_split": None, "_split_bufs": {}, "_bias_host": None}
 
     def _weights_changed(self) -> None:
-        """Variables were assigned (load_weights): drop everything derived from them."""
+        """Variables were assigned (load_weights): drop everything derived from them.  Captured CUDA graphs hold raw
+        pointers to the derived buffers (and the fused head's bias as a scalar argument): the bumped weights version
+        makes graph.CompiledForward re-capture before its next replay."""
+        from .core import bump_weights_version
+
         self._w_split = None
         self._bias_host = None
+        bump_weights_version()
 
     def split_kernel(self) -> torch.Tensor:
         """(Np, 2*Kp) split-bf16 K-major copy of the kernel for the tensor-core path (built once)."""
@@ -193,8 +198,7 @@ class _Dense(Block):
             raise ValueError(f"{self.name}: kernel has {self.kernel.shape[1]} columns, expected {self.units}")
         self.bias = None if bias is None else torch.as_tensor(bias, dtype=torch.float32).to(dev).contiguous()
         self.use_bias = bias is not None
-        self._w_split = None
-        self._bias_host = None
+        self._weights_changed()
         self.built = True
 
     def weights(self):
@@ -220,8 +224,70 @@ class _Dense(Block):
         return ops.dense_fp32(x, self.kernel, self.bias, self.activation, out, x0=x0)
 
 
+class BatchNormalization(Block):
+    """tf.keras.layers.BatchNormalization as MLPBlock(normalization="batch_norm") appends it after every Dense
+    (blocks/mlp.py:131-135), INFERENCE semantics: y = (x - moving_mean) / sqrt(moving_var + eps) * gamma + beta,
+    eps = 1e-3, fresh variables gamma = 1, beta = 0, moving_mean = 0, moving_var = 1.  On the forward path it never
+    runs as a layer of its own when a Dense follows: MLP.chain() folds it into that Dense's kernel and bias."""
+
+    def __init__(self, axis: int = -1, momentum: float = 0.99, epsilon: float = 1e-3, center: bool = True, scale: bool = True,
+                 name: Optional[str] = None, **kwargs):
+        super().__init__(name or unique_name("batch_normalization"))
+        if axis not in (-1, 1):
+            raise ValueError("BatchNormalization: only the feature axis (-1) is supported")
+        self.epsilon, self.momentum, self.center, self.scale = float(epsilon), float(momentum), center, scale
+        self.gamma = self.beta = self.moving_mean = self.moving_variance = None
+        self._st = None
+
+    _TRANSIENT = {"_st": None}
+
+    def build(self, width: Optional[int] = None, device=None) -> "BatchNormalization":
+        if self.gamma is None:
+            if width is None:
+                raise ValueError(f"{self.name}: cannot build without the input width")
+            device = device or default_device()
+            self.gamma = torch.ones(width, dtype=torch.float32, device=device)
+            self.beta = torch.zeros(width, dtype=torch.float32, device=device)
+            self.moving_mean = torch.zeros(width, dtype=torch.float32, device=device)
+            self.moving_variance = torch.ones(width, dtype=torch.float32, device=device)
+        self.built = True
+        return self
+
+    def set_weights(self, gamma=None, beta=None, moving_mean=None, moving_variance=None) -> None:
+        dev = default_device()
+        for name, v in (("gamma", gamma), ("beta", beta), ("moving_mean", moving_mean), ("moving_variance", moving_variance)):
+            if v is not None:
+                setattr(self, name, torch.as_tensor(v, dtype=torch.float32).to(dev).contiguous())
+        self._weights_changed()
+        self.built = True
+
+    def _weights_changed(self) -> None:
+        from .core import bump_weights_version
+
+        self._st = None
+        bump_weights_version()
+
+    def weights(self):
+        return {"gamma": self.gamma, "beta": self.beta, "moving_mean": self.moving_mean, "moving_variance": self.moving_variance}
+
+    def scale_shift(self):
+        """(scale, shift) with y = x * scale + shift (set-up time torch arithmetic, cached)."""
+        if self._st is None:
+            s = self.gamma / torch.sqrt(self.moving_variance + self.epsilon)
+            self._st = (s.contiguous(), (self.beta - self.moving_mean * s).contiguous())
+        return self._st
+
+    def call(self, inputs, training: bool = False, **kwargs):
+        if training:
+            raise NotImplementedError("BatchNormalization with batch statistics (training=True) is outside the forward hot path")
+        self.build(inputs.shape[1], inputs.device)
+        s, t = self.scale_shift()
+        return ops.scale_shift(inputs, s, t)
+
+
 class MLP(SequentialBlock):
-    """The SequentialBlock MLPBlock() returns; `.layers` are the _Dense layers."""
+    """The SequentialBlock MLPBlock() returns; `.layers` are the _Dense layers (each optionally followed by a
+    BatchNormalization, blocks/mlp.py:108-135; dropout is identity at inference and is not a layer here)."""
 
     def __init__(self, layers: Sequence[_Dense], filter_names: Optional[List[str]] = None, block_name: str = "MLPBlock",
                  dropout: Optional[float] = None):
@@ -234,16 +300,63 @@ class MLP(SequentialBlock):
         return [l for l in self.layers if isinstance(l, _Dense)]
 
     def build_from_width(self, width: int, device=None) -> "MLP":
-        for l in self.dense_layers:
-            l.build(width, device)
-            width = l.units
+        for l in self.layers:
+            if isinstance(l, _Dense):
+                l.build(width, device)
+                width = l.units
+            elif isinstance(l, BatchNormalization):
+                l.build(width, device)
         self.built = True
         return self
+
+    @property
+    def has_normalization(self) -> bool:
+        return any(isinstance(l, BatchNormalization) for l in self.layers)
+
+    def chain(self, extra: Sequence[_Dense] = ()):
+        """(dense layers to run, trailing normalization or None) for this block followed by the Dense layers `extra`
+        (e.g. the output head).  Every BatchNormalization that is followed by a Dense is folded into it:
+        (x * s + t) W + b = x (diag(s) W) + (b + t W) — the folded layers are cached shadow _Dense objects, rebuilt when
+        any variable is reassigned.  The block must be built."""
+        if not self.has_normalization:
+            return self.dense_layers + list(extra), None
+        from .core import weights_version
+
+        key = (weights_version(), tuple(id(e) for e in extra))
+        if getattr(self, "_chain_key", None) == key:
+            return self._chain
+        out, pending = [], None
+        for l in list(self.layers) + list(extra):
+            if isinstance(l, BatchNormalization):
+                if pending is not None:
+                    raise NotImplementedError("two normalizations in a row")
+                pending = l
+            elif isinstance(l, _Dense):
+                if pending is None:
+                    out.append(l)
+                    continue
+                if l.kernel is None or pending.gamma is None:
+                    raise RuntimeError("MLP.chain(): build the block first")
+                s, t = pending.scale_shift()
+                f = _Dense(l.units, activation=l.activation, use_bias=True, name=f"{l.name}/folded_bn")
+                # assigned directly: a derived layer is not a variable assignment (no weights-version bump)
+                f.kernel = (s.unsqueeze(1) * l.kernel).contiguous()
+                f.bias = (t @ l.kernel if l.bias is None else l.bias + t @ l.kernel).contiguous()
+                f.input_dim, f.built = l.kernel.shape[0], True
+                out.append(f)
+                pending = None
+        self._chain, self._chain_key = (out, pending), key
+        return self._chain
+
+    _TRANSIENT = {"_chain": None, "_chain_key": None}
 
     def call(self, inputs, training: bool = False, **kwargs):
         if self.dropout and training:
             raise NotImplementedError("dropout in training mode is outside the forward hot path")
+        if self.has_normalization and training:
+            raise NotImplementedError("BatchNormalization with batch statistics (training=True) is outside the forward hot path")
         x = inputs
+        a = K = None
         if isinstance(x, dict):
             if self.filter_names is not None:
                 x = {k: v for k, v in x.items() if k in self.filter_names}
@@ -251,9 +364,14 @@ class MLP(SequentialBlock):
             if _use_tc() and ops.concat_split_supported(pieces) and batch_size_of(x) > 0:
                 # ConcatFeatures straight into the split-bf16 operand of the first tensor-core layer
                 a, K = ops.concat_split(pieces)
-                return run_dense_chain(None, self.dense_layers, a_split=a, K=K)
-            x = concat_sorted(x)
-        return run_dense_chain(x, self.dense_layers)
+                x = None
+            else:
+                x = concat_sorted(x)
+        width = K if x is None else x.shape[1]
+        self.build_from_width(width, a.device if x is None else x.device)
+        layers, tail = self.chain()
+        out = run_dense_chain(x, layers, a_split=a, K=K) if x is None else run_dense_chain(x, layers)
+        return out if tail is None else tail(out)
 
     def oracle_layers(self):
         return [{"kernel": l.kernel.cpu().numpy(), "bias": None if l.bias is None else l.bias.cpu().numpy(),
@@ -267,14 +385,15 @@ def MLPBlock(dimensions: List[int], activation: Union[str, List[str]] = "relu", 
              no_activation_last_layer: bool = False, block_name: str = "MLPBlock", **kwargs) -> MLP:
     """blocks/mlp.py:35-139.  Activation is applied on every layer including the last unless
     `no_activation_last_layer` (:99-106).  Regularizers only matter for training and are accepted
-    and ignored; `normalization` (BatchNorm) is not on the forward hot path."""
+    and ignored.  `normalization="batch_norm"` (or a BatchNormalization instance, deep-copied per layer) follows every
+    Dense as in the reference (:131-135); at inference it is folded into the next Dense."""
     if isinstance(activation, list) and len(activation) != len(dimensions):
         raise ValueError(
             f"Activation and Dimensions length mismatch. \
         Activation length: {len(activation)}, Dimensions length: {len(dimensions)}"
         )
-    if normalization is not None:
-        raise NotImplementedError("MLPBlock(normalization=...) is outside the B200 hot path (see DESIGN.md)")
+    if normalization is not None and normalization != "batch_norm" and not isinstance(normalization, BatchNormalization):
+        raise ValueError("Normalization needs to be an instance `Layer` or " "`batch_norm`")
     layers = []
     for idx, dim in enumerate(dimensions):
         act = activation or "linear"
@@ -283,6 +402,10 @@ def MLPBlock(dimensions: List[int], activation: Union[str, List[str]] = "relu", 
             act_i = "linear"
         layers.append(_Dense(dim, activation=act_i, use_bias=use_bias, kernel_initializer=kernel_initializer,
                              bias_initializer=bias_initializer))
+        if normalization == "batch_norm":
+            layers.append(BatchNormalization())
+        elif normalization is not None:
+            layers.append(BatchNormalization(epsilon=normalization.epsilon, momentum=normalization.momentum))
     names = None
     if filter is not None:
         if isinstance(filter, Schema):
@@ -369,16 +492,29 @@ class Cross(Block):
         if self.dense_u is None:
             out = self.dense(x, x0=x0)  # fused epilogue x0 * (xW + b) + x
         else:
-            u = self.dense_u(x)
-            proj = torch.empty_like(x)
-            # low rank: the fused cross epilogue needs a square kernel, so run V with the cross
-            # epilogue reading x as the residual: out = x0 * (u V + b) + x  (K = r, N = d)
-            out = _cross_lowrank(u, self.dense, x0, x, proj)
+            out = _cross_lowrank(self.dense_u, self.dense, x0, x)
         return (x0, out) if self.output_x0 else out
 
 
-def _cross_lowrank(u, dense: _Dense, x0, x, out):
-    raise NotImplementedError("CrossBlock(low_rank_dim=...) is not implemented on the B200 path yet")
+def _cross_lowrank(dense_u: _Dense, dense: _Dense, x0, x):
+    """DenseMaybeLowRank (blocks/mlp.py:389-396): projection = dense(dense_u(x)) with dense_u (d -> r, no bias) and
+    dense (r -> d, bias); then the cross x0 * projection + x (blocks/cross.py:196-198).  Two GEMMs: U emits the
+    split-bf16 operand of V directly, V runs with the cross epilogue (K = r, N = d)."""
+    B, d = x.shape
+    out = torch.empty((B, d), dtype=torch.float32, device=x.device)
+    if not _use_tc():
+        u = ops.dense_fp32(x, dense_u.kernel, None, dense_u.activation, torch.empty((B, dense_u.units), dtype=torch.float32, device=x.device))
+        proj = ops.dense_fp32(u, dense.kernel, dense.bias, dense.activation, torch.empty_like(x))
+        return ops.cross_combine(x0, proj, x, out)
+    r = dense_u.units
+    ubuf = dense_u.split_buffer(B, x.device)
+    ops.dense_tc(ops.split_rows(x), d, dense_u.split_kernel(), r, None, dense_u.activation, out_split=ubuf)
+    if dense.activation == "linear":
+        ops.dense_tc(ubuf, r, dense.split_kernel(), d, dense.bias, "linear", out_f32=out, x0=x0, xres=x)
+        return out
+    proj = torch.empty_like(x)
+    ops.dense_tc(ubuf, r, dense.split_kernel(), d, dense.bias, dense.activation, out_f32=proj)
+    return ops.cross_combine(x0, proj, x, out)
 
 
 class CrossBlockSeq(SequentialBlock):

@@ -43,6 +43,20 @@ _BUFFER_NS = [0]
 _NEXT_NS = itertools.count(1)
 
 
+_WEIGHTS_VERSION = [0]
+
+
+def weights_version() -> int:
+    """Bumped whenever a variable is reassigned (load_weights / set_weights).  Derived state — BatchNorm-folded
+    layers, captured CUDA graphs (graph.CompiledForward re-captures when it changes) — is keyed by it."""
+    return _WEIGHTS_VERSION[0]
+
+
+def bump_weights_version() -> int:
+    _WEIGHTS_VERSION[0] += 1
+    return _WEIGHTS_VERSION[0]
+
+
 def buffer_namespace() -> int:
     return _BUFFER_NS[0]
 

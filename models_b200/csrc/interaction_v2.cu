@@ -55,6 +55,7 @@ struct Params {
   unsigned buf_bytes;   // one sample buffer (>= rows*D*4 and >= the staged output row)
   unsigned stage_cols;  // floats of the staged output row (out_Kp, or OW rounded up to 4)
   unsigned peer_off;    // byte offset of the peer pointer table in shared memory
+  unsigned ids_off;     // byte offset of the per-warp id rings (NBUF > 2)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,15 +107,20 @@ __device__ __forceinline__ void mma_bf16_1688(float (&c)[4], uint32_t a0, uint32
       : "r"(a0), "r"(a1), "r"(b0));
 }
 
-// K8: issue the Gram matrix as m16n8k8 MMAs.  With k16 every bf16x2 register must sit both in an A quad
-// {X[g],X[g+8]} x {k-lo,k-hi} and in a B pair {k-lo,k-hi} of one row — two incompatible adjacencies, which
-// cost 180 register moves per sample (ncu, r2a).  k8 operands are an A pair and a single B register: no
-// moves, twice the (half-size) MMAs.
-template <int MODE, int KD /* embedding dim: 16, 32, 64, 128 */, int NWARPS /* launch bound */, bool K8>
+// K8 (negative result, not instantiated): issue the Gram matrix as m16n8k8 MMAs.  With k16 every bf16x2
+// register must sit both in an A quad {X[g],X[g+8]} x {k-lo,k-hi} and in a B pair {k-lo,k-hi} of one row —
+// two incompatible adjacencies that cost ~180 register moves per sample (ncu, r2a).  k8 operands are an A
+// pair and a single B register: no moves, but twice as many MMAs, and HMMA.1688 occupies the legacy tensor
+// pipe as long as HMMA.16816 (8 cycles): 0.128 ms instead of 0.103 ms (profiles/r02_notes.md).
+// NBUF sample buffers per warp: NBUF-1 samples in flight behind the one being computed.  The product uses 2 with
+// 16 warps, for local tables and for rows that come over NVLink alike.  NBUF = 3 / 4 (10 / 7 warps, ids through a
+// shared-memory ring) exist for experiments (MM_IMMA_NBUF): measured on 2 x B200 they are never faster — what looked
+// like remote latency was hot rows of tiny sharded tables serialising on single cache lines of the owner
+// (profiles/r02_notes.md §b); with those tables replicated, 16 warps x 1 sample in flight reach 420-580 GB/s.
+template <int MODE, int KD /* embedding dim: 16, 32, 64, 128 */, int NWARPS /* launch bound */, bool K8, int NBUF>
 __global__ void __launch_bounds__(32 * NWARPS, 1)
 interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  constexpr int NBUF = 2;
   constexpr int D = KD, KS = KD / 16;
   constexpr int C = KD / 4;           // 16-byte chunks per row
   constexpr int L = C < 8 ? C : 8;    // lanes per row in the copy loop
@@ -170,6 +176,40 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
     }
     id_ptr += id_step;
     k_load += nw;
+    return r;
+  };
+
+  // ---- NBUF > 2 (rows over NVLink): ids travel through a per-warp shared-memory ring instead of registers.
+  // A register prefetch one sample ahead is useless here: the id load queues in the memory pipeline behind
+  // the row copies issued just before it and returns only after THEIR 10-20 us NVLink round trip, so every
+  // sample would wait for the previous one (ncu, r2h: 49 % of the stall samples sat on the id decode).  Instead
+  // the ids of sample j are copied (cp.async, 4-byte words) A = 2*NBUF-1 iterations before their rows are issued;
+  // they ride in the same commit groups as the rows, so `wait_group` orders everything and no extra wait exists.
+  constexpr bool IDS = NBUF > 2;
+  constexpr int A = 2 * NBUF - 1, SLOTS = NBUF + 1;
+  const uint32_t ring = smem_u32(smem_raw) + p.ids_off + (uint32_t)warp * (SLOTS * 256) + (uint32_t)lane * 8u;
+  uint32_t slot_w = 0, slot_r = 0;  // byte offsets of the ring slots written / read next
+  const uint8_t* idr_ptr = id_ptr;  // address of the id whose rows are issued next (bit offset inside its word)
+  auto submit_ids = [&]() {
+    if (MODE == 1 && is_table && k_load < n_cta) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(id_ptr);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring + slot_w), "l"(wp) : "memory");
+      if (my_64 || (int)(a & 3) + my_w > 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring + slot_w + 4u), "l"(wp + 1) : "memory");
+    }
+    id_ptr += id_step;
+    k_load += nw;
+    slot_w += 256u;
+    if (slot_w == SLOTS * 256u) slot_w = 0;
+  };
+  auto read_ids = [&]() -> RawIdx {
+    RawIdx r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.a), "=r"(r.b) : "r"(ring + slot_r));
+    r.sh = 8u * (uint32_t)(reinterpret_cast<uintptr_t>(idr_ptr) & 3);
+    idr_ptr += id_step;
+    slot_r += 256u;
+    if (slot_r == SLOTS * 256u) slot_r = 0;
     return r;
   };
 
@@ -243,7 +283,8 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
     }
     pfx_ptr += pfx_step;
     k_issue += nw;
-    buf_issue ^= p.buf_bytes;  // NBUF == 2 (buf_bytes is a power-of-two-free toggle: 0 <-> buf_bytes)
+    buf_issue += p.buf_bytes;
+    if (buf_issue == NBUF * p.buf_bytes) buf_issue = 0;
     cp_async_commit();  // one group per sample (empty past the end keeps the group count in step)
   };
 
@@ -278,25 +319,37 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
   float* of32 = p.out_f32 ? p.out_f32 + s0 * p.out_stride : nullptr;
   const bool f32_vec = ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
 
-  // ---- software pipeline: one sample in flight behind the one being computed; ids one iteration ahead
-  RawIdx raw_pref = load_raw();
-  {
-    const RawIdx cur = raw_pref;
+  // ---- software pipeline: NBUF-1 samples in flight behind the one being computed.
+  // registers (NBUF == 2): ids one iteration ahead of their rows; ring (NBUF > 2): iteration `it` submits the ids
+  // of sample it+A, issues the rows of sample it+NBUF-1, computes sample it — the first A iterations only fill.
+  RawIdx raw_pref{0u, 0u, 0u};
+  if (!IDS) {
     raw_pref = load_raw();
-    issue(cur);
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; ++i) {
+      const RawIdx cur = raw_pref;
+      raw_pref = load_raw();
+      issue(cur);
+    }
   }
   int k_cmp = warp;
   uint32_t buf_cmp = 0;
-  for (int it = 0; it < n_iter; ++it) {
-    {
+  for (int it = IDS ? -A : 0; it < n_iter; ++it) {
+    if (IDS) {
+      submit_ids();
+      if (it + NBUF - 1 >= 0) issue(read_ids());
+      else cp_async_commit();
+    } else {
       const RawIdx cur = raw_pref;
       raw_pref = load_raw();
       issue(cur);  // refills the buffer consumed (and used as output stage) in the previous iteration
     }
-    const uint32_t xs = wbase + buf_cmp;
-    buf_cmp ^= p.buf_bytes;
     cp_async_wait<NBUF - 1>();
     __syncwarp();
+    if (IDS && it < 0) continue;
+    const uint32_t xs = wbase + buf_cmp;
+    buf_cmp += p.buf_bytes;
+    if (buf_cmp == NBUF * p.buf_bytes) buf_cmp = 0;
     if (k_cmp < n_cta) {
       float acc[6][4];
 #pragma unroll
@@ -419,17 +472,19 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int MODE, int KD, int NWARPS, bool K8>
+template <int MODE, int KD, int NWARPS, bool K8, int NBUF>
 static int launch_kd(const LookupParams& lk, const Params& p, size_t smem, unsigned grid, cudaStream_t st, const char* who) {
-  auto kern = interact_v2_kernel<MODE, KD, NWARPS, K8>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  auto kern = interact_v2_kernel<MODE, KD, NWARPS, K8, NBUF>;
+  static bool attr_set[64] = {};  // per device: function attributes belong to the device's copy of the kernel
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(e));
       return (int)e;
     }
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   kern<<<grid, 32 * p.n_warps, smem, st>>>(lk, p);
   return check_launch(who);
@@ -469,30 +524,38 @@ int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float
   p.stage_cols = out_split ? (unsigned)out_Kp : (unsigned)((OW + 3) & ~3);
   const unsigned in_bytes = (unsigned)(rows * D * 4), stage_bytes = p.stage_cols * 4u;
   p.buf_bytes = ((in_bytes > stage_bytes ? in_bytes : stage_bytes) + 127u) & ~127u;
-  const unsigned per_warp = 2u * p.buf_bytes;
+  bool remote = false;
+  if (MODE == 1 && lk.world > 1)
+    for (int r = 0; r < rows; ++r) remote = remote || lk.sharded[r];
+  static int nbuf_env = -2;
+  if (nbuf_env == -2) nbuf_env = env_int("MM_IMMA_NBUF", 0);
+  const int nbuf = (nbuf_env >= 2 && nbuf_env <= 4) ? nbuf_env : 2;
+  (void)remote;
+  const unsigned ring_bytes = nbuf > 2 ? (unsigned)(nbuf + 1) * 256u : 0u;  // per-warp id ring
+  const unsigned per_warp = (unsigned)nbuf * p.buf_bytes + ring_bytes;
   const unsigned peer_bytes = (MODE == 1 && lk.world > 1) ? (unsigned)(rows * lk.world * 8) : 0u;
   const unsigned budget = 227u * 1024u - peer_bytes;
   static int warps_env = -2;
   if (warps_env == -2) warps_env = env_int("MM_IMMA_WARPS", 0);
-  const int want_warps = warps_env > 0 ? warps_env : 16;
+  const int want_warps = warps_env > 0 ? warps_env : (nbuf == 4 ? 8 : nbuf == 3 ? 10 : 16);
   int warps = (int)(budget / per_warp);
   if (warps > want_warps) warps = want_warps;
   if (warps > 16) warps = 16;
+  if (nbuf > 2 && warps > 12) warps = 12;
   if (warps < 2) return MM_ERR_UNSUPPORTED;
   p.n_warps = warps;
+  p.ids_off = (unsigned)warps * nbuf * p.buf_bytes;
   p.peer_off = (unsigned)warps * per_warp;
   const size_t smem = (size_t)p.peer_off + peer_bytes;
   const long long sms = sm_count();
   long long want = (B + warps - 1) / warps;
   const unsigned grid = (unsigned)(want < sms ? want : sms);
-  static int k8_env = -2;
-  if (k8_env == -2) k8_env = env_int("MM_IMMA_K8", 0);
-  const bool k8 = k8_env != 0;
-#define MM_V2_LAUNCH(KD)                                                                                        \
-  (warps > 12 ? (k8 ? launch_kd<MODE, KD, 16, true>(lk, p, smem, grid, st, who)                                 \
-                    : launch_kd<MODE, KD, 16, false>(lk, p, smem, grid, st, who))                               \
-              : (k8 ? launch_kd<MODE, KD, 12, true>(lk, p, smem, grid, st, who)                                 \
-                    : launch_kd<MODE, KD, 12, false>(lk, p, smem, grid, st, who)))
+  // instantiated variants: local tables = 16 (or 12) warps x 2 buffers; NVLink rows = 12-warp bound x 4 buffers
+#define MM_V2_LAUNCH(KD)                                                                                   \
+  (nbuf == 4 ? launch_kd<MODE, KD, 12, false, 4>(lk, p, smem, grid, st, who)                               \
+   : nbuf == 3 ? launch_kd<MODE, KD, 12, false, 3>(lk, p, smem, grid, st, who)                             \
+             : (warps > 12 ? launch_kd<MODE, KD, 16, false, 2>(lk, p, smem, grid, st, who)                 \
+                           : launch_kd<MODE, KD, 12, false, 2>(lk, p, smem, grid, st, who)))
   switch (D) {
     case 16: return MM_V2_LAUNCH(16);
     case 32: return MM_V2_LAUNCH(32);

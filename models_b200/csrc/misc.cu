@@ -120,6 +120,34 @@ __global__ void l2_normalize_kernel(const float* __restrict__ x, long long B, in
   }
 }
 
+
+// out[b, c] = x[b, c] * scale[c] + shift[c]: tf.keras.layers.BatchNormalization at inference with
+// scale = gamma / sqrt(moving_var + eps), shift = beta - moving_mean * scale (blocks/mlp.py:131-135).
+// Only the LAST normalization of a block reaches this kernel; the others are folded into the next Dense.
+__global__ void scale_shift_kernel(const float* __restrict__ x, long long B, int D, long long x_stride,
+                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                   float* __restrict__ out, long long out_stride) {
+  const long long total = B * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / D;
+    const int c = (int)(i - b * D);
+    out[b * out_stride + c] = fmaf(x[b * x_stride + c], scale[c], shift[c]);
+  }
+}
+
+
+// out = a * b + c elementwise over (B, D) row-major views (the DCN-v2 cross combine x0 * projection + x when the
+// projection is not produced by a GEMM with the fused cross epilogue: low-rank kernels on the exact-fp32 engine)
+__global__ void fma3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                            long long B, int D, long long sa, long long sb, long long sc, float* __restrict__ out, long long so) {
+  const long long total = B * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D;
+    const int k = (int)(i - r * D);
+    out[r * so + k] = fmaf(a[r * sa + k], b[r * sb + k], c[r * sc + k]);
+  }
+}
+
 }  // namespace mm
 
 extern "C" {
@@ -193,6 +221,34 @@ int mm_l2_normalize(const float* x, int64_t B, int D, int64_t x_stride, float* o
   mm::l2_normalize_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(x, B, D, x_stride, out,
                                                                                 out_stride);
   return mm::check_launch("mm_l2_normalize");
+}
+
+int mm_scale_shift(const float* x, int64_t B, int D, int64_t x_stride, const float* scale, const float* shift,
+                   float* out, int64_t out_stride, void* stream) {
+  MM_REQUIRE(x && out && scale && shift && B >= 0 && D > 0 && x_stride >= D && out_stride >= D, MM_ERR_ARG,
+             "mm_scale_shift: null pointer, D<=0 or stride < D");
+  if (B == 0) return MM_OK;
+  const int threads = 256;
+  long long blocks = (B * D + threads - 1) / threads;
+  const long long cap = (long long)mm::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  mm::scale_shift_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(x, B, D, x_stride, scale, shift, out,
+                                                                               out_stride);
+  return mm::check_launch("mm_scale_shift");
+}
+
+int mm_cross_combine(const float* x0, const float* proj, const float* x, int64_t B, int D, int64_t x0_stride,
+                     int64_t proj_stride, int64_t x_stride, float* out, int64_t out_stride, void* stream) {
+  MM_REQUIRE(x0 && proj && x && out && B >= 0 && D > 0 && x0_stride >= D && proj_stride >= D && x_stride >= D && out_stride >= D,
+             MM_ERR_ARG, "mm_cross_combine: null pointer, D<=0 or stride < D");
+  if (B == 0) return MM_OK;
+  const int threads = 256;
+  long long blocks = (B * D + threads - 1) / threads;
+  const long long cap = (long long)mm::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  mm::fma3_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(x0, proj, x, B, D, x0_stride, proj_stride, x_stride, out,
+                                                                        out_stride);
+  return mm::check_launch("mm_cross_combine");
 }
 
 }  // extern "C"

@@ -97,8 +97,22 @@ class CompiledForward:
         self.inputs = {name: _view(self.dev_buffer, example.offsets[name], shp, dt) for name, (shp, dt) in self.spec.items()}
         self.dev_buffer.copy_(example.buffer, non_blocking=True)
         self._oob = model.index_error_counter(self.device)
-        model.defer_index_check(True)
         self.namespace = new_buffer_namespace()  # private scratch buffers: graphs may run concurrently
+        self._capture()
+        self.output_host = torch.empty(self.output.shape, dtype=self.output.dtype, pin_memory=True)
+        self._oob_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        self.check_indices(sync=True)
+
+    def _capture(self) -> None:
+        """Warm-up + capture over the static buffers.  Runs at construction and again whenever a model variable was
+        reassigned since the last capture (core.weights_version): the graph holds raw pointers to derived buffers
+        (split-bf16 kernels, folded layers) and scalar arguments (the fused head's bias) that a reassignment frees or
+        changes, so replaying the old graph would read stale or freed memory."""
+        from . import ops
+        from .core import weights_version
+
+        model = self.model
+        model.defer_index_check(True)
         old_ns = set_buffer_namespace(self.namespace)
         try:
             # warm-up on a side stream (builds weights, split kernels, zeroed operand buffers, smem
@@ -110,20 +124,25 @@ class CompiledForward:
                     self._run()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            from . import ops
-
             self.graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
             with torch.cuda.graph(self.graph):
                 out = self._run()
             self.launches_per_replay = ops.launch_count() - n0  # kernels of libmm_b200.so inside the graph
+            if getattr(self, "output", None) is not None and (out.shape != self.output.shape or out.dtype != self.output.dtype):
+                raise RuntimeError("re-capture changed the output layout")
             self.output = out
+            self._wv = weights_version()
         finally:
             model.defer_index_check(False)
             set_buffer_namespace(old_ns)
-        self.output_host = torch.empty(self.output.shape, dtype=self.output.dtype, pin_memory=True)
-        self._oob_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
-        self.check_indices(sync=True)
+
+    def _ensure_current(self) -> None:
+        from .core import weights_version
+
+        if weights_version() != self._wv:
+            torch.cuda.synchronize()
+            self._capture()
 
     def _run(self) -> torch.Tensor:
         out = self.model(self.inputs, **self.call_kwargs)
@@ -143,6 +162,7 @@ class CompiledForward:
 
     # ---- device-resident inputs: copy into the static buffer and replay ---------------------------
     def replay(self) -> torch.Tensor:
+        self._ensure_current()
         self.graph.replay()
         return self.output
 
@@ -156,6 +176,7 @@ class CompiledForward:
         host predictions (valid until the next call)."""
         if batch.spec != self.spec:
             raise ValueError("batch layout differs from the one this forward was compiled for")
+        self._ensure_current()
         self.dev_buffer.copy_(batch.buffer, non_blocking=True)
         self.graph.replay()
         self.output_host.copy_(self.output, non_blocking=True)
@@ -188,6 +209,7 @@ class PipelinedForward:
         cf, st = self.slots[k], self.streams[k]
         if batch.spec != cf.spec:
             raise ValueError("batch layout differs from the one this forward was compiled for")
+        cf._ensure_current()
         st.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(st):
             cf.dev_buffer.copy_(batch.buffer, non_blocking=True)
@@ -205,6 +227,7 @@ class PipelinedForward:
         D2D refresh of the slot's static input buffer + graph replay on the slot's stream; no D2H."""
         k = self.n % len(self.slots)
         cf, st = self.slots[k], self.streams[k]
+        cf._ensure_current()
         st.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(st):
             cf.dev_buffer.copy_(packed, non_blocking=True)

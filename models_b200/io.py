@@ -106,6 +106,9 @@ def load_weights(model: Block, source: Union[str, os.PathLike, Mapping[str, np.n
         t.copy_(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(t.device, non_blocking=False))
         loaded[name] = src_name
     _notify_weights_changed(model)
+    from .core import bump_weights_version
+
+    bump_weights_version()  # captured graphs (graph.CompiledForward) re-capture before their next replay
     return loaded
 
 

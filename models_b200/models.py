@@ -271,7 +271,9 @@ class RankingModel(Model):
         if isinstance(self.body, DLRM) and self.body.top_block is not None:
             # top MLP + output layer as ONE dense chain (no fp32 round trip between them)
             bottom = self.body.bottom_forward(inputs)
-            layers = self.body.top_block.dense_layers + [self.prediction.to_call]
+            # top MLP (+ its normalizations, folded) + the output Dense as one chain
+            layers, tail = self.body.top_block.chain([self.prediction.to_call])
+            assert tail is None
             if dense_engine() != "fp32" and self.body.can_emit_split():
                 a = self.body.interaction_forward(inputs, bottom, as_split=True)
                 return run_dense_chain(None, layers, a_split=a, K=self.body.output_width_before_top())
@@ -279,7 +281,9 @@ class RankingModel(Model):
             return run_dense_chain(x, layers)
         if isinstance(self.body, DCNBody) and self.body.stacked:
             x = self.body.cross(self.body.input_block(inputs))
-            return run_dense_chain(x, self.body.deep.dense_layers + [self.prediction.to_call])
+            layers, tail = self.body.deep.chain([self.prediction.to_call])
+            assert tail is None
+            return run_dense_chain(x, layers)
         x = self.body(inputs, training=training)
         return self.prediction(x)
 

@@ -182,6 +182,29 @@ def dlrm_gather_interact(weights, indices, slots, D: int, bottom: Optional[torch
     return out
 
 
+def scale_shift(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = x * scale + shift per column (BatchNormalization at inference; mm_scale_shift)."""
+    _dev(x, "x", torch.float32), _dev(scale, "scale", torch.float32), _dev(shift, "shift", torch.float32)
+    out = torch.empty_like(x) if out is None else _dev(out, "out", torch.float32)
+    B, D = x.shape
+    if scale.numel() != D or shift.numel() != D:
+        raise ValueError(f"scale / shift must have {D} elements")
+    _cabi.check(_lib().mm_scale_shift(x.data_ptr(), B, D, _row_stride(x, "x"), scale.data_ptr(), shift.data_ptr(),
+                                      out.data_ptr(), _row_stride(out, "out"), _stream()), "mm_scale_shift")
+    return out
+
+
+def cross_combine(x0: torch.Tensor, proj: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out = x0 * proj + x (mm_cross_combine)."""
+    for n, t in (("x0", x0), ("proj", proj), ("x", x), ("out", out)):
+        _dev(t, n, torch.float32)
+    B, D = x.shape
+    _cabi.check(_lib().mm_cross_combine(x0.data_ptr(), proj.data_ptr(), x.data_ptr(), B, D, _row_stride(x0, "x0"),
+                                        _row_stride(proj, "proj"), _row_stride(x, "x"), out.data_ptr(), _row_stride(out, "out"),
+                                        _stream()), "mm_cross_combine")
+    return out
+
+
 def index_bytes_of(t: torch.Tensor) -> int:
     """Width in bytes of the ids a categorical column carries: int32 -> 4, int64 -> 8, and the packed
     host-batch forms uint8 (B,) -> 1, uint16 (B,) -> 2, uint8 (B, 3) -> 3 (little-endian 24-bit)."""

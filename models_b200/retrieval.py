@@ -366,7 +366,10 @@ class CategoricalOutput(Block):
 
     def refresh(self) -> None:
         """Drop the cached split-bf16 copies (call after changing the table)."""
+        from .core import bump_weights_version
+
         self._e_split = self._w_split = None
+        bump_weights_version()
 
     _weights_changed = refresh
 

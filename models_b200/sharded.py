@@ -1,10 +1,13 @@
 """Row-sharded embedding tables across the GPUs of one box (BASELINE config 4).
 
 Partitioning: row r of every sharded table lives on rank `r % world` at local row `r // world`
-(balanced under skew, keeps tiny tables from pinning to one GPU).  Tables with fewer than
-`replicate_below_rows` rows may be kept whole on every rank ("replicate tables with
-<= 64 k rows and shard only the big ones"); the default 0 shards everything.  Dense / MLP /
-interaction weights are replicated; the batch is sharded data-parallel.
+(balanced under skew).  Tables with fewer than `replicate_below_rows` rows (default 65 536 = 16 MB at
+D = 64) are kept whole on every rank ("replicate tables with <= 64 k rows and shard only
+the big ones"): a table of a handful of rows has nothing to shard, and sharding it anyway makes every
+sample of every GPU read the same few cache lines of one owner over NVLink — measured on 2 x B200, the
+8 tables under 1 000 rows of the Criteo-TB shape double the step time when sharded
+(profiles/r02_notes.md §b).  `replicate_below_rows=0` shards everything.  Dense / MLP / interaction
+weights are replicated; the batch is sharded data-parallel.
 
 Forward (one process per GPU): all shards live in ONE symmetric-memory arena per rank
 (`torch.distributed._symmetric_memory`: every rank maps every other rank's arena over NVLink, same
@@ -62,7 +65,7 @@ class ShardedEmbeddings:
     """Local shards of every table of an EmbeddingsBlock inside one symmetric-memory arena, the peer
     pointers of every other rank's arena, and the fused lookup + interaction launch."""
 
-    def __init__(self, embeddings: EmbeddingsBlock, group=None, device=None, replicate_below_rows: int = 0):
+    def __init__(self, embeddings: EmbeddingsBlock, group=None, device=None, replicate_below_rows: int = 65536):
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
@@ -237,7 +240,7 @@ class ShardedEmbeddings:
         return buf
 
 
-def shard_model(model, group=None, replicate_below_rows: int = 0):
+def shard_model(model, group=None, replicate_below_rows: int = 65536):
     """Row-shard the embedding tables of a DLRM model over `group` (call before the first forward;
     every rank then holds 1/world of each sharded table; tables with fewer than `replicate_below_rows`
     rows stay whole on every rank).  Returns the model."""

@@ -91,7 +91,10 @@ class _CandidateIndex(Block):
         return self._e_split
 
     def _weights_changed(self) -> None:
+        from .core import bump_weights_version
+
         self._e_split = None
+        bump_weights_version()
 
     def weights(self):
         return {} if self.values is None else {"candidates": self.values}

@@ -412,6 +412,70 @@ def main():
     dims_plain = np.array([su.infer_embedding_dim(c, multiplier=3.0, ensure_multiple_of_8=False) for c in colsd], dtype=np.int64)
     np.savez(OUT / "ref_torch_embedding_dims.npz", kind="embedding_dims", max_id=maxes, dims_default=dims_default,
              dims_mult3_plain=dims_plain, n_criteo=np.int64(len(names)))
+    # ---- 13. two towers: TabularInputBlock (continuous + embedded categoricals, sorted-name concat) -> MLPBlock,
+    #          on the ML-1M column names of SURVEY §8(a11): query = userId + TE_* floats, item = movieId + genres
+    #          (ragged multi-hot, mean combiner) + TE_movieId_rating; then the retrieval scorer pieces of the same
+    #          backend on the tower outputs (row-wise dot at inference, contrastive [positive | in-batch negatives]).
+    tab = importlib.import_module("merlin.models.torch.inputs.tabular")
+    embm = importlib.import_module("merlin.models.torch.inputs.embedding")
+    Bt, dt = 41, 16
+
+    def catc(name, mx, tags=(), is_list=False):
+        props = {"domain": {"min": 0, "max": mx, "name": name}}
+        if is_list:
+            props["value_count"] = {"min": 1, "max": 4}
+        return S.ColumnSchema(name, tags=("categorical",) + tuple(tags), dtype="int64", is_list=is_list, is_ragged=is_list,
+                              properties=props)
+
+    q_cols = [catc("userId", 6040, ("user", "user_id"))] + [
+        S.ColumnSchema(n, tags=("continuous", "user"), dtype="float32")
+        for n in ("TE_age_rating", "TE_gender_rating", "TE_occupation_rating", "TE_userId_rating", "TE_zipcode_rating")]
+    i_cols = [catc("movieId", 3684, ("item", "item_id")), catc("genres", 18, ("item",), is_list=True),
+              S.ColumnSchema("TE_movieId_rating", tags=("continuous", "item"), dtype="float32")]
+
+    def tower_init(block):
+        block.add_route(S.Tags.CONTINUOUS, required=False)
+        block.add_route(S.Tags.CATEGORICAL, embm.EmbeddingTables(dt, seq_combiner="mean"))
+
+    lens = rng.integers(1, 5, Bt)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tbatch = {"userId": rng.integers(1, 6041, Bt).astype(np.int64), "movieId": rng.integers(1, 3685, Bt).astype(np.int64),
+              "genres__values": rng.integers(1, 19, int(offs[-1])).astype(np.int64), "genres__offsets": offs,
+              "TE_movieId_rating": rng.random(Bt).astype(np.float32)}
+    tbatch["movieId"][5] = tbatch["movieId"][3]  # duplicate item -> an accidental hit off the diagonal
+    for c in q_cols[1:]:
+        tbatch[c.name] = rng.random(Bt).astype(np.float32)
+    blobs = {}
+    outs = {}
+    for tag, cols_t, seed in (("query", q_cols, 31), ("item", i_cols, 32)):
+        torch.manual_seed(seed)
+        sch = S.Schema(cols_t)
+        inp = tab.TabularInputBlock(sch, init=tower_init, agg="concat")
+        mlp_t = mlpm.MLPBlock([24, 12])
+        names_t = [c.name for c in cols_t]
+        feed_t = {k: torch.from_numpy(v) for k, v in tbatch.items() if any(k == n or k.startswith(n + "__") for n in names_t)}
+        concat = inp(feed_t)
+        out_t = mlp_t(concat)
+        outs[tag] = out_t.detach()
+        blobs[f"{tag}_concat"] = concat.detach().numpy()
+        blobs[f"{tag}_out"] = out_t.detach().numpy()
+        for name, m in inp.named_modules():
+            if isinstance(m, torch.nn.Embedding):
+                feat = [c.name for c in cols_t if f".{c.name}." in f".{name}."][0]
+                blobs[f"{tag}_table_{feat}"] = m.weight.detach().numpy().copy()
+        for i, l in enumerate([m for m in mlp_t.modules() if isinstance(m, torch.nn.Linear)]):
+            blobs[f"{tag}_kernel_{i}"] = l.weight.detach().numpy().T.copy()
+            blobs[f"{tag}_bias_{i}"] = l.bias.detach().numpy().copy()
+    qo, io = outs["query"], outs["item"]
+    inference_scores = (qo * io).sum(-1, keepdim=True)  # DotProduct of the towers at inference (outputs/contrastive.py)
+    item_ids = torch.from_numpy(tbatch["movieId"])
+    neg_e, neg_i = sampler(io, item_ids)
+    fake3 = types.SimpleNamespace(downscore_false_negatives=True, false_negative_score=MINF)
+    logits_t = con.ContrastiveOutput.contrastive_outputs(fake3, qo, io, neg_e, positive_id=item_ids, negative_id=neg_i)
+    np.savez(OUT / "ref_torch_two_tower.npz", kind="two_tower", dim=np.int64(dt), query_cols=np.array([c.name for c in q_cols]),
+             item_cols=np.array([c.name for c in i_cols]), inference_scores=inference_scores.numpy(),
+             train_logits=logits_t.numpy(), train_targets=fake3.target.numpy(), min_float=np.float32(MINF),
+             **{f"batch_{k}": v for k, v in tbatch.items()}, **blobs)
     print("wrote", sorted(p.name for p in OUT.glob("ref_torch_*.npz")))
 
 

@@ -124,6 +124,30 @@ def check(path: Path) -> None:
             cross = [{"kernel": l["kernel"], "bias": l["bias"]} for l in unpack_layers(z, "cross")]
             got = oracle.dcn_forward(batch, tables, {n: n for n in cat}, cont, cross, unpack_layers(z, "deep"), head)
         np.testing.assert_allclose(got, z["out"], rtol=1e-4, atol=1e-5)
+    elif kind == "two_tower":
+        # reference torch towers: TabularInputBlock(continuous + EmbeddingTables(mean combiner), agg="concat") -> MLPBlock,
+        # then the backend's retrieval pieces on the tower outputs
+        batch = {k[len("batch_"):]: z[k] for k in z if k.startswith("batch_")}
+        towers = {}
+        for tag in ("query", "item"):
+            cols = [str(c) for c in z[f"{tag}_cols"]]
+            tables = {c: z[f"{tag}_table_{c}"] for c in cols if f"{tag}_table_{c}" in z}
+            cont = [c for c in cols if c not in tables]
+            sub = {k: v for k, v in batch.items() if any(k == c or k.startswith(c + "__") for c in cols)}
+            layers = [{"kernel": z[f"{tag}_kernel_{i}"], "bias": z[f"{tag}_bias_{i}"], "activation": "relu"} for i in range(2)]
+            # the concat the first Dense sees: sorted feature names, embeddings (bags: mean) and continuous columns
+            feats = oracle.prepare_features(sub)
+            d = {c: oracle.embed_feature(tables[c], feats[c], "mean") for c in tables}
+            d.update({c: np.asarray(feats[c], dtype=np.float32) for c in cont})
+            np.testing.assert_allclose(oracle.concat_features(d), z[f"{tag}_concat"], rtol=RTOL, atol=ATOL)
+            towers[tag] = oracle.tower_forward(sub, tables, {c: c for c in tables}, cont, layers, combiner="mean")
+            np.testing.assert_allclose(towers[tag], z[f"{tag}_out"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(oracle.retrieval_scores(towers["query"], towers["item"]), z["inference_scores"], rtol=1e-5, atol=1e-6)
+        ids = batch["movieId"]
+        logits, targets = oracle.contrastive_logits(towers["query"], towers["item"], towers["item"], ids, ids, downscore=True,
+                                                    false_negative_score=float(z["min_float"]))
+        np.testing.assert_allclose(logits, z["train_logits"], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(targets, z["train_targets"])
     elif kind == "oracle_model":
         spec = json.loads(str(z["spec"]))
         got = run_model_fixture(z, spec)

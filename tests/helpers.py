@@ -14,8 +14,19 @@ def to_numpy(t):
 
 
 def mlp_layers(mlp):
-    return [{"kernel": to_numpy(l.kernel), "bias": None if l.bias is None else to_numpy(l.bias),
-             "activation": l.activation} for l in mlp.dense_layers]
+    """Oracle description of an MLP: one dict per Dense; a BatchNormalization that follows it rides along as
+    "batch_norm" (oracle.mlp applies it after the activation, as Keras does at inference)."""
+    from models_b200.blocks import BatchNormalization, _Dense
+
+    out = []
+    for l in mlp.layers:
+        if isinstance(l, _Dense):
+            out.append({"kernel": to_numpy(l.kernel), "bias": None if l.bias is None else to_numpy(l.bias),
+                        "activation": l.activation})
+        elif isinstance(l, BatchNormalization):
+            out[-1]["batch_norm"] = {"gamma": to_numpy(l.gamma), "beta": to_numpy(l.beta), "mean": to_numpy(l.moving_mean),
+                                     "var": to_numpy(l.moving_variance)}
+    return out
 
 
 def head_layer(out_block):

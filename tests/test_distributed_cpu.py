@@ -47,7 +47,7 @@ def _worker(rank, world, port, result):
         schema = datasets.criteo_schema({k: min(v, 97) for k, v in datasets.CRITEO_MAX.items()})
         cat = schema.select_by_tag(mm.Tags.CATEGORICAL)
         emb = mm.Embeddings(cat, dim=8)
-        se = sharded.ShardedEmbeddings(emb)
+        se = sharded.ShardedEmbeddings(emb, replicate_below_rows=0)
         rng = np.random.default_rng(5)
         full = {n: rng.standard_normal((t.input_dim, 8)).astype(np.float32) for n, t in emb.tables.items()}
         se.load_full_tables({n: torch.from_numpy(v) for n, v in full.items()}, torch.device("cpu"))

@@ -330,3 +330,51 @@ def test_reference_torch_mlp_activations(device, engine):
             np.testing.assert_allclose(mlp(x).cpu().numpy(), z[f"out_{name}"], rtol=2e-4, atol=2e-5, err_msg=name)
     finally:
         blocks.set_dense_engine("auto")
+
+
+def test_reference_torch_two_tower_end_to_end(device):
+    """merlin.models.torch towers (TabularInputBlock: continuous + EmbeddingTables(mean) -> sorted concat -> MLPBlock)
+    on the ML-1M column names, executed in the build container (ref_torch_two_tower.npz), against mm.TwoTowerModel
+    with the same tables and kernels: tower outputs, inference scores (B,1) and the train-mode
+    [positive | in-batch negatives] logits with the false-negative rescoring."""
+    from models_b200.schema import ColumnSchema, Schema, Tags
+
+    z = replay.load(G / "ref_torch_two_tower.npz")
+    dim = int(z["dim"])
+
+    def col(name, tower):
+        tags = ("user",) if tower == "query" else ("item",)
+        if f"{tower}_table_{name}" in z:
+            mx = z[f"{tower}_table_{name}"].shape[0] - 1
+            is_list = name == "genres"
+            props = {"domain": {"min": 0, "max": int(mx), "name": name}}
+            if is_list:
+                props["value_count"] = {"min": 1, "max": 4}
+            extra = ("user_id",) if name == "userId" else ("item_id",) if name == "movieId" else ()
+            return ColumnSchema(name, tags=("categorical",) + tags + extra, dtype="int64", is_list=is_list, is_ragged=is_list,
+                                properties=props)
+        return ColumnSchema(name, tags=("continuous",) + tags, dtype="float32")
+
+    cols = [col(str(n), "query") for n in z["query_cols"]] + [col(str(n), "item") for n in z["item_cols"]]
+    model = mm.TwoTowerModel(Schema(cols), query_tower=mm.MLPBlock([24, 12]), item_tower=mm.MLPBlock([24, 12]),
+                             embedding_options=mm.EmbeddingOptions(embedding_dim_default=dim))
+    for tag, tower in (("query", model.body.query), ("item", model.body.item)):
+        for name, table in tower.inputs.embeddings.tables.items():
+            table.table = torch.from_numpy(z[f"{tag}_table_{name}"]).cuda().contiguous()
+            assert table.table.shape == (table.input_dim, table.dim)
+            table.built = True
+        _set_mlp(tower.mlp, [{"kernel": z[f"{tag}_kernel_{i}"], "bias": z[f"{tag}_bias_{i}"], "activation": "relu"} for i in range(2)])
+    model.build(device)
+    batch = {k[len("batch_"):]: dev(z[k], device) for k in z if k.startswith("batch_")}
+    enc = model.body(batch)
+    np.testing.assert_allclose(enc["query"].cpu().numpy(), z["query_out"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(enc["item"].cpu().numpy(), z["item_out"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(model(batch).cpu().numpy(), z["inference_scores"], rtol=2e-4, atol=2e-5)
+    pred = model(batch, training=True)
+    got = pred.predictions.cpu().numpy()
+    assert got.shape == z["train_logits"].shape
+    hits = z["train_logits"] == z["min_float"]
+    assert hits[:, 1:].sum() > z["train_logits"].shape[0]  # the diagonal plus the duplicated item
+    assert np.array_equal(got == np.float32(z["min_float"]), hits)
+    np.testing.assert_allclose(got, z["train_logits"], rtol=2e-4, atol=5e-5)
+    assert np.array_equal(pred.targets.cpu().numpy(), z["train_targets"])
