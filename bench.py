@@ -808,6 +808,28 @@ def secondary_record(ctx, kind):
                 "steps": e2e_steps},
         "gpu_launches": cf.launches_per_replay * steps * world, "roofline": roof,
     }
+    if kind == "twotower":
+        # the same step with the soft-max cross-entropy folded into the scorer's epilogue (model(..., fused_loss=True)):
+        # outputs (B,3) [max, log-sum-exp, positive logit] instead of the (B, 1+B) logits — nothing of size B^2 is written
+        try:
+            kw = dict(call_kwargs, fused_loss=True)
+            cf2 = model.compile(hbs[0], **kw)
+            pf2 = model.pipeline(hbs[0], depth=2, **kw)
+            el2, _ = timed_replay(ctx, pf2, packed_dev, steps, args.warmup)
+            ser2 = timed_serial(cf2, packed_dev, steps)
+            e2e2, res2 = timed_e2e(ctx, pf2, hbs, e2e_steps, 2)
+            el2, e2e2 = ctx.max_over_ranks(el2, e2e2)
+            rec["fused_loss"] = {
+                "what": "model(batch, training=True, fused_loss=True): in-batch soft-max CE statistics from the GEMM epilogue "
+                        "(mm_inbatch_softmax_ce), no (B, 1+B) logits",
+                "value": world * B * steps / (el2 * 1e-3), "unit": "samples/s", "ms_per_step": el2 / steps,
+                "ms_per_step_single_stream": ser2,
+                "e2e": {"value": world * B * e2e_steps / (e2e2 * 1e-3), "unit": "samples/s",
+                        "h2d_bytes_per_step": int(hbs[0].payload_bytes()), "d2h_bytes_per_step": int(res2.numel() * res2.element_size())},
+                "gpu_launches": cf2.launches_per_replay * steps * world}
+            del cf2, pf2
+        except Exception as e:
+            rec["fused_loss"] = {"error": f"{type(e).__name__}: {e}"}
     del cf, pf, model
     return rec
 

@@ -329,6 +329,20 @@ int mm_catalog_score(const void* q_split, int64_t B, int D, const void* e_split,
                      float* topk_scores, int64_t* topk_ids, void* workspace, int64_t workspace_bytes,
                      void* stream);
 
+/* In-batch contrastive soft-max cross-entropy WITHOUT the (B, 1+N) logits: the same logits as
+ * mm_positive_scores + mm_inbatch_scores_tc (blocks/retrieval/base.py:339-396, outputs/contrastive.py:303-326,
+ * utils/tf_utils.py:126-154) folded straight into the inputs of CategoricalCrossEntropy(from_logits=True) against the
+ * one-hot target on column 0 (losses/listwise.py:38-50):
+ *   out_stats (B,3) = [row max, log-sum-exp over {pos} U {negatives}, pos]   ->  loss[b] = out_stats[b,1] - out_stats[b,2]
+ * pos_logit (B,): column 0 as mm_positive_scores writes it (logQ and temperature already applied);
+ * negatives: (pos_ids[b] == neg_ids[n] && downscore ? false_neg_score : q[b].neg[n] - log(neg_prob[n] + 1e-16)) / temperature.
+ * One tcgen05 pass of the catalog-scoring kernel (its epilogue with the id mask) + the merge kernel; 1.07 GB of
+ * logits at B = N = 16 384 never exist.  workspace: mm_catalog_workspace_bytes(B, N, 0). */
+int mm_inbatch_softmax_ce(const void* q_split, const void* neg_split, int64_t B, int64_t N, int D, const void* pos_ids,
+                          const void* neg_ids, int id_dtype, int downscore, float false_neg_score, const float* pos_logit,
+                          const float* neg_prob, float temperature, float* out_stats, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K13  Row-sharded tables over the GPUs of one NVLink domain: row r of every table lives on
  * rank r % world at local row r / world (the reference's counterpart is SOK's distributed

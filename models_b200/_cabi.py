@@ -99,6 +99,7 @@ SIGNATURES = {
     "mm_rowwise_dot": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
     "mm_catalog_workspace_bytes": (_i64, [_i64, _i64, _i]),
     "mm_catalog_score": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp]),
+    "mm_inbatch_softmax_ce": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _f, _vp, _vp, _i64, _vp]),
     "mm_shard_gather_push": (_i, [_tables, _i, _i, _i64, _i64, _i, _i, _i, C.POINTER(C.c_void_p), _i64, _vp, _vp]),
     "mm_init_uniform_hash_rows": (_i, [_vp, _i64, _i, _u64, _f, _f, _i64, _i64, _vp]),
     "mm_positive_scores": (_i, [_vp, _vp, _i64, _i, _vp, _f, _vp, _i64, _vp]),

@@ -373,7 +373,9 @@ class RetrievalModel(Model):
         if not self.built:
             self.build(next(iter(inputs.values())).device)
         emb = self.body(inputs, training=False)
-        return self.prediction(emb, features=inputs, training=training, testing=testing)
+        # fused_loss=True (training/testing): Prediction.outputs = (B,3) [max, log-sum-exp, positive logit] of the in-batch
+        # logits — loss = outputs[:,1] - outputs[:,2] — instead of the (B, 1+B) logits themselves
+        return self.prediction(emb, features=inputs, training=training, testing=testing, **kwargs)
 
     # -- top-k retrieval / evaluation (models/base.py:2266-2489) ---------------------
     @property

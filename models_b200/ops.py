@@ -344,6 +344,44 @@ def inbatch_scores(q, pos, neg, out, pos_ids=None, neg_ids=None, downscore=True,
     return out
 
 
+def inbatch_softmax_ce(q, pos, neg, pos_ids=None, neg_ids=None, downscore=True, false_neg_score: float = -655.04,
+                       pos_prob=None, neg_prob=None, temperature: float = 1.0) -> torch.Tensor:
+    """(B,3) = [row max, log-sum-exp, positive logit] of the in-batch contrastive logits [q.pos | masked(q @ neg^T)] / T —
+    the inputs of softmax cross-entropy against the one-hot target on column 0 — without materialising the (B, 1+N)
+    logits (mm_positive_scores + mm_inbatch_softmax_ce).  loss = stats[:,1] - stats[:,2]."""
+    for n_, t_ in (("q", q), ("pos", pos), ("neg", neg)):
+        _dev(t_, n_, torch.float32)
+        if not t_.is_contiguous():
+            raise ValueError(f"{n_} must be contiguous")
+    B, D = q.shape
+    N = neg.shape[0]
+    if N == 0 or B == 0:
+        raise ValueError("in-batch softmax needs at least one query and one negative")
+    id_dt = MM_I64
+    if downscore:
+        if pos_ids is None or neg_ids is None:
+            raise ValueError("downscore_false_negatives requires positive and negative item ids")
+        neg_ids = neg_ids.reshape(-1).contiguous()
+        pos_ids = pos_ids.reshape(-1).to(neg_ids.dtype).contiguous()  # utils/tf_utils.py:136
+        id_dt = _idx_dtype(neg_ids, "neg_ids")
+    dev = q.device
+    pos_logit = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    _cabi.check(_lib().mm_positive_scores(q.data_ptr(), pos.data_ptr(), B, D, _ptr(pos_prob), float(temperature),
+                                          pos_logit.data_ptr(), 1, _stream()), "mm_positive_scores")
+    qs = split_rows(q)
+    ns = qs if neg.data_ptr() == q.data_ptr() else split_rows(neg)
+    stats = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    nbytes = int(_lib().mm_catalog_workspace_bytes(B, N, 0))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    _cabi.check(
+        _lib().mm_inbatch_softmax_ce(qs.data_ptr(), ns.data_ptr(), B, N, D, _ptr(pos_ids) if downscore else None,
+                                     _ptr(neg_ids) if downscore else None, id_dt, int(bool(downscore)), float(false_neg_score),
+                                     pos_logit.data_ptr(), _ptr(neg_prob), float(temperature), stats.data_ptr(), ws.data_ptr(),
+                                     nbytes, _stream()),
+        "mm_inbatch_softmax_ce")
+    return stats
+
+
 _CONCAT_DTYPES = {torch.int32: _cabi.MM_I32, torch.int64: _cabi.MM_I64, torch.float32: _cabi.MM_F32,
                   torch.float64: _cabi.MM_F64}
 

@@ -165,8 +165,17 @@ def _target_row(width: int, device) -> torch.Tensor:
 
 
 def _score(query, pos_item, neg_items, pos_ids, neg_ids, downscore, false_neg_score, temperature,
-           pos_prob=None, neg_prob=None) -> Prediction:
+           pos_prob=None, neg_prob=None, fused_loss: bool = False) -> Prediction:
     B, N = query.shape[0], neg_items.shape[0]
+    if fused_loss:
+        # soft-max cross-entropy against the one-hot target on column 0, straight from the GEMM epilogue: the
+        # (B, 1+N) logits (1.07 GB at B = 16 384) are never written.  outputs = (B,3) [max, log-sum-exp, positive logit]
+        if dense_engine() == "fp32":
+            raise NotImplementedError("fused_loss runs on the tensor-core engine")
+        stats = ops.inbatch_softmax_ce(query.contiguous(), pos_item.contiguous(), neg_items.contiguous(), pos_ids=pos_ids,
+                                       neg_ids=neg_ids, downscore=downscore, false_neg_score=false_neg_score,
+                                       pos_prob=pos_prob, neg_prob=neg_prob, temperature=temperature)
+        return Prediction(stats, None, negative_candidate_ids=neg_ids, kind="softmax_ce_stats")
     # (B, 1+N) logits as a view into a (B, 4+Nr) buffer starting at physical column 3: the negatives
     # (logical columns 1..N) then start 16-byte aligned in every row, so the GEMM epilogue can use
     # 128-bit stores; Nr = N rounded up to 4 keeps the row stride a multiple of 16 bytes
@@ -215,8 +224,9 @@ class ItemRetrievalScorer(Block):
         return ops.rowwise_dot(q, it, out)
 
     def call_outputs(self, predictions: Dict[str, torch.Tensor], features: TabularData, temperature: float = 1.0,
-                     **kwargs) -> Prediction:
-        """Training / testing logits (retrieval/base.py:283-429)."""
+                     fused_loss: bool = False, **kwargs) -> Prediction:
+        """Training / testing logits (retrieval/base.py:283-429); `fused_loss=True`: the cross-entropy statistics
+        of those logits instead of the logits (see _score)."""
         assert len(self.samplers) > 0, "At least one sampler is required by ItemRetrievalScorer for negative sampling"
         self._check_input_from_two_tower(predictions)
         q, items = predictions[self.query_name], predictions[self.item_name]
@@ -239,7 +249,7 @@ class ItemRetrievalScorer(Block):
         if pos_ids is not None:
             nid = neg_i[0] if len(neg_i) == 1 else torch.cat(neg_i, dim=0)
         return _score(q, items, neg, pos_ids, nid, self.downscore_false_negatives, self.false_negatives_score,
-                      temperature)
+                      temperature, fused_loss=fused_loss)
 
 
 class ItemRetrievalTask(Block):
@@ -263,9 +273,9 @@ class ItemRetrievalTask(Block):
         self.target_name = target_name
 
     def call(self, inputs, features: Optional[TabularData] = None, training: bool = False, testing: bool = False,
-             **kwargs):
+             fused_loss: bool = False, **kwargs):
         if training or testing:
-            return self.scorer.call_outputs(inputs, features, temperature=self.logits_temperature)
+            return self.scorer.call_outputs(inputs, features, temperature=self.logits_temperature, fused_loss=fused_loss)
         return self.scorer(inputs)
 
 
@@ -293,7 +303,8 @@ class ContrastiveOutput(Block):
         self.logq_sampling_correction = logq_sampling_correction
 
     def call(self, inputs: Dict[str, torch.Tensor], candidate_ids: Optional[torch.Tensor] = None,
-             training: bool = False, testing: bool = False, sampling_probs: Optional[torch.Tensor] = None, **kwargs):
+             training: bool = False, testing: bool = False, sampling_probs: Optional[torch.Tensor] = None,
+             fused_loss: bool = False, **kwargs):
         q, c = inputs[self.query_name], inputs[self.candidate_name]
         if not (training or testing):
             out = torch.empty((q.shape[0], 1), dtype=torch.float32, device=q.device)
@@ -317,7 +328,7 @@ class ContrastiveOutput(Block):
             pos_prob = sampling_probs[ids.long()].contiguous()
             neg_prob = sampling_probs[nid.long()].contiguous()
         return _score(q, c, neg, ids, nid, self.downscore_false_negatives, self.false_negative_score,
-                      self.logits_temperature, pos_prob, neg_prob)
+                      self.logits_temperature, pos_prob, neg_prob, fused_loss=fused_loss)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -81,3 +81,89 @@ def test_categorical_output_block(device):
     np.testing.assert_allclose(scores.cpu().numpy(), rv, rtol=1e-4, atol=1e-4)
     with pytest.raises(ValueError, match="k must be"):
         out.top_k(dev(x, device), 64)
+
+
+def test_catalog_full_size_sampled_rows(device):
+    """BASELINE configs[2] size: 10 M items x D 64.  The (B, 10 M) logits cannot be checked densely, so (a) the log-sum-exp
+    and target logit of a sample of query rows are recomputed on the host in float64 over the WHOLE catalog (hash-initialised:
+    any block of rows is regenerated on the host), and (b) the fused top-k of those rows is checked against the host's."""
+    I, D, B = 10_000_000, 64, 384
+    rng = np.random.default_rng(17)
+    E = torch.empty((I, D), dtype=torch.float32, device=device)
+    ops.init_uniform_hash(E, 77, -0.5, 0.5)
+    x = (rng.standard_normal((B, D)) * 0.6).astype(np.float32)
+    targets = rng.integers(0, I, B).astype(np.int64)
+    targets[:3] = [0, I - 1, 127]  # tile / range edges
+    stats, scores, ids = ops.catalog_score(dev(x, device), ops.split_rows(E), I, targets=dev(targets, device), k=8)
+    stats, scores, ids = stats.cpu().numpy(), scores.cpu().numpy(), ids.cpu().numpy()
+    rows = [0, 1, 2, 127, 128, 200, 383]
+    xs = x[rows].astype(np.float64)
+    m = np.full(len(rows), -np.inf)
+    s = np.zeros(len(rows))
+    best_v = np.full((len(rows), 8), -np.inf)
+    best_i = np.full((len(rows), 8), -1, dtype=np.int64)
+    step = 500_000
+    for r0 in range(0, I, step):
+        blk = oracle.hash_table_rows(np.arange(r0, min(I, r0 + step)), D, 77, -0.5, 0.5).astype(np.float64)
+        lg = xs @ blk.T
+        m_new = np.maximum(m, lg.max(axis=1))
+        s = s * np.exp(m - m_new) + np.exp(lg - m_new[:, None]).sum(axis=1)
+        m = m_new
+        cand_v = np.concatenate([best_v, lg], axis=1)
+        cand_i = np.concatenate([best_i, np.broadcast_to(np.arange(r0, r0 + lg.shape[1]), lg.shape)], axis=1)
+        order = np.argsort(-cand_v, axis=1, kind="stable")[:, :8]
+        best_v, best_i = np.take_along_axis(cand_v, order, 1), np.take_along_axis(cand_i, order, 1)
+    lse = m + np.log(s)
+    tl = np.einsum("bd,bd->b", xs, oracle.hash_table_rows(targets[rows], D, 77, -0.5, 0.5).astype(np.float64))
+    np.testing.assert_allclose(stats[rows, 0], m, rtol=0, atol=5e-4)
+    np.testing.assert_allclose(stats[rows, 1], lse, rtol=0, atol=5e-4)
+    np.testing.assert_allclose(stats[rows, 2], tl, rtol=0, atol=5e-4)
+    np.testing.assert_allclose(scores[rows], best_v, rtol=0, atol=5e-4)
+    same = ids[rows] == best_i
+    assert same.mean() > 0.9 and np.allclose(scores[rows][~same], best_v[~same], atol=1e-3)  # near-ties may swap
+
+
+@pytest.mark.parametrize("B,N,D", [(100, 77, 32), (300, 1000, 64), (129, 256, 128), (1024, 1024, 128)])
+@pytest.mark.parametrize("downscore,logq,temperature", [(True, False, 1.0), (True, True, 0.5), (False, False, 1.0), (False, True, 2.0)])
+def test_inbatch_softmax_ce_equals_ce_of_the_materialised_logits(device, B, N, D, downscore, logq, temperature):
+    """mm_inbatch_softmax_ce: [max, lse, positive logit] of exactly the logits mm_inbatch_scores produces."""
+    rng = np.random.default_rng(B + N)
+    q = rng.standard_normal((B, D)).astype(np.float32) * 0.7
+    pos = rng.standard_normal((B, D)).astype(np.float32) * 0.7
+    neg = pos if N == B else (rng.standard_normal((N, D)).astype(np.float32) * 0.7)
+    pos_ids = rng.integers(0, max(4, N // 3), B).astype(np.int64)       # many duplicates -> many accidental hits
+    neg_ids = pos_ids if N == B else rng.integers(0, max(4, N // 3), N).astype(np.int64)
+    pp = rng.uniform(1e-4, 0.2, B).astype(np.float32) if logq else None
+    npb = (pp if N == B else rng.uniform(1e-4, 0.2, N).astype(np.float32)) if logq else None
+    logits, _ = oracle.contrastive_logits(q, pos, neg, pos_ids, neg_ids, downscore=downscore, pos_prob=pp, neg_prob=npb,
+                                          temperature=temperature)
+    ref = oracle.softmax_ce_stats(logits, np.zeros(B, dtype=np.int64))
+    d = lambda a: None if a is None else dev(a, device)
+    nt = d(pos) if N == B else d(neg)
+    pt = nt if N == B else d(pos)
+    stats = ops.inbatch_softmax_ce(d(q), pt, nt, pos_ids=d(pos_ids), neg_ids=d(neg_ids), downscore=downscore,
+                                   pos_prob=d(pp), neg_prob=d(npb), temperature=temperature).cpu().numpy()
+    tol = 4e-4 * max(1.0, np.sqrt(D / 64)) / min(1.0, temperature)
+    np.testing.assert_allclose(stats, ref, rtol=2e-4, atol=tol)
+    loss = stats[:, 1] - stats[:, 2]
+    assert np.all(loss >= -1e-4)
+
+
+def test_two_tower_fused_loss_matches_logits_path(device):
+    """model(batch, training=True, fused_loss=True) returns the cross-entropy statistics of the logits that
+    model(batch, training=True) returns — eager and through the CUDA-graph runtime."""
+    mm.set_seed(7)
+    schema = datasets.movielens_1m_schema()
+    model = mm.TwoTowerModel(schema, query_tower=mm.MLPBlock([128, 64]), logits_temperature=0.8)
+    batch = datasets.generate_batch(schema, 512, seed=4)
+    feats, _ = datasets.split_targets(schema, batch)
+    cols = model.input_columns()
+    dbatch = {k: dev(feats[k], device) for k in cols}
+    logits = model(dbatch, training=True).predictions.cpu().numpy()
+    ref = oracle.softmax_ce_stats(logits, np.zeros(512, dtype=np.int64))
+    pred = model(dbatch, training=True, fused_loss=True)
+    assert pred.targets is None and tuple(pred.predictions.shape) == (512, 3)
+    np.testing.assert_allclose(pred.predictions.cpu().numpy(), ref, rtol=2e-4, atol=5e-4)
+    hb = mm.HostBatch.like(feats, cols)
+    cf = model.compile(hb, training=True, fused_loss=True)
+    np.testing.assert_allclose(cf(hb).numpy(), ref, rtol=2e-4, atol=5e-4)

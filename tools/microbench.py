@@ -145,6 +145,16 @@ def main():
             report(f"mm_inbatch_scores 16384x16384 D=64 ({'tcgen05 split-bf16 incl. operand split' if tc else 'fp32 SIMT'})", m, mn,
                    bytes_=Bq * (Bq + 1) * 4, flops=2.0 * Bq * Bq * Dq)
 
+    if "fusedce" in only:
+        Bq = 16384
+        ids = torch.randint(0, 10_000_000, (Bq,), device=dev, dtype=torch.int64)
+        for Dq in (64, 128):
+            q = torch.randn((Bq, Dq), device=dev)
+            it = torch.randn((Bq, Dq), device=dev)
+            m, mn = timeit(lambda i: ops.inbatch_softmax_ce(q, it, it, pos_ids=ids, neg_ids=ids), max(5, args.iters // 2))
+            report(f"mm_inbatch_softmax_ce 16384x16384 D={Dq} (fused CE stats, incl. operand split + positive scores)", m, mn,
+                   flops=2.0 * Bq * Bq * Dq * 3, logical_flops=2.0 * Bq * Bq * Dq)
+
     if "catalog" in only:
         Bq, Dq, I = 16384, 64, args.catalog_items
         q = torch.randn((Bq, Dq), device=dev)
