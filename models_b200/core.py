@@ -234,9 +234,34 @@ class Block:
         return SequentialBlock(layers)
 
     def copy(self) -> "Block":
+        """Keras `copy()` goes through from_config: the copy gets fresh layer names and therefore independently
+        initialised variables.  Here variables are seeded from the layer name (create_variable), so a plain deepcopy
+        of an unbuilt block would initialise, e.g., the default item tower identically to the query tower: every Block
+        inside the copy gets a new unique name."""
         import copy as _copy
+        import re as _re
 
-        return _copy.deepcopy(self)
+        new = _copy.deepcopy(self)
+
+        def rename(o, depth=0, seen=None):
+            seen = set() if seen is None else seen
+            if id(o) in seen or depth > 8:
+                return
+            seen.add(id(o))
+            if isinstance(o, Block):
+                base = _re.sub(r"_\d+$", "", o.name.split("/")[-1]) or "block"
+                o.name = unique_name(base)
+                for v in vars(o).values():
+                    rename(v, depth + 1, seen)
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    rename(v, depth + 1, seen)
+            elif isinstance(o, dict):
+                for v in o.values():
+                    rename(v, depth + 1, seen)
+
+        rename(new)
+        return new
 
 
 class SequentialBlock(Block):

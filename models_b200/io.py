@@ -177,12 +177,22 @@ class _TensorUnpickler(pickle.Unpickler):
             self.cache[idx] = t.to(self.device) if e.get("device") == "cuda" else t
         return self.cache[idx]
 
+    # value types a structure file may legitimately name besides this package's own classes
+    _ALLOWED = {("collections", "OrderedDict"), ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "slice"),
+                ("builtins", "range"), ("builtins", "complex"), ("builtins", "bytearray")}
+
     def find_class(self, module, name):
-        # the structure file may only name classes of this package, numpy/torch value types and builtins
-        root = module.split(".")[0]
-        if root not in ("models_b200", "numpy", "torch", "builtins", "collections", "_codecs", "functools"):
-            raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a model file")
-        return super().find_class(module, name)
+        """Exact allowlist: classes DEFINED in this package (types whose __module__ is models_b200.*, looked up by a
+        plain, undotted name) plus a few inert value types.  Anything else — builtins.eval / getattr / __import__,
+        functools.partial, torch.load, numpy.load, or a module object re-exported by one of this package's modules
+        (`models_b200.csrc.build.subprocess`) — is refused, so loading an untrusted export cannot run code."""
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        if (module == "models_b200" or module.startswith("models_b200.")) and "." not in name:
+            obj = super().find_class(module, name)
+            if isinstance(obj, type) and (obj.__module__ == "models_b200" or obj.__module__.startswith("models_b200.")):
+                return obj
+        raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a model file")
 
 
 def save_model(model: Block, export_path) -> None:

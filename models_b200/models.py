@@ -333,7 +333,21 @@ class DCNBody(Block):
             return self.deep(c)
         d = self.deep(x0)
         out = torch.empty((x0.shape[0], c.shape[1] + d.shape[1]), dtype=torch.float32, device=x0.device)
-        return ops.concat_columns([c, d], out)
+        return ops.concat_columns([c, d] if self.branch_order() == ("cross", "deep") else [d, c], out)
+
+    def branch_order(self):
+        """Column order of the non-stacked concat.  The reference's `connect_branch(CrossBlock(depth), deep_block,
+        aggregation="concat")` builds a ParallelBlock keyed by the two layers' auto names and ConcatFeatures sorts the
+        keys (core/combinators.py, core/aggregation.py:54-66): both are `sequential_block[_N]`, the deep block is created
+        first, so the order is normally [deep | cross] — by STRING comparison of the names (`..._10` < `..._9`).  The same
+        rule is applied to this package's Keras-style names; set `body.concat_order = ("cross", "deep")` (or the reverse)
+        to pin the layout of an imported checkpoint's output kernel explicitly."""
+        forced = getattr(self, "concat_order", None)
+        if forced is not None:
+            if tuple(forced) not in (("cross", "deep"), ("deep", "cross")):
+                raise ValueError("concat_order must be ('cross', 'deep') or ('deep', 'cross')")
+            return tuple(forced)
+        return ("cross", "deep") if self.cross.name < self.deep.name else ("deep", "cross")
 
 
 def DCNModel(schema: Schema, depth: int, deep_block: Optional[MLP] = None, stacked: bool = True,
@@ -462,6 +476,76 @@ class RetrievalModel(Model):
                 scores, order = torch.topk(out.outputs, k, dim=1)
                 return Prediction(scores, torch.gather(out.targets, 1, order))
         return evaluate_topk(predict, x, metrics)
+
+
+class RetrievalModelV2(Model):
+    """models/base.py RetrievalModelV2 (forward): query Encoder, candidate Encoder, one output layer.
+    Inference: output({"query": q, "candidate": c}) -> (B,1); training/testing: [positive | negatives] logits from the
+    output's samplers (or their soft-max CE statistics with fused_loss=True)."""
+
+    def __init__(self, query, candidate, output, schema: Optional[Schema] = None, candidate_id_tag=Tags.ITEM_ID):
+        from .retrieval import Encoder
+
+        if schema is None:
+            cols = list(query.schema) + [c for c in candidate.schema if c.name not in query.schema]
+            schema = Schema(cols)
+        super().__init__(query, output, schema)
+        self.query_encoder_block, self.candidate_encoder_block = query, candidate
+        ids = candidate.schema.select_by_tag(candidate_id_tag).column_names
+        if not ids:
+            raise ValueError(f"the candidate tower has no column tagged {candidate_id_tag}")
+        self.candidate_id_name = ids[0]
+
+    @property
+    def blocks(self) -> List[Block]:
+        return [self.query_encoder_block, self.candidate_encoder_block, self.prediction]
+
+    def weights(self):
+        out = {f"query/{k}": v for k, v in self.query_encoder_block.weights().items()}
+        out.update({f"candidate/{k}": v for k, v in self.candidate_encoder_block.weights().items()})
+        return out
+
+    def build(self, device=None):
+        self.query_encoder_block.build(device)
+        self.candidate_encoder_block.build(device)
+        self.built = True
+        return self
+
+    def input_columns(self) -> List[str]:
+        return expected_input_columns(self.schema)
+
+    def query_encoder(self) -> Block:
+        return self.query_encoder_block
+
+    def candidate_encoder(self) -> Block:
+        return self.candidate_encoder_block
+
+    def call(self, inputs: TabularData, targets=None, training: bool = False, testing: bool = False, **kwargs):
+        self._check_inputs(inputs)
+        if not self.built:
+            self.build(next(iter(inputs.values())).device)
+        out = self.prediction
+        enc = {out.query_name: self.query_encoder_block(inputs), out.candidate_name: self.candidate_encoder_block(inputs)}
+        return out(enc, candidate_ids=inputs[self.candidate_id_name], training=training, testing=testing, **kwargs)
+
+
+def TwoTowerModelV2(query_tower, candidate_tower, candidate_id_tag=Tags.ITEM_ID, outputs=None, logits_temperature: float = 1.0,
+                    negative_samplers=None, schema: Optional[Schema] = None, **kwargs) -> RetrievalModelV2:
+    """models/retrieval.py:409-486: two Encoder towers + ContrastiveOutput(DotProduct, in-batch negatives by default)."""
+    from .retrieval import ContrastiveOutput, Encoder
+
+    assert isinstance(query_tower, Encoder), ValueError("The query tower should be an instance of `Encoder` class")
+    assert isinstance(candidate_tower, Encoder), ValueError("The query tower should be an instance of `Encoder` class")
+    if not outputs:
+        if not negative_samplers:
+            negative_samplers = ["in-batch"]
+        outputs = ContrastiveOutput(to_call=None, negative_samplers=negative_samplers, logits_temperature=logits_temperature,
+                                    **kwargs)
+    if isinstance(outputs, (list, tuple)):
+        if len(outputs) != 1:
+            raise NotImplementedError("multi-task outputs are outside the hot path")
+        outputs = outputs[0]
+    return RetrievalModelV2(query_tower, candidate_tower, outputs, schema=schema, candidate_id_tag=candidate_id_tag)
 
 
 def TwoTowerModel(schema: Schema, query_tower: MLP, item_tower: Optional[MLP] = None, query_tower_tag=Tags.USER,

@@ -282,7 +282,7 @@ def cross_layers(x0: np.ndarray, layers: Sequence[dict]) -> np.ndarray:
 
 
 def dcn_forward(batch, tables, feature_table, continuous, cross, deep, head, stacked: bool = True,
-                combiner: str = "mean") -> np.ndarray:
+                combiner: str = "mean", branch_order=("deep", "cross")) -> np.ndarray:
     """DCNModel (models/ranking.py:95-168): InputBlockV2 concat (sorted names over embeddings +
     continuous, inputs/base.py:216-341) -> CrossBlock -> deep MLP -> BinaryOutput."""
     feats = prepare_features(batch)
@@ -292,8 +292,12 @@ def dcn_forward(batch, tables, feature_table, continuous, cross, deep, head, sta
     x0 = concat_features(d)
     if stacked:
         body = mlp(cross_layers(x0, cross), deep)
-    else:  # connect_branch(..., aggregation="concat"): branches named by block -> cross first
-        body = np.concatenate([cross_layers(x0, cross), mlp(x0, deep)], axis=1)
+    else:
+        # connect_branch(CrossBlock(depth), deep_block, aggregation="concat") (models/ranking.py:159-166): a ParallelBlock
+        # keyed by the layers' auto names, concatenated in sorted-key order (core/aggregation.py:54-66).  Both are
+        # `sequential_block[_N]`; the deep block exists before CrossBlock(depth) is built, so normally [deep | cross].
+        br = {"cross": cross_layers(x0, cross), "deep": mlp(x0, deep)}
+        body = np.concatenate([br[branch_order[0]], br[branch_order[1]]], axis=1)
     return dense(body, head["kernel"], head.get("bias"), head.get("activation", "sigmoid"))
 
 

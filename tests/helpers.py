@@ -57,7 +57,7 @@ def oracle_dcn(model, batch):
     cross = [{"kernel": to_numpy(l.dense.kernel), "bias": None if l.dense.bias is None else to_numpy(l.dense.bias)}
              for l in body.cross.cross_layers]
     return oracle.dcn_forward(batch, tables, f2t, cont, cross, mlp_layers(body.deep), head_layer(model.prediction),
-                              stacked=body.stacked)
+                              stacked=body.stacked, branch_order=body.branch_order())
 
 
 def oracle_tower(tower, batch, l2=False):

@@ -123,3 +123,30 @@ def test_integration_doc_lists_every_exported_symbol():
     doc = (Path(__file__).resolve().parent.parent / "INTEGRATION.md").read_text()
     missing = [s for s in sorted(_cabi.declared_symbols()) if s not in doc]
     assert not missing, f"INTEGRATION.md does not mention: {missing}"
+
+
+def test_model_file_unpickler_refuses_everything_but_package_classes(tmp_path):
+    """model.pkl may only name classes defined in models_b200 (plus a few inert value types); builtins.eval,
+    functools.partial, torch.load or a module re-exported by one of the package's modules must be refused."""
+    import io as _io
+    import pickle
+
+    import torch
+
+    from models_b200 import io as mmio
+
+    def payload(mod, name):
+        return pickle.PROTO + bytes([4]) + b"\x8c" + bytes([len(mod)]) + mod.encode() + b"\x8c" + bytes([len(name)]) + name.encode() + b"\x93."
+
+    def load(mod, name):
+        return mmio._TensorUnpickler(_io.BytesIO(payload(mod, name)), tmp_path, {"variables": []}, torch.device("cpu")).load()
+
+    for mod, name in (("builtins", "eval"), ("builtins", "getattr"), ("builtins", "__import__"), ("functools", "partial"),
+                      ("torch", "load"), ("numpy", "load"), ("os", "system"), ("models_b200.csrc.build", "subprocess"),
+                      ("models_b200.csrc.build", "subprocess.run"), ("models_b200.io", "pickle")):
+        with pytest.raises(pickle.UnpicklingError, match="refusing to load"):
+            load(mod, name)
+    import models_b200 as mm
+
+    assert load("models_b200.schema", "Schema") is mm.Schema
+    assert load("collections", "OrderedDict").__name__ == "OrderedDict"
