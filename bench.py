@@ -858,8 +858,8 @@ def reference_arm(args, mm, datasets, cores):
     from oracle import oracle, oracle_torch
 
     torch.set_num_threads(cores)
-    B = args.batch
-    sample = min(args.cpu_sample, B)
+    B = args.batch or 65536
+    sample = min(args.cpu_sample or B, B)  # default: the SAME 65 536-sample step as our arm (same_config)
     schema = datasets.criteo_schema()
     rng = np.random.default_rng(4321)
     cat = schema.select_by_tag(mm.Tags.CATEGORICAL)
@@ -914,7 +914,9 @@ def reference_arm(args, mm, datasets, cores):
         "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic (uniform indices over bundled Criteo cardinalities)",
         "config": {"workload": "mm.DLRMModel Criteo-shape (26 cat, 13 dense, emb_dim 64), bottom [128,64], top [128,64,32]",
-                   "batch_per_step": sample, "note": "each step = a bounded sample of the 65536 batch"},
+                   "batch_per_gpu": sample, "global_batch": sample, "batch_per_step": sample,
+                   "note": "each step = one pass of the CPU restatement over the same 65536-sample batch shape as the GPU arm"
+                           if sample == B else "each step = a bounded sample of the batch"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{done} steps x {sample} samples; PyTorch-CPU restatement of the reference "
                                    "TF op sequence (TensorFlow/merlin-core not installable: no network)"},
