@@ -43,7 +43,8 @@ def main():
         sharded.build(dev)
         for name, t in tables.items():
             want_rows = t[rank::world] if se.is_sharded(name) else t
-            assert torch.equal(se.shards[name], want_rows), name
+            # a rank that owns no row of a tiny table (rows < world) still holds a 1-row placeholder shard
+            assert torch.equal(se.shards[name][: want_rows.shape[0]], want_rows), name
         batches = []
         for step in range(3):
             B = 512
