@@ -158,7 +158,7 @@ def dlrm_bytes_per_sample(T=26, D=64, id_bytes_total=104, P=64):
     return fused, gather
 
 
-NCU_FUSED_SUMMARY = "profiles/r02_ncu_fused_v2.txt"  # `ncu --set full` summary of THIS round's dominant kernel
+NCU_FUSED_SUMMARY = "profiles/r02_ncu_fused_operand.txt"  # `ncu --set full` summary of THIS round's dominant kernel
 
 
 def cpu_baseline_dlrm(model, feats_host, sample_rows, threads):
@@ -358,10 +358,12 @@ def dlrm_record(ctx):
     body = model.body
     slots = body.slots()
     names = body.embeddings.feature_names
-    tables = [body.embeddings.feature_to_table[f].table for f in names]
+    operand = body.use_operand_rows()  # split-bf16 table mirrors + operand-format bottom vector (what the step runs)
+    tables = [body.embeddings.feature_to_table[f].operand_mirror() if operand else body.embeddings.feature_to_table[f].table
+              for f in names]
     rows = [t.shape[0] for t in tables]
     slot_list = [slots[f] for f in names]
-    bottoms = [body.bottom_forward(d) for d in devs]
+    bottoms = [body.bottom_forward(d, operand_out=operand) for d in devs]
     width = body.output_width_before_top()
     a_out = torch.empty((B, 2 * ops.tc_padded_k(width)), dtype=torch.bfloat16, device=dev)
     # packed id views of the device-resident batches (same layout the graph reads)
@@ -372,7 +374,7 @@ def dlrm_record(ctx):
 
     def dominant(i):
         ops.dlrm_lookup_interact(tables, idx_lists[i % n_bufs], slot_list, rows, 64, bottoms[i % n_bufs],
-                                 slots["bottom_block"], a_out)
+                                 slots["bottom_block"], a_out, operand_rows=operand)
 
     kern_ms = event_times(dominant, args.steps, args.warmup)
 
@@ -407,7 +409,10 @@ def dlrm_record(ctx):
             "batch_per_gpu": B, "global_batch": B * world,
             "index_dtype": f"packed per table (8 x u8, 10 x u16, 8 x u24 = {id_bytes_total} B/sample; Model.id_bytes())",
             "table_rows": 45621194,
-            "table_gb": 11.68, "parallelism": f"replicas x{world} (no data-path collective)",
+            "table_gb": 11.68,
+            "table_mirror": ("split-bf16 copy of every table (ops.split_rows, +11.68 GB): the lookup+interaction kernel loads MMA "
+                             "fragments with ldmatrix instead of splitting fp32 rows per sample" if operand else "off (MM_TABLE_MIRROR=0)"),
+            "parallelism": f"replicas x{world} (no data-path collective)",
             "l2": f"inputs larger than L2: 11.7 GB of tables, {n_bufs} rotating input batches, no flush",
             "runtime": f"CUDA graph replay, {depth} graph instances on {depth} streams (model.pipeline): independent steps overlap; "
                        "input refresh = one D2D copy of the packed batch per step",
@@ -633,10 +638,13 @@ def sharded_record(ctx):
         serial_ms = timed_serial(cf, packed_dev, steps)
         # the fused lookup + interaction kernel alone
         body = model.body
+        operand = body.use_operand_rows()
         bottoms = [body.bottom_forward(d) for d in devs]
+        bottoms_k = [body.bottom_forward(d, operand_out=True) for d in devs] if operand else bottoms
         slots = body.slots()
         k_out = torch.empty((B, 2 * ops.tc_padded_k(body.output_width_before_top())), dtype=torch.bfloat16, device=dev)
-        kern_ms = event_times(lambda i: se.lookup_interact(devs[i % n_bufs], slots, bottoms[i % n_bufs], k_out), max(5, steps // 2))
+        kern_ms = event_times(lambda i: se.lookup_interact(devs[i % n_bufs], slots, bottoms_k[i % n_bufs], k_out, operand_rows=operand),
+                              max(5, steps // 2))
         e2e_steps = max(5, min(steps, 20))
         e2e_ms, _ = timed_e2e(ctx, pf, hbs, e2e_steps, args.pipeline_depth)
         # exact NVLink payload of this rank's batch 0: rows whose owner is another rank
@@ -652,6 +660,7 @@ def sharded_record(ctx):
         rec["placements"][label] = {
             "replicate_below_rows": below, "tables_sharded": n_sharded, "tables_replicated": 26 - n_sharded,
             "shard_gb_per_gpu": float(se.arena.numel() * 4 / 1e9) if se.arena is not None else 0.0,
+            "table_mirror": bool(operand),
             "parity": "bit-exact vs the unsharded model on every rank" if int(flag.item()) == 1 else "MISMATCH",
             "graph_replay_parity": bool(graph_ok),
             "value": world * B * steps / (elapsed_ms * 1e-3), "unit": "samples/s", "ms_per_step": elapsed_ms / steps,

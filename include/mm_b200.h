@@ -198,9 +198,18 @@ typedef struct {
   const float* const* peer_weights_host; /* NULL, or `world` shard pointers (host array) */
 } mm_lookup_table;
 
+/* row_format: MM_ROWS_F32 — `weights` / `bottom` are fp32 rows; MM_ROWS_OPERAND (D = 64) — they are split-bf16 rows
+ * [hi(0..D) | lo(0..D)] (mm_split_rows with Kp = D: the operand format of every tensor-core layer here; same row size),
+ * so the kernel loads its MMA fragments with ldmatrix and the per-sample bf16 split and operand moves (more than a
+ * third of its instructions) disappear.  Needs the split-bf16 output (`out_split`); same arithmetic as MM_ROWS_F32
+ * (the k order inside an MMA differs, so results agree to fp32 rounding, not bit for bit).  The price is a second
+ * copy of the tables in HBM (bottom: mm_mlp_tc_operand_out writes it directly). */
+#define MM_ROWS_F32 0
+#define MM_ROWS_OPERAND 1
 int mm_dlrm_lookup_interact(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, int rank, int world,
                             const float* bottom, int64_t bottom_stride, int bottom_slot, float* out,
-                            int64_t out_stride, void* out_split, int out_Kp, int32_t* oob_count, void* stream);
+                            int64_t out_stride, void* out_split, int out_Kp, int32_t* oob_count, int row_format,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4  Dense layer, exact fp32 on CUDA cores:  out = act(x @ W + bias).
@@ -262,6 +271,14 @@ int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* c
               const int* widths, const float* const* bias, const int* acts, float* out,
               int64_t out_stride, const float* head_w, float head_b, int head_act, float* head_out,
               void* stream);
+
+/* mm_mlp_tc whose last layer also (or only: out may be NULL) leaves its rows as split-bf16 rows
+ * out_operand (M, 2 * widths[n-1]) bf16 = [hi | lo] per row (widths[n-1] % 4 == 0; the mm_split_rows layout when the
+ * width is a multiple of 64) — the bottom tower of a DLRM hands its vector to
+ * mm_dlrm_lookup_interact(row_format = MM_ROWS_OPERAND) this way, without a fp32 round trip. */
+int mm_mlp_tc_operand_out(const void* a_split, int64_t M, int K, int n_layers, const void* const* w_split,
+                          const int* widths, const float* const* bias, const int* acts, float* out,
+                          int64_t out_stride, void* out_operand, void* stream);
 
 /* Whole-op entry points over fp32 Keras-layout weights (kernel (in, out) row-major, bias (out,) or
  * NULL) and a caller-provided workspace — for callers outside this package's Python host; nothing is

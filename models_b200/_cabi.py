@@ -79,7 +79,7 @@ SIGNATURES = {
     "mm_cross_combine": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _i64, _vp, _i64, _vp]),
     "mm_dot_interaction": (_i, [_vp, _i64, _i, _i, _i64, _vp, _i, _i64, _i, _vp, _i64, _vp, _i, _vp]),
     "mm_dlrm_gather_interact": (_i, [_tables, _i, _i, _i64, _i, _vp, _i64, _i, _vp, _i64, _vp, _i, _vp, _vp]),
-    "mm_dlrm_lookup_interact": (_i, [C.POINTER(LookupTable), _i, _i64, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i, _vp, _vp]),
+    "mm_dlrm_lookup_interact": (_i, [C.POINTER(LookupTable), _i, _i64, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i, _vp, _i, _vp]),
     "mm_dense_fp32": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64, _vp]),
     "mm_tc_padded_k": (_i, [_i]),
     "mm_tc_padded_n": (_i, [_i]),
@@ -96,6 +96,8 @@ SIGNATURES = {
     "mm_mlp_tc_supported": (_i, [_i, _i, C.POINTER(C.c_int), _i]),
     "mm_mlp_tc": (_i, [_vp, _i64, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
                        _vp, _i64, _vp, _f, _i, _vp, _vp]),
+    "mm_mlp_tc_operand_out": (_i, [_vp, _i64, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_int), _vp, _i64, _vp, _vp]),
     "mm_rowwise_dot": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
     "mm_catalog_workspace_bytes": (_i64, [_i64, _i64, _i]),
     "mm_catalog_score": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp]),

@@ -51,9 +51,29 @@ def last_dense_path() -> str:
     return _LAST_PATH[0]
 
 
+_TABLE_MIRROR = [None]  # None: decide from MM_TABLE_MIRROR (default on); True / False: forced
+
+
+def set_table_mirror(on: Optional[bool]) -> None:
+    """Split-bf16 mirrors of the embedding tables for the fused DLRM kernel (D = 64): a second copy of every table in
+    HBM; the kernel then loads MMA fragments with ldmatrix instead of splitting fp32 rows per sample.
+    None = environment default (MM_TABLE_MIRROR, on unless it is '0')."""
+    _TABLE_MIRROR[0] = on
+
+
+def table_mirror() -> bool:
+    if _TABLE_MIRROR[0] is not None:
+        return bool(_TABLE_MIRROR[0])
+    import os
+
+    return os.environ.get("MM_TABLE_MIRROR", "1") != "0"
+
+
 def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: Optional[torch.Tensor] = None,
-                    K: Optional[int] = None) -> torch.Tensor:
-    """A chain of Dense layers on one input matrix.
+                    K: Optional[int] = None, operand_out: bool = False) -> torch.Tensor:
+    """A chain of Dense layers on one input matrix.  operand_out=True: the result rows come back as bf16 split rows
+    (B, 2*Kp) = [hi | lo] (the interaction kernel's operand format) — directly from the whole-tower kernel's last
+    epilogue when it applies, by one mm_split_rows pass over the fp32 result otherwise.
 
     tensor-core engine ("auto"/"tc"): x is split once into bf16 (hi, lo); every layer is one
     tcgen05 launch whose epilogue (bias + activation) directly emits the NEXT layer's split-bf16
@@ -73,7 +93,7 @@ def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: 
         for l in layers:
             x = l(x)
         _LAST_PATH[0] = "fp32"
-        return x
+        return ops.split_rows(x.contiguous()) if operand_out else x
     if a_split is None:
         a = ops.split_rows(x)
     out = None
@@ -93,12 +113,16 @@ def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: 
         if fuse_head:
             out = torch.empty((B, 1), dtype=torch.float32, device=device)
             kw = dict(head_w=head.kernel.reshape(-1), head_b=head.bias_value(), head_act=head.activation, head_out=out)
+        elif operand_out and widths[-1] % 64 == 0:
+            out = torch.empty((B, 2 * widths[-1]), dtype=torch.bfloat16, device=device)  # split rows [hi | lo]
+            kw = dict(out_operand=out)
+            operand_out = False  # done by the kernel
         else:
             out = torch.empty((B, widths[-1]), dtype=torch.float32, device=device)
             kw = dict(out=out)
         ops.mlp_tc(a, K, [l.split_kernel() for l in layers], widths, [l.bias for l in layers],
                    [l.activation for l in layers], **kw)
-        return out
+        return ops.split_rows(out) if operand_out else out
     _LAST_PATH[0] = "dense_tc"
     for i, l in enumerate(layers):
         last = i == len(layers) - 1
@@ -116,7 +140,7 @@ def run_dense_chain(x: Optional[torch.Tensor], layers: "List[_Dense]", a_split: 
             nxt = l.split_buffer(B, device)
         ops.dense_tc(a, K, l.split_kernel(), l.units, l.bias, l.activation, passes=3, out_f32=out, out_split=nxt)
         a, K = nxt, l.units
-    return out
+    return ops.split_rows(out) if operand_out else out
 
 
 class _Dense(Block):
@@ -350,7 +374,7 @@ class MLP(SequentialBlock):
 
     _TRANSIENT = {"_chain": None, "_chain_key": None}
 
-    def call(self, inputs, training: bool = False, **kwargs):
+    def call(self, inputs, training: bool = False, operand_out: bool = False, **kwargs):
         if self.dropout and training:
             raise NotImplementedError("dropout in training mode is outside the forward hot path")
         if self.has_normalization and training:
@@ -370,8 +394,11 @@ class MLP(SequentialBlock):
         width = K if x is None else x.shape[1]
         self.build_from_width(width, a.device if x is None else x.device)
         layers, tail = self.chain()
-        out = run_dense_chain(x, layers, a_split=a, K=K) if x is None else run_dense_chain(x, layers)
-        return out if tail is None else tail(out)
+        if tail is not None:  # a trailing normalization runs on fp32 rows
+            out = tail(run_dense_chain(x, layers, a_split=a, K=K) if x is None else run_dense_chain(x, layers))
+            return ops.split_rows(out) if operand_out else out
+        return (run_dense_chain(x, layers, a_split=a, K=K, operand_out=operand_out) if x is None
+                else run_dense_chain(x, layers, operand_out=operand_out))
 
     def oracle_layers(self):
         return [{"kernel": l.kernel.cpu().numpy(), "bias": None if l.bias is None else l.bias.cpu().numpy(),
@@ -628,14 +655,27 @@ class DLRM(Block):
         F = len(self.embeddings.feature_names) + (1 if self.bottom_block is not None else 0)
         return 2 <= F <= 32 and self.embedding_dim in (16, 32, 64, 128)
 
-    def bottom_forward(self, inputs: TabularData) -> Optional[torch.Tensor]:
+    def bottom_forward(self, inputs: TabularData, operand_out: bool = False) -> Optional[torch.Tensor]:
+        """Bottom MLP over the continuous columns: (B, D) fp32, or — operand_out — the same rows in the interaction
+        kernel's operand format (written by the tower kernel's last epilogue, no fp32 round trip)."""
         if self.bottom_block is None:
             return None
-        return self.bottom_block(self.continuous(inputs))
+        return self.bottom_block(self.continuous(inputs), operand_out=operand_out)
 
-    def interaction_forward(self, inputs: TabularData, bottom: Optional[torch.Tensor], as_split: bool = False) -> torch.Tensor:
+    def use_operand_rows(self, as_split: bool = True) -> bool:
+        """Operand-format table mirrors + operand-format bottom vector for the fused kernel: only on the production
+        path (split-bf16 output feeding the top MLP), when mirrors are enabled (blocks.set_table_mirror)."""
+        ok = bool(as_split and self.fused and table_mirror() and self.can_emit_split() and self.bottom_block is not None
+                  and self.top_block is not None and self.embedding_dim == 64)
+        if ok and self.sharded is not None:
+            ok = bool(self.sharded.mirrors)  # built collectively in ShardedEmbeddings.build (never lazily inside a step)
+        return ok
+
+    def interaction_forward(self, inputs: TabularData, bottom: Optional[torch.Tensor], as_split: bool = False,
+                            operand_rows: bool = False) -> torch.Tensor:
         """[bottom |] interactions, (B, P + F(F-1)/2) fp32 — or, with as_split, the split-bf16 operand
-        (B, 2*Kp) of the top MLP's first tensor-core layer, written directly by the kernel."""
+        (B, 2*Kp) of the top MLP's first tensor-core layer, written directly by the kernel.  operand_rows: `bottom` is in
+        operand format and the tables' operand-format mirrors are used (see use_operand_rows)."""
         self.build(next(iter(inputs.values())).device)
         D = self.embedding_dim
         slots = self.slots()
@@ -659,7 +699,7 @@ class DLRM(Block):
             if with_prefix == (bottom is not None) and self.can_emit_split():
                 # row-sharded tables, product path: the lookup is part of the interaction kernel — rows owned
                 # by other ranks are read over NVLink straight into shared memory (no exchange, no barrier)
-                self.sharded.lookup_interact(inputs, slots, bottom, out, oob)
+                self.sharded.lookup_interact(inputs, slots, bottom, out, oob, operand_rows=operand_rows)
                 emb.finish_check(oob)
                 return out
             # staged protocol (index all-gather + owner-computes NVLink push + barrier) rebuilds the (B,F,D)
@@ -676,9 +716,9 @@ class DLRM(Block):
             if self.can_emit_split():
                 # ids travel at their own width (packed uint8 / uint16 / 24-bit host batches, int32, int64)
                 idx = [i if i.dtype in (torch.uint8, torch.uint16) else _as_index(i).reshape(-1) for i in raw]
-                tabs = [emb.feature_to_table[f].table for f in feats]
+                tabs = [emb.feature_to_table[f].operand_mirror() if operand_rows else emb.feature_to_table[f].table for f in feats]
                 ops.dlrm_lookup_interact(tabs, idx, [slots[f] for f in feats], [t.shape[0] for t in tabs], D, bottom,
-                                         slots.get("bottom_block", -1), out, oob)
+                                         slots.get("bottom_block", -1), out, oob, operand_rows=operand_rows)
             else:
                 idx = [_as_index(i).reshape(-1) for i in raw]
                 if len({i.dtype for i in idx}) > 1:

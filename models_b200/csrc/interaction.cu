@@ -22,7 +22,7 @@ namespace imma2 {  // interaction_v2.cu: second-generation warp-per-sample kerne
 template <int MODE>
 int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float* prefix, int64_t prefix_stride, int P,
            int bottom_slot, int64_t B, int F, int D, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
-           int32_t* oob, cudaStream_t st, const char* who);
+           int32_t* oob, cudaStream_t st, const char* who, bool presplit);
 }
 namespace imma {  // interaction_mma.cu: warp-level mma.sync path (F <= 32, D in {16,32,64,128})
 template <int MODE, typename IdxT>
@@ -243,8 +243,12 @@ extern "C" {
 
 int mm_dlrm_lookup_interact(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, int rank, int world,
                             const float* bottom, int64_t bottom_stride, int bottom_slot, float* out,
-                            int64_t out_stride, void* out_split, int out_Kp, int32_t* oob_count, void* stream) {
+                            int64_t out_stride, void* out_split, int out_Kp, int32_t* oob_count, int row_format,
+                            void* stream) {
   const char* who = "mm_dlrm_lookup_interact";
+  MM_REQUIRE(row_format == MM_ROWS_F32 || row_format == MM_ROWS_OPERAND, MM_ERR_ARG, "%s: bad row_format", who);
+  MM_REQUIRE(row_format == MM_ROWS_F32 || (out_split && !out), MM_ERR_ARG,
+             "%s: operand-format rows need the split-bf16 output (the fp32 prefix cannot be rebuilt exactly)", who);
   MM_REQUIRE(tables_host && n_tables > 0 && (out || out_split) && B >= 0, MM_ERR_ARG, "%s: bad table list / null out / B<0", who);
   MM_REQUIRE(!(out && out_split), MM_ERR_ARG, "%s: give either out or out_split", who);
   MM_REQUIRE(D == 16 || D == 32 || D == 64 || D == 128, MM_ERR_UNSUPPORTED, "%s: D must be 16, 32, 64 or 128", who);
@@ -295,7 +299,8 @@ int mm_dlrm_lookup_interact(const mm_lookup_table* tables_host, int n_tables, in
              "%s: out_Kp must be a multiple of 64 >= the row width, out_split 16-B aligned", who);
   if (B == 0) return MM_OK;
   const int rc = mm::imma2::launch<1>(nullptr, 0, lk, bottom, bottom_stride, P, bottom ? bottom_slot : -1, B, F, D, out,
-                                      out_stride, out_split, out_Kp, oob_count, (cudaStream_t)stream, who);
+                                      out_stride, out_split, out_Kp, oob_count, (cudaStream_t)stream, who,
+                                      row_format == MM_ROWS_OPERAND);
   MM_REQUIRE(rc != MM_ERR_UNSUPPORTED, MM_ERR_UNSUPPORTED, "%s: shape outside the fused kernel (F=%d, D=%d)", who, F, D);
   return rc;
 }
@@ -324,7 +329,7 @@ int mm_dot_interaction(const float* x, int64_t B, int F, int D, int64_t x_stride
     memset(&lk, 0, sizeof(lk));
     lk.world = 1;
     const int rc2 = mm::imma2::launch<0>(x, x_stride, lk, prefix, prefix_stride, P, -1, B, F, D, out, out_stride, out_split,
-                                         out_Kp, nullptr, (cudaStream_t)stream, "mm_dot_interaction");
+                                         out_Kp, nullptr, (cudaStream_t)stream, "mm_dot_interaction", false);
     if (rc2 != MM_ERR_UNSUPPORTED) return rc2;
   }
   if (!self_interaction) {
@@ -391,7 +396,7 @@ int mm_dlrm_gather_interact(const mm_gather_table* tables_host, int n_tables, in
       lk.idx_bytes[r] = idx_dtype == MM_I32 ? 4 : 8;
     }
     const int rc2 = mm::imma2::launch<1>(nullptr, 0, lk, bottom, bottom_stride, P, bottom ? bottom_slot : -1, B, F, D, out,
-                                         out_stride, out_split, out_Kp, oob_count, st, "mm_dlrm_gather_interact");
+                                         out_stride, out_split, out_Kp, oob_count, st, "mm_dlrm_gather_interact", false);
     if (rc2 != MM_ERR_UNSUPPORTED) return rc2;
   }
   {

@@ -97,31 +97,40 @@ __device__ __forceinline__ void sts32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+
 struct RawIdx {
   uint32_t a, b, sh;  // the aligned word(s) holding an id, and the bit offset of the id inside `a`
 };
 
-__device__ __forceinline__ void mma_bf16_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(b0));
-}
-
-// K8 (negative result, not instantiated): issue the Gram matrix as m16n8k8 MMAs.  With k16 every bf16x2
-// register must sit both in an A quad {X[g],X[g+8]} x {k-lo,k-hi} and in a B pair {k-lo,k-hi} of one row —
-// two incompatible adjacencies that cost ~180 register moves per sample (ncu, r2a).  k8 operands are an A
-// pair and a single B register: no moves, but twice as many MMAs, and HMMA.1688 occupies the legacy tensor
-// pipe as long as HMMA.16816 (8 cycles): 0.128 ms instead of 0.103 ms (profiles/r02_notes.md).
+// Negative result kept as a note (the code is gone): issuing the Gram matrix as m16n8k8 MMAs.  With k16 every bf16x2
+// register must sit both in an A quad {X[g],X[g+8]} x {k-lo,k-hi} and in a B pair {k-lo,k-hi} of one row — two
+// incompatible adjacencies that cost ~180 register moves per sample (ncu, r2a).  k8 operands are an A pair and a single
+// B register: no moves, but twice as many MMAs, and HMMA.1688 occupies the legacy tensor pipe as long as HMMA.16816
+// (8 cycles per SMSP): 0.128 ms instead of 0.103 ms (profiles/r02_notes.md §a).
+//
+// PS ("pre-split", D = 64): the staged rows are split-bf16 rows [hi(0..D) | lo(0..D)] — the operand format of every
+// tensor-core layer of this library (mm_split_rows) — read from a second copy of the tables in HBM; the bottom vector
+// arrives in the same format from the tower kernel.  The rows land in shared memory with the 128-byte XOR swizzle
+// (16-byte chunk c of row r at chunk c ^ (r & 7)) and the MMA fragments are loaded by ldmatrix.x4: per 16-wide k-step
+// four loads give the A quads (hi and lo, two m-tiles) and four the B pairs (hi and lo, four n-tiles), each already in the
+// register shape HMMA wants.  Per sample: 32 LDSM + 16 LOP3 + 72 HMMA instead of 16 LDS.128 + 192 split instructions
+// + ~180 operand moves + 72 HMMA.  Same values as the in-kernel split => bit-identical output.
+// (A first attempt kept the lane-private LDS.128 scheme with hi and lo interleaved per chunk: fewer instructions, but
+// the A quads still had to be assembled with moves and nothing overlapped the load -> HMMA latency: 0.116 ms vs 0.104.)
 // NBUF sample buffers per warp: NBUF-1 samples in flight behind the one being computed.  The product uses 2 with
 // 16 warps, for local tables and for rows that come over NVLink alike.  NBUF = 3 / 4 (10 / 7 warps, ids through a
 // shared-memory ring) exist for experiments (MM_IMMA_NBUF): measured on 2 x B200 they are never faster — what looked
 // like remote latency was hot rows of tiny sharded tables serialising on single cache lines of the owner
 // (profiles/r02_notes.md §b); with those tables replicated, 16 warps x 1 sample in flight reach 420-580 GB/s.
-template <int MODE, int KD /* embedding dim: 16, 32, 64, 128 */, int NWARPS /* launch bound */, bool K8, int NBUF>
+template <int MODE, int KD /* embedding dim: 16, 32, 64, 128 */, int NWARPS /* launch bound */, bool PS, int NBUF>
 __global__ void __launch_bounds__(32 * NWARPS, 1)
 interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
+  extern __shared__ __align__(256) uint8_t smem_raw[];
   constexpr int D = KD, KS = KD / 16;
+  static_assert(!PS || KD == 64, "operand-format rows: D = 64");
   constexpr int C = KD / 4;           // 16-byte chunks per row
   constexpr int L = C < 8 ? C : 8;    // lanes per row in the copy loop
   constexpr int J = C / L;            // copies per lane and row
@@ -216,8 +225,11 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
   // ---- copy-loop constants of this lane
   const int cl = lane & (L - 1), rl = lane / L;
   const uint32_t src_lane_off = (uint32_t)cl * 16u;
+  // fp32 rows: chunk XOR 4 on odd rows; PS rows (row = 4i + rl, 8 lanes per 128-byte half): chunk ^ (row & 7) with
+  // row & 7 = rl + 4 (i & 1) -> one constant for even i, one for odd i
   const uint32_t dst_lane_off =
-      (uint32_t)rl * (D * 4) + (uint32_t)((SWZ ? (cl ^ ((rl & 1) << 2)) : cl) * 16);
+      (uint32_t)rl * (D * 4) + (uint32_t)((PS ? (cl ^ rl) : SWZ ? (cl ^ ((rl & 1) << 2)) : cl) * 16);
+  const uint32_t dst_lane_off_odd = (uint32_t)rl * (D * 4) + (uint32_t)((cl ^ (rl + 4)) * 16);  // PS, odd i
   const uint8_t* x_ptr = MODE == 0 ? reinterpret_cast<const uint8_t*>(p.x + s0 * p.x_stride) + (size_t)rl * (D * 4) + src_lane_off
                                    : nullptr;
   const long long x_step = (long long)nw * p.x_stride * 4;
@@ -264,8 +276,9 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
           const uint32_t hi = __shfl_sync(0xffffffffu, src_hi, row);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(((uintptr_t)hi << 32) | lo) + src_lane_off;
           const bool on = row < live_rows;
+          const uint32_t xd = (PS && (i & 1)) ? xs - dst_lane_off + dst_lane_off_odd : xs;
 #pragma unroll
-          for (int j = 0; j < J; ++j) cp_async16_if(on, xs + (uint32_t)(i * R * D * 4 + j * L * 16), src + j * L * 16);
+          for (int j = 0; j < J; ++j) cp_async16_if(on, xd + (uint32_t)(i * R * D * 4 + j * L * 16), src + j * L * 16);
         }
       }
     } else {
@@ -300,6 +313,22 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
     pe[q] = base + sb;
     po[q] = base - sb;
   }
+  // ---- PS: ldmatrix row addresses.  Lane l supplies row (l & 7) of matrix (l >> 3).
+  //   A quad of m-tile mt (rows 16mt..): matrices (rows +0..7, k-lo) (rows +8..15, k-lo) (rows +0..7, k-hi) (rows +8..15, k-hi)
+  //   B pairs of n-tiles 2u, 2u+1 (rows 16u..): matrices (rows +0..7, k-lo) (rows +0..7, k-hi) (rows +8..15, k-lo) (rows +8..15, k-hi)
+  // k-lo / k-hi = chunks 2ks / 2ks+1 of the hi half (+128 bytes: lo half).  With 256-byte aligned buffers the byte offset
+  // is row*256 | ((chunk ^ (row & 7)) << 4), and (2ks + b) ^ x = (2ks) ^ (b ^ x): one XOR with 32*ks per k-step.
+  uint32_t la[2], lb[2];
+  {
+    const int mi = lane >> 3, j = lane & 7;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int ra = min(16 * u + (mi & 1) * 8 + j, F - 1), rbq = min(16 * u + (mi >> 1) * 8 + j, F - 1);
+      la[u] = (uint32_t)ra * 256u | (uint32_t)((((mi >> 1) ^ ra) & 7) << 4);
+      lb[u] = (uint32_t)rbq * 256u | (uint32_t)((((mi & 1) ^ rbq) & 7) << 4);
+    }
+  }
+
   // ---- output constants: accumulator (i, j) with i = 8*qi + g, j = 8*nt + 2t + e lands at
   // P + i(2F-i-1)/2 + (j-i-1) = rb[qi] + 8*nt + e   (floats); valid iff i < j < F
   int rb[4];
@@ -357,6 +386,37 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[ti][c] = 0.0f;
 
+      if (PS) {
+        const uint32_t a0b = xs + la[0], a1b = xs + la[1], b0b = xs + lb[0], b1b = xs + lb[1];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+          const uint32_t kx = 32u * ks;
+          ldsm_x4(a0b ^ kx, ah[0][0], ah[0][1], ah[0][2], ah[0][3]);
+          ldsm_x4((a0b ^ kx) + 128u, al[0][0], al[0][1], al[0][2], al[0][3]);
+          ldsm_x4(a1b ^ kx, ah[1][0], ah[1][1], ah[1][2], ah[1][3]);
+          ldsm_x4((a1b ^ kx) + 128u, al[1][0], al[1][1], al[1][2], al[1][3]);
+          ldsm_x4(b0b ^ kx, bh[0][0], bh[0][1], bh[1][0], bh[1][1]);
+          ldsm_x4((b0b ^ kx) + 128u, bl[0][0], bl[0][1], bl[1][0], bl[1][1]);
+          ldsm_x4(b1b ^ kx, bh[2][0], bh[2][1], bh[3][0], bh[3][1]);
+          ldsm_x4((b1b ^ kx) + 128u, bl[2][0], bl[2][1], bl[3][0], bl[3][1]);
+#pragma unroll
+          for (int ti = 0; ti < 6; ++ti) {
+            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+            mma_bf16_16816(acc[ti], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bl[nt][0], bl[nt][1]);
+          }
+#pragma unroll
+          for (int ti = 0; ti < 6; ++ti) {
+            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+            mma_bf16_16816(acc[ti], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh[nt][0], bh[nt][1]);
+          }
+#pragma unroll
+          for (int ti = 0; ti < 6; ++ti) {
+            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+            mma_bf16_16816(acc[ti], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bh[nt][0], bh[nt][1]);
+          }
+        }
+      } else {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t h[4][2], l[4][2];
@@ -368,52 +428,40 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
         }
         // tile (mt, nt): A = rows q = 2mt, 2mt+1; B (n-tile nt = rows 8nt + g) = the registers of q = nt.
         // Pass-major order: six independent accumulators between dependent MMAs.
-        if (K8) {
 #pragma unroll
-          for (int kh = 0; kh < 2; ++kh) {
-#pragma unroll
-            for (int ti = 0; ti < 6; ++ti) {
-              const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-              mma_bf16_1688(acc[ti], h[2 * mt][kh], h[2 * mt + 1][kh], l[nt][kh]);
-            }
-#pragma unroll
-            for (int ti = 0; ti < 6; ++ti) {
-              const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-              mma_bf16_1688(acc[ti], l[2 * mt][kh], l[2 * mt + 1][kh], h[nt][kh]);
-            }
-#pragma unroll
-            for (int ti = 0; ti < 6; ++ti) {
-              const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-              mma_bf16_1688(acc[ti], h[2 * mt][kh], h[2 * mt + 1][kh], h[nt][kh]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int ti = 0; ti < 6; ++ti) {
-            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-            mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], l[nt][0], l[nt][1]);
-          }
-#pragma unroll
-          for (int ti = 0; ti < 6; ++ti) {
-            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-            mma_bf16_16816(acc[ti], l[2 * mt][0], l[2 * mt + 1][0], l[2 * mt][1], l[2 * mt + 1][1], h[nt][0], h[nt][1]);
-          }
-#pragma unroll
-          for (int ti = 0; ti < 6; ++ti) {
-            const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
-            mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], h[nt][0], h[nt][1]);
-          }
+        for (int ti = 0; ti < 6; ++ti) {
+          const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+          mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], l[nt][0], l[nt][1]);
         }
+#pragma unroll
+        for (int ti = 0; ti < 6; ++ti) {
+          const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+          mma_bf16_16816(acc[ti], l[2 * mt][0], l[2 * mt + 1][0], l[2 * mt][1], l[2 * mt + 1][1], h[nt][0], h[nt][1]);
+        }
+#pragma unroll
+        for (int ti = 0; ti < 6; ++ti) {
+          const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
+          mma_bf16_16816(acc[ti], h[2 * mt][0], h[2 * mt + 1][0], h[2 * mt][1], h[2 * mt + 1][1], h[nt][0], h[nt][1]);
+        }
+      }
       }
 
       // ---- the prefix row leaves the buffer before the buffer becomes the output stage
       float4 pfx = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.P > 0 && lane < C) pfx = lds128(xs + pfx_off);
+      if (PS) {  // chunk (lane & 7) of the hi (lanes 0-7) / lo (lanes 8-15) half of the bottom row, un-swizzled
+        if (p.P > 0 && lane < 16)
+          pfx = lds128(xs + (uint32_t)prow * 256u + ((uint32_t)(lane & 8) << 4) + (uint32_t)((((lane & 7) ^ prow) & 7) << 4));
+      } else if (p.P > 0 && lane < C) pfx = lds128(xs + pfx_off);
       __syncwarp();  // every lane is done reading the sample
-      if (p.P > 0 && lane < C)
+      if (PS) {
+        // split-bf16 prefix: the hi and lo halves of the bottom row go straight to the hi / lo halves of the output row
+        if (p.P > 0 && lane < 16)
+          *reinterpret_cast<float4*>(osplit + ((lane & 8) ? p.out_Kp : 0) + 8 * (lane & 7)) = pfx;
+      } else if (p.P > 0 && lane < C) {
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(xs + lane * 16u), "f"(pfx.x), "f"(pfx.y), "f"(pfx.z),
                      "f"(pfx.w)
                      : "memory");
+      }
 #pragma unroll
       for (int ti = 0; ti < 6; ++ti) {
         const int mt = ti < 4 ? 0 : 1, nt = ti < 4 ? ti : ti - 2;
@@ -432,7 +480,7 @@ interact_v2_kernel(const __grid_constant__ LookupParams lk, const Params p) {
       // ---- coalesced row store
       if (p.out_split) {
         const int groups = p.out_Kp >> 3;  // 8 columns = one 16-byte bf16 store for hi and one for lo
-        for (int gi = lane; gi < groups; gi += 32) {
+        for (int gi = (PS ? (p.P >> 3) : 0) + lane; gi < groups; gi += 32) {  // PS: the prefix groups are already out
           const float4 a = lds128(xs + (uint32_t)gi * 32u), b = lds128(xs + (uint32_t)gi * 32u + 16u);
           uint32_t hh[4], ll[4];
           split_pair(a.x, a.y, hh[0], ll[0]);
@@ -472,9 +520,9 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int MODE, int KD, int NWARPS, bool K8, int NBUF>
+template <int MODE, int KD, int NWARPS, bool PS, int NBUF>
 static int launch_kd(const LookupParams& lk, const Params& p, size_t smem, unsigned grid, cudaStream_t st, const char* who) {
-  auto kern = interact_v2_kernel<MODE, KD, NWARPS, K8, NBUF>;
+  auto kern = interact_v2_kernel<MODE, KD, NWARPS, PS, NBUF>;
   static bool attr_set[64] = {};  // per device: function attributes belong to the device's copy of the kernel
   int dev = 0;
   cudaGetDevice(&dev);
@@ -495,7 +543,8 @@ static int launch_kd(const LookupParams& lk, const Params& p, size_t smem, unsig
 template <int MODE>
 int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float* prefix, int64_t prefix_stride, int P,
            int bottom_slot, int64_t B, int F, int D, float* out_f32, int64_t out_stride, void* out_split, int out_Kp,
-           int32_t* oob, cudaStream_t st, const char* who) {
+           int32_t* oob, cudaStream_t st, const char* who, bool presplit) {
+  if (presplit && (MODE != 1 || !out_split || D != 64)) return MM_ERR_UNSUPPORTED;
   if (F < 2 || F > 32 || (D != 16 && D != 32 && D != 64 && D != 128)) return MM_ERR_UNSUPPORTED;
   if (P != 0 && P != D) return MM_ERR_UNSUPPORTED;
   if (out_f32 && out_split) return MM_ERR_UNSUPPORTED;
@@ -523,7 +572,7 @@ int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float
   p.oob_count = oob;
   p.stage_cols = out_split ? (unsigned)out_Kp : (unsigned)((OW + 3) & ~3);
   const unsigned in_bytes = (unsigned)(rows * D * 4), stage_bytes = p.stage_cols * 4u;
-  p.buf_bytes = ((in_bytes > stage_bytes ? in_bytes : stage_bytes) + 127u) & ~127u;
+  p.buf_bytes = ((in_bytes > stage_bytes ? in_bytes : stage_bytes) + 255u) & ~255u;  // 256-B aligned (ldmatrix address XOR)
   bool remote = false;
   if (MODE == 1 && lk.world > 1)
     for (int r = 0; r < rows; ++r) remote = remote || lk.sharded[r];
@@ -550,12 +599,16 @@ int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float
   const long long sms = sm_count();
   long long want = (B + warps - 1) / warps;
   const unsigned grid = (unsigned)(want < sms ? want : sms);
-  // instantiated variants: local tables = 16 (or 12) warps x 2 buffers; NVLink rows = 12-warp bound x 4 buffers
-#define MM_V2_LAUNCH(KD)                                                                                   \
-  (nbuf == 4 ? launch_kd<MODE, KD, 12, false, 4>(lk, p, smem, grid, st, who)                               \
-   : nbuf == 3 ? launch_kd<MODE, KD, 12, false, 3>(lk, p, smem, grid, st, who)                             \
-             : (warps > 12 ? launch_kd<MODE, KD, 16, false, 2>(lk, p, smem, grid, st, who)                 \
-                           : launch_kd<MODE, KD, 12, false, 2>(lk, p, smem, grid, st, who)))
+  // instantiated variants: 16 (or 12) warps x 2 buffers; operand-format rows (presplit) only with 2 buffers;
+  // 3 / 4 buffers (id ring) for experiments
+#define MM_V2_LAUNCH(KD)                                                                                                \
+  (nbuf == 4 ? launch_kd<MODE, KD, 12, false, 4>(lk, p, smem, grid, st, who)                                            \
+   : nbuf == 3 ? launch_kd<MODE, KD, 12, false, 3>(lk, p, smem, grid, st, who)                                          \
+   : (presplit && MODE == 1 && KD == 64)                                                                                \
+       ? (warps > 12 ? launch_kd<1, 64, 16, true, 2>(lk, p, smem, grid, st, who) : launch_kd<1, 64, 12, true, 2>(lk, p, smem, grid, st, who)) \
+       : (warps > 12 ? launch_kd<MODE, KD, 16, false, 2>(lk, p, smem, grid, st, who)                                    \
+                     : launch_kd<MODE, KD, 12, false, 2>(lk, p, smem, grid, st, who)))
+  if (presplit && nbuf != 2) return MM_ERR_UNSUPPORTED;
   switch (D) {
     case 16: return MM_V2_LAUNCH(16);
     case 32: return MM_V2_LAUNCH(32);
@@ -566,9 +619,9 @@ int launch(const float* x, int64_t x_stride, const LookupParams& lk, const float
 }
 
 template int launch<0>(const float*, int64_t, const LookupParams&, const float*, int64_t, int, int, int64_t, int, int,
-                       float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*);
+                       float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*, bool);
 template int launch<1>(const float*, int64_t, const LookupParams&, const float*, int64_t, int, int, int64_t, int, int,
-                       float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*);
+                       float*, int64_t, void*, int, int32_t*, cudaStream_t, const char*, bool);
 
 }  // namespace imma2
 }  // namespace mm

@@ -64,6 +64,7 @@ struct Params {
   const float* bias[kMaxChain + 1];  // layer 1, chain layers
   uint32_t w_bytes;                  // total resident weight bytes
   float* out_f32;                    // (M, N_last) fp32 rows, or null
+  uint8_t* out_operand;              // (M, 2*N_last) bf16 split rows [hi | lo], or null
   long long out_stride;
   const float* head_w;               // fused Dense(N_last -> 1) head, or null
   float head_b;
@@ -309,7 +310,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int set = p.dual ? group : 0;
     const uint32_t col_a = p.dual ? 128u + 192u * (uint32_t)set : 256u;
     float* stg_f = reinterpret_cast<float*>(stage_tiles + (size_t)e * EPI_STAGE_BYTES);
-    const bool vec_f32 = p.out_f32 && ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+    const bool vec_f32 = p.out_operand ||  // (the host checks that a fp32 output beside an operand output is vector-aligned)
+                         (p.out_f32 && ((p.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0));
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t d_phase = 0;
     long long it = 0;
@@ -380,7 +382,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               for (int j = 0; j < 32; ++j) hsum = fmaf(v[j], head_s[j], hsum);
               if (row0 + lane < p.M) p.head_out[row0 + lane] = apply_act(hsum, p.head_act);
             }
-            if (p.out_f32) {
+            if (p.out_f32 || p.out_operand) {
               __syncwarp();
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -394,12 +396,22 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                   const int n = c0 + cv;
                   if (grow < p.M && cv < ncols && n < N) {
                     const float4 t = *reinterpret_cast<const float4*>(stg_f + rr * 36 + cv);
-                    float* g = p.out_f32 + grow * p.out_stride + n;
-                    if (n + 3 < N) *reinterpret_cast<float4*>(g) = t;
-                    else {
-                      g[0] = t.x;
-                      if (n + 1 < N) g[1] = t.y;
-                      if (n + 2 < N) g[2] = t.z;
+                    if (p.out_operand) {  // N % 4 == 0: the chunk is whole
+                      uint32_t h0, l0, h1, l1;
+                      split_pair(t.x, t.y, h0, l0);
+                      split_pair(t.z, t.w, h1, l1);
+                      uint8_t* rowp = p.out_operand + grow * ((long long)N * 4);
+                      *reinterpret_cast<uint2*>(rowp + n * 2) = make_uint2(h0, h1);
+                      *reinterpret_cast<uint2*>(rowp + N * 2 + n * 2) = make_uint2(l0, l1);
+                    }
+                    if (p.out_f32) {
+                      float* g = p.out_f32 + grow * p.out_stride + n;
+                      if (n + 3 < N) *reinterpret_cast<float4*>(g) = t;
+                      else {
+                        g[0] = t.x;
+                        if (n + 1 < N) g[1] = t.y;
+                        if (n + 2 < N) g[2] = t.z;
+                      }
                     }
                   }
                 }
@@ -497,14 +509,19 @@ int mm_mlp_tc_supported(int K, int n_layers, const int* widths, int with_head) {
   return plan_tower(K, n_layers, widths, true, p, smem) ? 1 : 0;
 }
 
-int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* const* w_split, const int* widths,
-              const float* const* bias, const int* acts, float* out, int64_t out_stride, const float* head_w,
-              float head_b, int head_act, float* head_out, void* stream) {
+}  // extern "C"
+
+static int mlp_tc_impl(const void* a_split, int64_t M, int K, int n_layers, const void* const* w_split, const int* widths,
+                       const float* const* bias, const int* acts, float* out, int64_t out_stride, const float* head_w,
+                       float head_b, int head_act, float* head_out, void* out_operand, void* stream) {
   using namespace mm::mlp;
   MM_REQUIRE(a_split && w_split && widths && bias && acts && M >= 0 && K > 0, MM_ERR_ARG, "mm_mlp_tc: null pointer or bad M/K");
   MM_REQUIRE(n_layers >= 1 && n_layers <= kMaxChain + 1, MM_ERR_UNSUPPORTED, "mm_mlp_tc: 1..%d layers (got %d)", kMaxChain + 1,
              n_layers);
-  MM_REQUIRE(out || head_out, MM_ERR_ARG, "mm_mlp_tc: no output requested");
+  MM_REQUIRE(out || head_out || out_operand, MM_ERR_ARG, "mm_mlp_tc: no output requested");
+  MM_REQUIRE(!out_operand || (widths[n_layers - 1] % 4 == 0 && ((uintptr_t)out_operand % 16) == 0 &&
+                              (!out || ((out_stride & 3) == 0 && ((uintptr_t)out % 16) == 0))),
+             MM_ERR_ALIGN, "mm_mlp_tc: operand-format output needs a last width that is a multiple of 4 and 16-B aligned outputs");
   MM_REQUIRE((head_w == nullptr) == (head_out == nullptr), MM_ERR_ARG, "mm_mlp_tc: head weights and head output go together");
   MM_REQUIRE(((uintptr_t)a_split % 16) == 0, MM_ERR_ALIGN, "mm_mlp_tc: a_split must be 16-B aligned");
   MM_REQUIRE(M < (1ll << 31), MM_ERR_UNSUPPORTED, "mm_mlp_tc: M too large for 32-bit TMA coordinates");
@@ -522,7 +539,7 @@ int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* c
 
   Params p;
   size_t smem = 0;
-  MM_REQUIRE(plan_tower(K, n_layers, widths, out != nullptr, p, smem), MM_ERR_UNSUPPORTED,
+  MM_REQUIRE(plan_tower(K, n_layers, widths, out != nullptr || out_operand != nullptr, p, smem), MM_ERR_UNSUPPORTED,
              "mm_mlp_tc: the tower does not fit in shared memory with two pipeline stages (mm_mlp_tc_supported)");
   p.M = M;
   p.act1 = acts[0];
@@ -530,6 +547,7 @@ int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* c
   for (int c = 0; c < p.n_chain; ++c) p.c[c].act = acts[c + 1];
   p.out_f32 = out;
   p.out_stride = out_stride;
+  p.out_operand = (uint8_t*)out_operand;
   p.head_w = head_w;
   p.head_b = head_b;
   p.head_act = head_act;
@@ -582,6 +600,23 @@ int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* c
     fprintf(stderr, "\n");
   }
   return mm::check_launch("mm_mlp_tc");
+}
+
+extern "C" {
+
+int mm_mlp_tc(const void* a_split, int64_t M, int K, int n_layers, const void* const* w_split, const int* widths,
+              const float* const* bias, const int* acts, float* out, int64_t out_stride, const float* head_w,
+              float head_b, int head_act, float* head_out, void* stream) {
+  return mlp_tc_impl(a_split, M, K, n_layers, w_split, widths, bias, acts, out, out_stride, head_w, head_b, head_act, head_out,
+                     nullptr, stream);
+}
+
+int mm_mlp_tc_operand_out(const void* a_split, int64_t M, int K, int n_layers, const void* const* w_split, const int* widths,
+                          const float* const* bias, const int* acts, float* out, int64_t out_stride, void* out_operand,
+                          void* stream) {
+  MM_REQUIRE(out_operand != nullptr, MM_ERR_ARG, "mm_mlp_tc_operand_out: out_operand is null");
+  return mlp_tc_impl(a_split, M, K, n_layers, w_split, widths, bias, acts, out, out_stride, nullptr, 0.0f, 0, nullptr, out_operand,
+                     stream);
 }
 
 }  // extern "C"

@@ -71,6 +71,31 @@ class EmbeddingTable(Block):
         self.embeddings_initializer = embeddings_initializer
         self.trainable = trainable
         self.table: Optional[torch.Tensor] = None
+        self._mirror: Optional[torch.Tensor] = None
+        self._mirror_src = None
+
+    _TRANSIENT = {"_mirror": None, "_mirror_src": None}
+
+    def operand_mirror(self) -> torch.Tensor:
+        """The table as bf16 split rows (rows, 2*dim) = [hi | lo] (ops.split_rows; dim a multiple of 64): a second,
+        same-size copy in HBM that removes the per-sample bf16 split from the fused lookup + interaction kernel.  Built on
+        first use; rebuilt when the table tensor was replaced; call `_weights_changed()` after modifying the table in place."""
+        t = self.embeddings
+        key = (t.data_ptr(), tuple(t.shape))
+        if self._mirror is None or self._mirror_src != key:
+            reuse = self._mirror is not None and self._mirror.shape[0] == t.shape[0]
+            self._mirror = ops.split_rows(t.contiguous(), out=self._mirror if reuse else None)
+            self._mirror_src = key
+        return self._mirror
+
+    def _weights_changed(self) -> None:
+        from .core import bump_weights_version
+
+        if self._mirror is not None and self.table is not None and self._mirror.shape[0] == self.table.shape[0]:
+            ops.split_rows(self.table.contiguous(), out=self._mirror)  # refresh in place: captured graphs keep valid pointers
+        else:
+            self._mirror = None
+        bump_weights_version()
 
     def add_feature(self, col_schema: ColumnSchema) -> None:
         """inputs/embedding.py:99-130: all features of a table must share the domain."""

@@ -257,6 +257,12 @@ class RankingModel(Model):
         self.built = True
         return self
 
+    def _all_onehot(self, inputs: TabularData) -> bool:
+        from .core import get_feature
+
+        emb = self.body.embeddings
+        return all(emb.feature_to_table[f].lookup_kind(get_feature(inputs, f)) == "onehot" for f in emb.feature_names)
+
     def body_width(self) -> int:
         if isinstance(self.body, DLRM):
             if self.body.top_block is not None:
@@ -270,13 +276,17 @@ class RankingModel(Model):
             self.build(next(iter(inputs.values())).device)
         if isinstance(self.body, DLRM) and self.body.top_block is not None:
             # top MLP + output layer as ONE dense chain (no fp32 round trip between them)
-            bottom = self.body.bottom_forward(inputs)
             # top MLP (+ its normalizations, folded) + the output Dense as one chain
             layers, tail = self.body.top_block.chain([self.prediction.to_call])
             assert tail is None
             if dense_engine() != "fp32" and self.body.can_emit_split():
-                a = self.body.interaction_forward(inputs, bottom, as_split=True)
+                # production path: bottom vector and table rows in the interaction kernel's operand format when the
+                # mirrors are on (no bf16 split inside the hot loop); split-bf16 row straight into the top tower
+                op = self.body.use_operand_rows() and self._all_onehot(inputs)
+                bottom = self.body.bottom_forward(inputs, operand_out=op)
+                a = self.body.interaction_forward(inputs, bottom, as_split=True, operand_rows=op)
                 return run_dense_chain(None, layers, a_split=a, K=self.body.output_width_before_top())
+            bottom = self.body.bottom_forward(inputs)
             x = self.body.interaction_forward(inputs, bottom)
             return run_dense_chain(x, layers)
         if isinstance(self.body, DCNBody) and self.body.stacked:

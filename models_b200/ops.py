@@ -232,11 +232,13 @@ def widen_index(t: torch.Tensor) -> torch.Tensor:
 
 def dlrm_lookup_interact(weights, indices, slots, rows, D: int, bottom: Optional[torch.Tensor], bottom_slot: int,
                          out: torch.Tensor, oob: Optional[torch.Tensor] = None, peers=None, rank: int = 0,
-                         world: int = 1) -> torch.Tensor:
+                         world: int = 1, operand_rows: bool = False) -> torch.Tensor:
     """Fused lookup + interaction with per-table id widths and optional row-sharded tables
     (mm_dlrm_lookup_interact).  weights[t]: the (rows, D) table or this rank's shard; indices[t]: (B,) ids
     (any width, see index_bytes_of); rows[t]: GLOBAL row count; peers[t]: None (replicated) or the `world`
-    device pointers of the shards as mapped in this process."""
+    device pointers of the shards as mapped in this process.  operand_rows=True (D = 64): `weights`, the peers' shards
+    and `bottom` are bf16 split rows (rows, 2*D) = [hi | lo] (split_rows / mlp_tc(out_operand=...)); needs a split-bf16
+    `out`."""
     _dev(out, "out")
     B = out.shape[0]
     n = len(weights)
@@ -244,11 +246,14 @@ def dlrm_lookup_interact(weights, indices, slots, rows, D: int, bottom: Optional
         raise ValueError("weights / indices / slots / rows length mismatch")
     arr = (_cabi.LookupTable * n)()
     keep = []
+    wdt, wcols = (torch.bfloat16, 2 * D) if operand_rows else (torch.float32, D)
+    if operand_rows and bottom is not None and (bottom.dtype != torch.bfloat16 or bottom.shape[1] != 2 * D):
+        raise ValueError(f"operand_rows: bottom must be bf16 split rows (B, {2 * D})")
     for t in range(n):
-        w = _dev(weights[t], f"weights[{t}]", torch.float32)
+        w = _dev(weights[t], f"weights[{t}]", wdt)
         ix = _dev(indices[t], f"indices[{t}]")
-        if w.dim() != 2 or w.shape[1] != D or not w.is_contiguous():
-            raise ValueError(f"weights[{t}] must be a contiguous (rows, {D}) matrix")
+        if w.dim() != 2 or w.shape[1] != wcols or not w.is_contiguous():
+            raise ValueError(f"weights[{t}] must be a contiguous (rows, {wcols}) {wdt} matrix")
         wb = index_bytes_of(ix)
         if ix.numel() != B * (3 if wb == 3 else 1) or not ix.is_contiguous():
             raise ValueError(f"indices[{t}] must be contiguous with {B} ids, got {tuple(ix.shape)}")
@@ -267,8 +272,8 @@ def dlrm_lookup_interact(weights, indices, slots, rows, D: int, bottom: Optional
     o32, ostride, osplit, okp = _split_out_args(out)
     _cabi.check(
         _lib().mm_dlrm_lookup_interact(arr, n, B, D, rank, world, _ptr(bottom),
-                                       0 if bottom is None else _row_stride(_dev(bottom, "bottom", torch.float32), "bottom"),
-                                       bottom_slot, o32, ostride, osplit, okp, _ptr(oob), _stream()),
+                                       0 if bottom is None else (_row_stride(_dev(bottom, "bottom", wdt), "bottom") // (2 if operand_rows else 1)),
+                                       bottom_slot, o32, ostride, osplit, okp, _ptr(oob), 1 if operand_rows else 0, _stream()),
         "mm_dlrm_lookup_interact")
     return out
 
@@ -628,9 +633,10 @@ def mlp_tc_supported(K: int, widths: Sequence[int], head: bool = False) -> bool:
 def mlp_tc(a_split: torch.Tensor, K: int, w_splits: Sequence[torch.Tensor], widths: Sequence[int],
            biases: Sequence[Optional[torch.Tensor]], acts: Sequence[Optional[str]], out: Optional[torch.Tensor] = None,
            head_w: Optional[torch.Tensor] = None, head_b: float = 0.0, head_act: Optional[str] = None,
-           head_out: Optional[torch.Tensor] = None):
+           head_out: Optional[torch.Tensor] = None, out_operand: Optional[torch.Tensor] = None):
     """Whole MLP tower in one launch (mm_mlp_tc): layer 1 from the split-bf16 rows `a_split`, layers 2..n on
-    chip (activations stay in tensor memory).  out: (M, widths[-1]) fp32 and/or head_out: (M, 1)."""
+    chip (activations stay in tensor memory).  out: (M, widths[-1]) fp32 and/or head_out: (M, 1); out_operand:
+    (M, 2*widths[-1]) bf16 split rows [hi | lo] for the interaction kernel (mm_mlp_tc_operand_out)."""
     n = len(widths)
     if not (len(w_splits) == len(biases) == len(acts) == n):
         raise ValueError("mlp_tc: w_splits / widths / biases / acts must have one entry per layer")
@@ -662,6 +668,17 @@ def mlp_tc(a_split: torch.Tensor, K: int, w_splits: Sequence[torch.Tensor], widt
     bp = (C.c_void_p * n)(*[_ptr(b) for b in biases])
     wd = (C.c_int * n)(*[int(w) for w in widths])
     ac = (C.c_int * n)(*[ACTIVATIONS[a] for a in acts])
+    if out_operand is not None:
+        if head_w is not None:
+            raise ValueError("out_operand and the fused head exclude each other")
+        _dev(out_operand, "out_operand", torch.bfloat16)
+        if tuple(out_operand.shape) != (M, 2 * int(widths[-1])) or not out_operand.is_contiguous():
+            raise ValueError(f"out_operand must be a contiguous ({M}, {2 * int(widths[-1])}) bf16 buffer")
+        _cabi.check(
+            _lib().mm_mlp_tc_operand_out(a_split.data_ptr(), M, K, n, wp, wd, bp, ac, _ptr(out),
+                                         out.stride(0) if out is not None else 0, out_operand.data_ptr(), _stream()),
+            "mm_mlp_tc_operand_out")
+        return
     _cabi.check(
         _lib().mm_mlp_tc(a_split.data_ptr(), M, K, n, wp, wd, bp, ac, _ptr(out), out.stride(0) if out is not None else 0,
                          _ptr(head_w), float(head_b), ACTIVATIONS[head_act], _ptr(head_out), _stream()),

@@ -82,6 +82,11 @@ class ShardedEmbeddings:
         self.global_rows: Dict[str, int] = {n: t.input_dim for n, t in embeddings.tables.items()}
         self.arena = None
         self._arena_hdl = None
+        self._offsets: Dict[str, int] = {}
+        self.mirrors: Dict[str, torch.Tensor] = {}   # table name -> shard / table as bf16 split rows (ops.split_rows)
+        self.mirror_peer_ptrs: Dict[str, Optional[List[int]]] = {}
+        self.mirror_arena = None
+        self._mirror_hdl = None
         self._symm = None
         self._symm_key = None
 
@@ -101,6 +106,7 @@ class ShardedEmbeddings:
                 offsets[name] = off
                 lrows_max = (table.input_dim + self.world - 1) // self.world  # same on every rank
                 off += ((max(lrows_max, 1) * D + 63) // 64) * 64  # 256-B aligned shards
+        self._offsets, self._arena_floats = offsets, off
         arena_ptrs = None
         if off and device.type == "cuda":
             import torch.distributed._symmetric_memory as symm_mem
@@ -119,6 +125,12 @@ class ShardedEmbeddings:
             else:
                 self.shards[name] = torch.empty((table.input_dim, D), dtype=torch.float32, device=device)
                 self.peer_ptrs[name] = None
+
+    def _maybe_mirror(self):
+        from .blocks import table_mirror
+
+        if table_mirror() and self.device is not None and self.device.type == "cuda" and self.D == 64:
+            self.build_mirrors()
 
     def _publish(self):
         """Shards are written once; every rank must see every other rank's rows before the first lookup."""
@@ -151,6 +163,7 @@ class ShardedEmbeddings:
                 w[:lrows].copy_(shard_of(full, self.rank, self.world) if shd else full)
                 del full
         self._publish()
+        self._maybe_mirror()
         return self
 
     def load_full_tables(self, full: Dict[str, torch.Tensor], device) -> "ShardedEmbeddings":
@@ -165,13 +178,41 @@ class ShardedEmbeddings:
             else:
                 self.shards[name].copy_(src)
         self._publish()
+        self._maybe_mirror()
         return self
+
+    def build_mirrors(self) -> None:
+        """Operand-format copies of every shard (a second symmetric arena, same offsets: peers read the MIRROR rows over
+        NVLink) and of every replicated table.  Collective over the group (rendezvous + barrier); idempotent."""
+        if self.mirrors or not self.shards:
+            return
+        dev = self.device
+        arena_ptrs = None
+        if self._arena_floats and dev.type == "cuda":
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.mirror_arena = symm_mem.empty((2 * self._arena_floats,), dtype=torch.bfloat16, device=dev)
+            self._mirror_hdl = symm_mem.rendezvous(self.mirror_arena, group=self.group)
+            arena_ptrs = [int(p) for p in self._mirror_hdl.buffer_ptrs]
+        for name, shard in self.shards.items():
+            if name in self._offsets and self.mirror_arena is not None:
+                o = self._offsets[name]
+                view = self.mirror_arena[2 * o: 2 * o + 2 * shard.numel()].view(shard.shape[0], 2 * shard.shape[1])
+                ops.split_rows(shard, out=view)
+                self.mirrors[name] = view
+                self.mirror_peer_ptrs[name] = [p + 4 * o for p in arena_ptrs]
+            else:
+                self.mirrors[name] = ops.split_rows(shard.contiguous())
+                self.mirror_peer_ptrs[name] = None
+        self._publish()
 
     # ---- the product path: lookup fused into the interaction kernel ----------------------------------
     def lookup_interact(self, local_inputs: Dict[str, torch.Tensor], slots: Dict[str, int], bottom: Optional[torch.Tensor],
-                        out: torch.Tensor, oob: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        out: torch.Tensor, oob: Optional[torch.Tensor] = None, operand_rows: bool = False) -> torch.Tensor:
         """out = [bottom | pairwise dots] of this rank's samples; rows owned by other ranks are read over
-        NVLink inside the kernel (mm_dlrm_lookup_interact)."""
+        NVLink inside the kernel (mm_dlrm_lookup_interact).  operand_rows: `bottom` is in operand format and the
+        operand-format mirrors of the shards are read (build_mirrors must have run — ShardedEmbeddings.build does it
+        when the table mirrors are enabled)."""
         if not self.shards:
             raise RuntimeError("ShardedEmbeddings.build(device) must be called first")
         from .core import get_feature
@@ -179,10 +220,15 @@ class ShardedEmbeddings:
         names = [self.embeddings.feature_to_table[f].table_name for f in self.feature_names]
         idx = [get_feature(local_inputs, f) for f in self.feature_names]
         idx = [i if i.dtype in (torch.uint8, torch.uint16) else _as_index(i).reshape(-1) for i in idx]
+        if operand_rows and not self.mirrors:
+            raise RuntimeError("operand-format rows requested but build_mirrors() has not run")
+        tabs = self.mirrors if operand_rows else self.shards
+        pp = self.mirror_peer_ptrs if operand_rows else self.peer_ptrs
         return ops.dlrm_lookup_interact(
-            [self.shards[n] for n in names], idx, [slots[f] for f in self.feature_names], [self.global_rows[n] for n in names],
+            [tabs[n] for n in names], idx, [slots[f] for f in self.feature_names], [self.global_rows[n] for n in names],
             self.D, bottom, slots.get("bottom_block", -1), out, oob,
-            peers=[self.peer_ptrs[n] if self.is_sharded(n) else None for n in names], rank=self.rank, world=self.world)
+            peers=[pp[n] if self.is_sharded(n) else None for n in names], rank=self.rank, world=self.world,
+            operand_rows=operand_rows)
 
     # ---- step 1: replicate the indices ----------------------------------------------------------------
     def gather_indices(self, local_inputs: Dict[str, torch.Tensor]) -> torch.Tensor:

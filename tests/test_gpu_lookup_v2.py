@@ -212,3 +212,90 @@ def test_dlrm_model_accepts_packed_host_batch(device):
         bad["C6"] = feats["C6"].copy()
         bad["C6"][0] = 300
         packed.fill(bad)
+
+
+@pytest.mark.parametrize("T,with_perm", [(26, False), (26, True), (31, True), (1, False), (12, True)])
+def test_operand_format_rows_match_fp32_rows(device, T, with_perm):
+    """MM_ROWS_OPERAND: tables and bottom as bf16 split rows [hi | lo] (ops.split_rows), fragments by ldmatrix.  Same
+    products as the fp32-row kernel; the k order inside an MMA differs, so equality holds to fp32 rounding."""
+    D = 64
+    rng = np.random.default_rng(D + T)
+    B = 1531
+    F = T + 1
+    rows = [int(r) for r in rng.integers(3, 3000, T)]
+    tn = [rng.standard_normal((r, D)).astype(np.float32) for r in rows]
+    tables = [dev(t, device) for t in tn]
+    idn = [rng.integers(0, r, B).astype(np.int64) for r in rows]
+    idn[0][7] = rows[0] + 3  # out of range -> zero row in both formats
+    idx = [dev(i.astype(np.int32), device) for i in idn]
+    bn = rng.standard_normal((B, D)).astype(np.float32)
+    bottom = dev(bn, device)
+    perm = rng.permutation(F).tolist() if with_perm else list(range(F))
+    W = D + F * (F - 1) // 2
+    a = torch.empty((B, 2 * ops.tc_padded_k(W)), dtype=torch.bfloat16, device=device)
+    b = torch.empty_like(a)
+    oa, ob = torch.zeros(1, dtype=torch.int32, device=device), torch.zeros(1, dtype=torch.int32, device=device)
+    ops.dlrm_lookup_interact(tables, idx, perm[:T], rows, D, bottom, perm[T], a, oa)
+    ops.dlrm_lookup_interact([ops.split_rows(t) for t in tables], idx, perm[:T], rows, D, ops.split_rows(bottom), perm[T], b, ob,
+                             operand_rows=True)
+    assert int(oa.item()) == int(ob.item()) == 1
+    ua, ub = unsplit(a, W), unsplit(b, W)
+    assert np.array_equal(ua[:, :D], ub[:, :D])  # the prefix is the same hi/lo pair either way
+    np.testing.assert_allclose(ub, ua, rtol=1e-5, atol=1e-5)
+    ref = reference(tn, idn, rows, perm[:T], bn, perm[T], F, D)
+    np.testing.assert_allclose(ub, ref, rtol=2e-4, atol=4e-4)
+    with pytest.raises(ValueError, match="operand-format rows need the split-bf16 output"):
+        ops.dlrm_lookup_interact([ops.split_rows(t) for t in tables], idx, perm[:T], rows, D, ops.split_rows(bottom), perm[T],
+                                 torch.empty((B, W), device=device), operand_rows=True)
+
+
+def test_tower_kernel_operand_output_equals_split_of_fp32_output(device):
+    rng = np.random.default_rng(3)
+    M, K, widths = 1000, 13, [128, 64]
+    x = dev(rng.standard_normal((M, K)).astype(np.float32), device)
+    Ws = [dev((rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32), device) for k, n in zip([K] + widths[:-1], widths)]
+    bs = [dev(rng.standard_normal(n).astype(np.float32) * 0.1, device) for n in widths]
+    a = ops.split_rows(x)
+    ws = [ops.split_weights(w) for w in Ws]
+    out = torch.empty((M, 64), device=device)
+    op = torch.empty((M, 128), dtype=torch.bfloat16, device=device)
+    ops.mlp_tc(a, K, ws, widths, bs, ["relu", "relu"], out=out)
+    ops.mlp_tc(a, K, ws, widths, bs, ["relu", "relu"], out_operand=op)
+    assert torch.equal(ops.split_rows(out).view(torch.int16), op.view(torch.int16))
+    both_f, both_o = torch.empty_like(out), torch.empty_like(op)
+    ops.mlp_tc(a, K, ws, widths, bs, ["relu", "relu"], out=both_f, out_operand=both_o)
+    assert torch.equal(both_f, out) and torch.equal(both_o.view(torch.int16), op.view(torch.int16))
+
+
+def test_dlrm_model_table_mirror_on_off_agree(device):
+    import models_b200 as mm
+    from models_b200 import blocks, datasets
+
+    mm.set_seed(12)
+    schema = datasets.criteo_schema({k: min(v, 9000) for k, v in datasets.CRITEO_MAX.items()})
+    model = mm.DLRMModel(schema, embedding_dim=64, bottom_block=mm.MLPBlock([128, 64]), top_block=mm.MLPBlock([128, 64, 32]))
+    model.build(device)
+    feats, _ = datasets.split_targets(schema, datasets.generate_batch(schema, 2048, seed=5, index_law="uniform", index_dtype=np.int32))
+    batch = {k: dev(v, device) for k, v in feats.items()}
+    try:
+        blocks.set_table_mirror(False)
+        assert not model.body.use_operand_rows()
+        ref = model(batch).clone()
+        blocks.set_table_mirror(True)
+        assert model.body.use_operand_rows()
+        got = model(batch)
+        close = lambda x, y: torch.allclose(x, y, rtol=1e-5, atol=1e-6)  # same products, different k order inside the MMAs
+        assert close(ref, got)
+        hb = mm.HostBatch.like(feats, model.input_columns(), id_bytes=model.id_bytes())
+        cf = model.compile(hb)
+        assert torch.equal(cf(hb).to(device), got)
+        # a table reassigned after the capture: the mirror is refreshed in place and the graph re-captured
+        t = model.body.embeddings.tables["C2"]
+        t.table.mul_(0.5)
+        t._weights_changed()
+        blocks.set_table_mirror(False)
+        ref2 = model(batch).clone()
+        blocks.set_table_mirror(True)
+        assert not close(ref2, ref) and close(cf(hb).to(device), ref2)
+    finally:
+        blocks.set_table_mirror(None)

@@ -122,6 +122,13 @@ def main():
         m, mn = timeit(lambda i: ops.dlrm_lookup_interact(tables, pidx[i % nb], sl, rows, D, bottom, slots["bottom_block"], osplit[i % 2]), args.iters)
         report(f"mm_dlrm_lookup_interact (packed ids {idb} B/sample, split out)", m, mn,
                bytes_=B * (T * D * 4 + idb + D * 4 + (D + 351) * 4), law=args.law)
+        mirrors = [ops.split_rows(t) for t in tables]
+        bottom_op = ops.split_rows(bottom)
+        m, mn = timeit(lambda i: ops.dlrm_lookup_interact(mirrors, pidx[i % nb], sl, rows, D, bottom_op, slots["bottom_block"], osplit[i % 2],
+                                                          operand_rows=True), args.iters)
+        report(f"mm_dlrm_lookup_interact (operand-format rows, packed ids {idb} B/sample, split out)", m, mn,
+               bytes_=B * (T * D * 4 + idb + D * 4 + (D + 351) * 4), law=args.law)
+        del mirrors
         m, mn = timeit(lambda i: ops.dlrm_gather_interact(tables, idx[i % nb], sl, D, bottom, slots["bottom_block"], osplit[i % 2]), args.iters)
         report("mm_dlrm_gather_interact (legacy entry, split out)", m, mn, bytes_=B * (T * D * 4 + T * 4 + D * 4 + (D + 351) * 4), law=args.law)
 

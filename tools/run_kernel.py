@@ -28,7 +28,7 @@ if what == "dense_tc":
     nxt = torch.zeros((B, 2 * ops.tc_padded_k(N)), dtype=torch.bfloat16, device=dev)
     for _ in range(5):
         ops.dense_tc(a, K, w, N, b, "relu", out_split=nxt)
-elif what in ("gather", "fused", "interact"):
+elif what in ("gather", "fused", "fused_operand", "interact"):
     T, D = 26, 64
     F = T + 1
     schema = datasets.criteo_schema()
@@ -52,6 +52,11 @@ elif what in ("gather", "fused", "interact"):
             ops.gather_multi(tables, idx, [slots[n] * D for n in names], stack)
         elif what == "fused":
             ops.dlrm_gather_interact(tables, idx, [slots[n] for n in names], D, bottom, slots["bottom_block"], out)
+        elif what == "fused_operand":
+            if i == 0:
+                mirrors, bottom_op = [ops.split_rows(t) for t in tables], ops.split_rows(bottom)
+            ops.dlrm_lookup_interact(mirrors, idx, [slots[n] for n in names], [t.shape[0] for t in tables], D, bottom_op,
+                                     slots["bottom_block"], out, operand_rows=True)
         else:
             ops.dot_interaction(xs[i % 2], out, prefix=bottom)
 elif what == "scores":
