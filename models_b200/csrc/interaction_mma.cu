@@ -1,10 +1,11 @@
-// DLRM pairwise interaction on tensor cores, one warp per sample.
+// DLRM pairwise interaction on tensor cores, one warp per sample — FIRST-GENERATION kernel, kept for A/B measurements
+// (MM_IMMA_V1=1) and as the fallback of the legacy entry points; the product path is interaction_v2.cu.
 //
 // The per-sample Gram matrix X X^T (X = F x D, F <= 32) is far too small for tcgen05 (M >= 64 per
 // instruction would waste > 4x on block-diagonal padding), so it runs on the warp-level
 // mma.sync.m16n8k16 bf16 path with the same 3-pass split as the dense layers (hi*lo + lo*hi + hi*hi,
-// fp32 accumulate) — the kernel stays HBM-bound instead of shared-memory-bandwidth bound like the
-// CUDA-core version (interaction.cu, 3x3 register blocking: 0.31 ms vs the 0.086 ms HBM floor).
+// fp32 accumulate).  It is NOT HBM-bound: ncu shows 1 155 warp instructions per sample at 62 % issue
+// utilisation and DRAM at 35 % of peak (profiles/r01_notes.md §h) — the v2 kernel cuts the instruction count in half.
 //
 // Data movement: rows go from the embedding tables — or the stacked (B,F,D) tensor — straight
 // into a padded shared-memory tile with 16-byte cp.async (LDGSTS: no register staging, zero-fill

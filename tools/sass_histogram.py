@@ -13,7 +13,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "models_b200" / "_lib" / "libmm_b200.so"
-KEY = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "HMMA", "LDGSTS", "LDG", "STG", "LDS", "STS", "SHFL",
+KEY = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "HMMA", "LDSM", "LDGSTS", "LDG", "STG", "LDS", "STS", "SHFL",
        "MUFU", "BAR", "SYNCS", "ATOM", "RED"]
 
 
