@@ -280,6 +280,19 @@ int mm_mlp_tc_operand_out(const void* a_split, int64_t M, int K, int n_layers, c
                           const int* widths, const float* const* bias, const int* acts, float* out,
                           int64_t out_stride, void* out_operand, void* stream);
 
+/* Narrow-input two-layer tower in ONE launch: out = act2(act1(concat(pieces) W1 + b1) W2 + b2), K = total piece width
+ * <= 16, N1 in {32, 64, 128}, N2 in {16, 32, 64} (mm_tower2_small_supported) — the DLRM bottom tower over the continuous
+ * columns: ContinuousFeatures + ConcatFeatures (inputs/continuous.py:117-138, core/aggregation.py:54-66: pieces in
+ * sorted-name order, cast to fp32) feeding MLPBlock([N1, N2]) (blocks/mlp.py:97-139).  One warp per 16 samples on
+ * mma.sync (3-pass split-bf16, fp32 accumulate), hidden activations stay in registers, both weight matrices
+ * (mm_split_weights layouts) in shared memory.  out: (B, N2) fp32 (nullable); out_split: (B, 2*N2) bf16 [hi | lo]
+ * (nullable) — the operand format of mm_dlrm_lookup_interact(row_format = MM_ROWS_OPERAND).  pieces: as
+ * mm_concat_columns, listed in column order (out_col = running sum of widths). */
+int mm_tower2_small_supported(int K, int N1, int N2);
+int mm_tower2_small(const mm_concat_piece* pieces_host, int n_pieces, int64_t B, const void* w1_split, int N1,
+                    const float* bias1, int act1, const void* w2_split, int N2, const float* bias2, int act2, float* out,
+                    int64_t out_stride, void* out_split, void* stream);
+
 /* Whole-op entry points over fp32 Keras-layout weights (kernel (in, out) row-major, bias (out,) or
  * NULL) and a caller-provided workspace — for callers outside this package's Python host; nothing is
  * allocated, no pre-split weights are needed (the bf16 splits live in the workspace).

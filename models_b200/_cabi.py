@@ -98,6 +98,8 @@ SIGNATURES = {
                        _vp, _i64, _vp, _f, _i, _vp, _vp]),
     "mm_mlp_tc_operand_out": (_i, [_vp, _i64, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_int), _vp, _i64, _vp, _vp]),
+    "mm_tower2_small_supported": (_i, [_i, _i, _i]),
+    "mm_tower2_small": (_i, [C.POINTER(ConcatPiece), _i, _i64, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i64, _vp, _vp]),
     "mm_rowwise_dot": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
     "mm_catalog_workspace_bytes": (_i64, [_i64, _i64, _i]),
     "mm_catalog_score": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i64, _vp]),

@@ -51,6 +51,7 @@ def last_dense_path() -> str:
     return _LAST_PATH[0]
 
 
+_SMALL_TOWER = [True]  # mm_tower2_small for narrow-input two-layer towers (tests switch it off to reach the TMA tower kernel)
 _TABLE_MIRROR = [None]  # None: decide from MM_TABLE_MIRROR (default on); True / False: forced
 
 
@@ -385,6 +386,25 @@ class MLP(SequentialBlock):
             if self.filter_names is not None:
                 x = {k: v for k, v in x.items() if k in self.filter_names}
             pieces = [x[k] for k in sorted(x)]
+            if _use_tc() and _SMALL_TOWER[0] and batch_size_of(x) > 0:
+                # narrow-input two-layer tower (the DLRM bottom tower): columns -> layer 1 -> layer 2 in one launch
+                K_in = sum(1 if t.dim() == 1 else int(t.shape[1]) for t in pieces)
+                self.build_from_width(K_in, pieces[0].device)
+                layers, tail = self.chain()
+                if (tail is None and len(layers) == 2 and layers[0].input_dim == K_in
+                        and ops.tower2_small_supported(pieces, layers[0].units, layers[1].units)):
+                    B = batch_size_of(x)
+                    l1, l2 = layers
+                    _LAST_PATH[0] = "tower2_small"
+                    if operand_out:
+                        out = torch.empty((B, 2 * l2.units), dtype=torch.bfloat16, device=pieces[0].device)
+                        ops.tower2_small(pieces, l1.split_kernel(), l1.units, l1.bias, l1.activation, l2.split_kernel(), l2.units,
+                                         l2.bias, l2.activation, out_split=out)
+                    else:
+                        out = torch.empty((B, l2.units), dtype=torch.float32, device=pieces[0].device)
+                        ops.tower2_small(pieces, l1.split_kernel(), l1.units, l1.bias, l1.activation, l2.split_kernel(), l2.units,
+                                         l2.bias, l2.activation, out=out)
+                    return out
             if _use_tc() and ops.concat_split_supported(pieces) and batch_size_of(x) > 0:
                 # ConcatFeatures straight into the split-bf16 operand of the first tensor-core layer
                 a, K = ops.concat_split(pieces)

@@ -466,6 +466,49 @@ def concat_split(pieces: Sequence[torch.Tensor], out: Optional[torch.Tensor] = N
     return out, K
 
 
+def tower2_small_supported(pieces: Sequence[torch.Tensor], N1: int, N2: int) -> bool:
+    """mm_tower2_small applies: <= 16 input columns of concat-able dtypes, N1 in {32,64,128}, N2 in {16,32,64}."""
+    if not pieces or any(t.dtype not in _CONCAT_DTYPES for t in pieces):
+        return False
+    K = sum(1 if t.dim() == 1 else int(t.shape[1]) for t in pieces)
+    return bool(_lib().mm_tower2_small_supported(int(K), int(N1), int(N2)))
+
+
+def tower2_small(pieces: Sequence[torch.Tensor], w1_split: torch.Tensor, N1: int, bias1, act1, w2_split: torch.Tensor, N2: int,
+                 bias2, act2, out: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None):
+    """act2(act1(concat(pieces) W1 + b1) W2 + b2) in one launch (mm_tower2_small).  out: (B, N2) fp32 and / or
+    out_split: (B, 2*N2) bf16 [hi | lo]."""
+    flat, col = [], 0
+    B = pieces[0].shape[0]
+    for i, t in enumerate(pieces):
+        _dev(t, f"pieces[{i}]")
+        if t.dim() == 1:
+            t = t.unsqueeze(1)
+        if t.dim() != 2 or t.shape[0] != B or (t.shape[1] > 1 and t.stride(1) != 1):
+            raise ValueError(f"pieces[{i}] must be (B,) or (B,w) with unit inner stride, got {tuple(t.shape)}")
+        flat.append((t.data_ptr(), t.stride(0), int(t.shape[1]), _CONCAT_DTYPES[t.dtype], col))
+        col += int(t.shape[1])
+    _dev(w1_split, "w1_split", torch.bfloat16), _dev(w2_split, "w2_split", torch.bfloat16)
+    if tuple(w1_split.shape) != (tc_padded_n(N1), 2 * tc_padded_k(col)) or tuple(w2_split.shape) != (tc_padded_n(N2), 2 * tc_padded_k(N1)):
+        raise ValueError("w1_split / w2_split must be the mm_split_weights layouts of the (K, N1) and (N1, N2) kernels")
+    if out is not None:
+        _dev(out, "out", torch.float32)
+        if tuple(out.shape) != (B, N2) or out.stride(1) != 1:
+            raise ValueError(f"out must be ({B}, {N2}) fp32")
+    if out_split is not None:
+        _dev(out_split, "out_split", torch.bfloat16)
+        if tuple(out_split.shape) != (B, 2 * N2) or not out_split.is_contiguous():
+            raise ValueError(f"out_split must be a contiguous ({B}, {2 * N2}) bf16 matrix")
+    arr = (_cabi.ConcatPiece * len(flat))()
+    for i, (ptr, sstride, w, dt, oc) in enumerate(flat):
+        arr[i].src, arr[i].src_stride, arr[i].width, arr[i].dtype, arr[i].out_col = ptr, sstride, w, dt, oc
+    _cabi.check(
+        _lib().mm_tower2_small(arr, len(flat), B, w1_split.data_ptr(), N1, _ptr(bias1), ACTIVATIONS[act1], w2_split.data_ptr(), N2,
+                               _ptr(bias2), ACTIVATIONS[act2], _ptr(out), out.stride(0) if out is not None else 0, _ptr(out_split),
+                               _stream()), "mm_tower2_small")
+    return out if out is not None else out_split
+
+
 def l2_normalize(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _dev(x, "x", torch.float32)
     if out is None:

@@ -175,7 +175,11 @@ def test_mlp_block_on_feature_dict_uses_concat_split(device):
     feats = {f"I{i}": dev(rng.random(777).astype(np.float32), device) for i in range(1, 14)}
     mm.set_seed(6)
     mlp = mm.MLPBlock([128, 64])
-    got = mlp(feats)
+    blocks._SMALL_TOWER[0] = False  # the narrow-input kernel (mm_tower2_small) would take this tower: test the TMA tower path
+    try:
+        got = mlp(feats)
+    finally:
+        blocks._SMALL_TOWER[0] = True
     assert blocks.last_dense_path() == "mlp_tc"
     x = torch.stack([feats[k] for k in sorted(feats)], dim=1)  # ConcatFeatures order: I1, I10, ..., I13, I2, ...
     layers = [{"kernel": l.kernel.cpu().numpy(), "bias": l.bias.cpu().numpy(), "activation": l.activation} for l in mlp.dense_layers]
@@ -239,3 +243,54 @@ def test_mm_cross_forward_whole_op_matches_oracle(device, d, depth):
     assert H.rel_err(out.cpu().numpy(), ref) < 1e-4
     with pytest.raises(ValueError, match="should be positive"):
         ops.cross_forward(dev(x0, device), [], [])
+
+
+@pytest.mark.parametrize("dims,K,acts", [([128, 64], 13, "relu"), ([64, 32], 5, ["tanh", "linear"]), ([32, 16], 16, ["gelu", "sigmoid"]),
+                                         ([128, 16], 1, "relu")])
+@pytest.mark.parametrize("B", [1, 17, 4099])
+def test_tower2_small_matches_oracle_and_tower_kernel(device, dims, K, acts, B):
+    """mm_tower2_small: <= 16 scalar columns (mixed dtypes, (B,) and (B,1) and one (B,2) piece) -> two dense layers, fp32 rows and
+    split-bf16 rows; against the oracle MLP over the sorted-name concat, and against the TMA/tcgen05 tower path."""
+    import models_b200 as mm
+    from models_b200 import blocks
+    from oracle import oracle
+
+    rng = np.random.default_rng(K * 100 + B)
+    mm.set_seed(K)
+    cols = {}
+    k = 0
+    while k < K:
+        name = f"I{k}"
+        if k == 2 and K - k >= 2:
+            cols[name] = rng.standard_normal((B, 2)).astype(np.float32)
+            k += 2
+        elif k % 4 == 1:
+            cols[name] = rng.integers(-3, 4, B).astype(np.int64)
+            k += 1
+        elif k % 4 == 3:
+            cols[name] = rng.standard_normal((B, 1)).astype(np.float64)
+            k += 1
+        else:
+            cols[name] = rng.standard_normal(B).astype(np.float32)
+            k += 1
+    mlp = mm.MLPBlock(dims, activation=acts)
+    dcols = {n: torch.from_numpy(v).to(device) for n, v in cols.items()}
+    got = mlp(dcols).cpu().numpy()
+    assert blocks._LAST_PATH[0] == "tower2_small"
+    x = oracle.concat_features({n: np.asarray(v, dtype=np.float32) for n, v in cols.items()})
+    assert x.shape == (B, K)
+    layers = [{"kernel": l.kernel.cpu().numpy(), "bias": l.bias.cpu().numpy(), "activation": l.activation} for l in mlp.dense_layers]
+    ref = oracle.mlp(x, layers)
+    np.testing.assert_allclose(got, ref, rtol=2e-4, atol=2e-5)
+    op = mlp(dcols, operand_out=True)
+    assert op.dtype == torch.bfloat16 and tuple(op.shape) == (B, 2 * dims[-1])
+    assert torch.equal(op.view(torch.int16), ops.split_rows(torch.from_numpy(got).to(device))[:, : 2 * dims[-1]].view(torch.int16)) or dims[-1] % 64
+    rec = op.float().cpu().numpy()
+    np.testing.assert_allclose(rec[:, : dims[-1]] + rec[:, dims[-1]:], got, rtol=2e-5, atol=1e-6)  # hi + lo carries 16-17 bits
+    blocks._SMALL_TOWER[0] = False
+    try:
+        other = mlp(dcols).cpu().numpy()
+        assert blocks._LAST_PATH[0] != "tower2_small"
+    finally:
+        blocks._SMALL_TOWER[0] = True
+    np.testing.assert_allclose(got, other, rtol=1e-5, atol=1e-5)  # two fp32-grade paths: different accumulation order

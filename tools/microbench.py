@@ -224,6 +224,21 @@ def main():
             m, mn = timeit(layered, args.iters)
             report(f"mm_dense_tc chain {name} ({len(widths)} launches)", m, mn, bytes_=io_bytes)
 
+    if "bottom" in only:
+        # DLRM bottom path: 13 continuous columns -> 128 -> 64 (fp32 rows out / operand-format rows out)
+        from models_b200 import blocks
+
+        mm.set_seed(3)
+        cols = {f"I{i}": torch.rand(B, device=dev) for i in range(1, 14)}
+        mlp = mm.MLPBlock([128, 64])
+        for small in (True, False):
+            blocks._SMALL_TOWER[0] = small
+            for op in (False, True):
+                m, mn = timeit(lambda i: mlp(cols, operand_out=op), args.iters)
+                report(f"bottom tower 13->128->64 ({'mm_tower2_small' if small else 'mm_concat_split + mm_mlp_tc'}, "
+                       f"{'split-bf16 rows' if op else 'fp32 rows'} out; eager: includes launch gaps)", m, mn, bytes_=B * (13 * 4 + 64 * 4))
+        blocks._SMALL_TOWER[0] = True
+
     if "models" in only:
         mm.set_seed(1)
         # config 5: DCN-v2, bundled Criteo, inferred dims (d = 1037), depth 3, deep [256, 128]

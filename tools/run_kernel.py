@@ -59,6 +59,12 @@ elif what in ("gather", "fused", "fused_operand", "interact"):
                                      slots["bottom_block"], out, operand_rows=True)
         else:
             ops.dot_interaction(xs[i % 2], out, prefix=bottom)
+elif what == "bottom":
+    mm.set_seed(3)
+    cols = {f"I{i}": torch.rand(B, device=dev) for i in range(1, 14)}
+    mlp = mm.MLPBlock([128, 64])
+    for _ in range(6):
+        mlp(cols, operand_out=True)
 elif what == "scores":
     Bq, Dq = 16384, int(sys.argv[2]) if len(sys.argv) > 2 else 128
     q = torch.randn((Bq, Dq), device=dev)
