@@ -674,6 +674,35 @@ def sharded_record(ctx):
                     "h2d_bytes_per_step": int(hbs[0].payload_bytes()), "d2h_bytes_per_step": B * 4},
             "gpu_launches": ctx.sum_over_ranks(cf.launches_per_replay * steps), "clocks": clocks,
         }
+        if world > 1:
+            # NCCL baseline on the same shards: ids all-gather + local gather + ONE variable-size all-to-all of the vectors
+            # (split sizes read back on the host) + scatter + interaction from the stack — torch ops + torch.distributed
+            from models_b200.sharded import lookup_stack_nccl
+
+            F_n = len(slots)
+            out_n = torch.empty((B, 2 * ops.tc_padded_k(body.output_width_before_top())), dtype=torch.bfloat16, device=dev)
+
+            def nccl_step(i):
+                d = devs[i % n_bufs]
+                stack = lookup_stack_nccl(se, d, slots, F_n)
+                ops.concat_columns([bottoms[i % n_bufs]], stack, [slots["bottom_block"] * 64])
+                ops.dot_interaction(stack.view(B, F_n, 64), out_n, prefix=bottoms[i % n_bufs])
+
+            for i in range(2):
+                nccl_step(i)
+            ctx.barrier()
+            n0_, n1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_nc = 5
+            n0_.record()
+            for i in range(n_nc):
+                nccl_step(i)
+            n1_.record()
+            ctx.barrier()
+            (nc_ms,) = ctx.max_over_ranks(n0_.elapsed_time(n1_) / n_nc)
+            rec["placements"][label]["nccl_all_to_all_ms"] = nc_ms
+            rec["placements"][label]["nccl_all_to_all"] = ("baseline: NCCL all-gather of ids + torch gather + one variable-size NCCL all_to_all_single of "
+                                                           "the rows + scatter + interaction from the stack (eager torch / torch.distributed; lookup + "
+                                                           "interaction only, compare with lookup_interact_kernel_ms)")
         if below == 0 and world > 1:
             # staged baseline on the same shards: ids all-gathered by NCCL, owner-computes push into the destination
             # rank's (B,F,D) stack, barriers, interaction from the stack — eager, as in round 1

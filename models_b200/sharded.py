@@ -286,6 +286,53 @@ class ShardedEmbeddings:
         return buf
 
 
+def lookup_stack_nccl(se: "ShardedEmbeddings", local_inputs: Dict[str, torch.Tensor], slots: Dict[str, int], n_slots: int) -> torch.Tensor:
+    """BASELINE, not a product path: the row-sharded lookup the way the north star words it and the way a PyTorch/NCCL
+    program (or SOK's lookup_sparse, distributed/embedding.py:75-84,144-148) does it — all-gather of the ids, a local gather
+    of the owned rows packed by destination rank, ONE variable-size NCCL all-to-all of the vectors (split sizes exchanged
+    first and read back on the host, as `all_to_all_single` needs them), then a scatter into the (B_local, n_slots*D)
+    stack.  Written with torch ops + torch.distributed on purpose: it is what the fused peer-memory kernel is measured
+    against (bench.py `sharded.nccl_all_to_all_ms`), and tests/dist_sharded_check.py checks that both give the same rows.
+    Replicated tables are looked up locally."""
+    W, rank, D = se.world, se.rank, se.D
+    names = [(f, se.embeddings.feature_to_table[f].table_name) for f in se.feature_names]
+    sharded = [(f, n) for f, n in names if se.is_sharded(n)]
+    dev = next(iter(local_inputs.values())).device
+    Bl = _as_index(local_inputs[se.feature_names[0]]).reshape(-1).shape[0]
+    stack = torch.zeros((Bl, n_slots * D), dtype=torch.float32, device=dev)
+    for f, n in names:
+        if not se.is_sharded(n):
+            stack.view(Bl, n_slots, D)[:, slots[f]] = se.shards[n][_as_index(local_inputs[f]).reshape(-1).long()]
+    if not sharded:
+        return stack
+    ids = torch.stack([_as_index(local_inputs[f]).reshape(-1).long() for f, _ in sharded], dim=1).contiguous()  # (Bl, Ts)
+    Ts = ids.shape[1]
+    gids = torch.empty((W, Bl, Ts), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gids.view(-1), ids.view(-1), group=se.group)
+    mine = (gids % W) == rank                                   # entries of every rank's batch whose row I own
+    send_counts = mine.view(W, -1).sum(dim=1)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=se.group)
+    in_splits, out_splits = send_counts.tolist(), recv_counts.tolist()   # host sync: all_to_all_single needs python ints
+    w_idx, b_idx, t_idx = mine.nonzero(as_tuple=True)                    # sorted by destination rank, then (sample, table)
+    lrow = gids[w_idx, b_idx, t_idx] // W
+    send = torch.empty((int(w_idx.numel()), D), dtype=torch.float32, device=dev)
+    for j, (_, n) in enumerate(sharded):
+        sel = t_idx == j
+        send[sel] = se.shards[n][lrow[sel]]
+    recv = torch.empty((int(sum(out_splits)), D), dtype=torch.float32, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=out_splits, input_split_sizes=in_splits, group=se.group)
+    owner = ids % W                                                       # who sent me which of my (sample, table) entries
+    col = torch.tensor([slots[f] for f, _ in sharded], device=dev)
+    view = stack.view(Bl, n_slots, D)
+    off = 0
+    for r in range(W):
+        b_r, t_r = (owner == r).nonzero(as_tuple=True)
+        view[b_r, col[t_r]] = recv[off: off + b_r.numel()]
+        off += b_r.numel()
+    return stack
+
+
 def shard_model(model, group=None, replicate_below_rows: int = 65536):
     """Row-shard the embedding tables of a DLRM model over `group` (call before the first forward;
     every rank then holds 1/world of each sharded table; tables with fewer than `replicate_below_rows`

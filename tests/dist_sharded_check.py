@@ -58,6 +58,15 @@ def main():
             want = full(d)
             got = sharded(d)  # product path: lookup over NVLink inside the interaction kernel
             ok &= bool(torch.equal(want, got))
+            # NCCL baseline (ids all-gather + local gather + one variable-size all-to-all + scatter): same rows
+            from models_b200.sharded import lookup_stack_nccl
+
+            slots_n = sharded.body.slots()
+            st = lookup_stack_nccl(se, d, slots_n, len(slots_n))
+            ref_n = torch.zeros_like(st)
+            full.body.embeddings.lookup_all_into(d, ref_n, {f: slots_n[f] * 64 for f in full.body.embeddings.feature_names})
+            cols_n = [c for f in full.body.embeddings.feature_names for c in range(slots_n[f] * 64, slots_n[f] * 64 + 64)]
+            ok &= bool(torch.equal(st[:, cols_n], ref_n[:, cols_n]))
             if replicate_below == 0:
                 # staged protocol (index all-gather + push + barrier): stack bit-exactness
                 slots = sharded.body.slots()
