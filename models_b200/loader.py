@@ -135,7 +135,8 @@ class Loader:
                  buffer_size=0.1, device=None, parts_per_chunk: int = 1, reader_kwargs=None,
                  global_size: Optional[int] = None, global_rank: Optional[int] = None, drop_last: bool = False,
                  sparse_names=None, sparse_max=None, sparse_as_dense: bool = False, schema: Optional[Schema] = None,
-                 index_dtype: str = "int32", prefetch: int = 2, **loader_kwargs):
+                 index_dtype: str = "int32", prefetch: int = 2, id_bytes: Optional[Dict[str, int]] = None,
+                 **loader_kwargs):
         if batch_size is None or int(batch_size) <= 0:
             raise ValueError("`batch_size` must be a positive integer")
         self.batch_size = int(batch_size)
@@ -174,6 +175,8 @@ class Loader:
         self.prefetch = max(1, int(prefetch))
         self._index_dtype = np.dtype(index_dtype)
         self._epoch = 0
+        # `Model.id_bytes()`: scalar id columns listed here travel packed (1/2/3-byte unsigned) over PCIe
+        self.id_bytes = {k: int(v) for k, v in (id_bytes or {}).items() if int(v) in (1, 2, 3)}
         self._casts = self._plan_casts()
         self._copy_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
 
@@ -244,8 +247,8 @@ class Loader:
                     v = vals[np.repeat(off[rows] - o[:-1], lens) + np.arange(int(o[-1]))]
                 arrays[n + "__values"] = v.astype(dt, copy=False)
                 arrays[n + "__offsets"] = o.astype(np.int32)
-        hb = HostBatch({k: (v.shape, v.dtype) for k, v in arrays.items()})
-        hb.fill(arrays)
+        packed = {k: w for k, w in self.id_bytes.items() if k in self._cols.scalar and k in arrays and k not in self.label_names}
+        hb = HostBatch.like(arrays, id_bytes=packed)
         return hb, hb.spec
 
     def _to_device(self, hb: HostBatch) -> Tuple[Dict[str, torch.Tensor], Optional[torch.cuda.Event]]:

@@ -152,3 +152,17 @@ def test_loader_errors(tmp_path):
         mm.Loader({"a": np.arange(4)}, batch_size=0, device="cpu")
     big = mm.Loader({"id": np.array([0, 2**40], dtype=np.int64)}, batch_size=2, shuffle=False, device="cpu")
     assert big.peek()[0]["id"].dtype == torch.int64  # does not fit int32: kept wide
+
+
+def test_packed_id_columns(dataset_dir):
+    """`id_bytes` (`Model.id_bytes()`): scalar id columns travel as 1/2/3-byte unsigned ids; ragged ones stay int32."""
+    d, f = dataset_dir
+    loader = mm.Loader(str(d), batch_size=256, shuffle=False, device="cpu", id_bytes={"user_id": 2, "item_id": 3, "genres": 1})
+    hb = next(iter(loader.host_batches()))
+    assert hb.spec["user_id"] == ((256,), np.dtype(np.uint16)) and hb.spec["item_id"] == ((256, 3), np.dtype(np.uint8))
+    assert hb.spec["genres__values"][1] == np.dtype(np.int32)
+    assert np.array_equal(hb.columns["user_id"].numpy(), f["user_id"][:256].astype(np.uint16))
+    packed = hb.columns["item_id"].numpy().astype(np.int64)
+    assert np.array_equal(packed[:, 0] | packed[:, 1] << 8 | packed[:, 2] << 16, f["item_id"][:256])
+    inputs, _ = next(iter(loader))
+    assert inputs["user_id"].dtype == torch.uint16 and inputs["item_id"].shape == (256, 3)
