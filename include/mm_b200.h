@@ -396,6 +396,81 @@ int mm_shard_gather_push(const mm_gather_table* tables_host, int n_tables, int i
 int mm_init_uniform_hash_rows(float* w, int64_t local_rows, int D, uint64_t seed, float lo, float hi,
                               int64_t row0, int64_t row_step, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K14  Training step of the DLRM path: the backward of the same kernels and the optimizer,
+ * i.e. what `Model.train_step` (merlin/models/tf/models/base.py:1121-1231) obtains from tf.GradientTape +
+ * `optimizer.apply_gradients` for DLRMBlock (blocks/dlrm.py:32-133) + BinaryOutput (outputs/classification.py:114):
+ *
+ *   mm_bce_head_fwd_bwd       Dense(K -> 1) + sigmoid + binary cross-entropy (Keras evaluates it on the logits),
+ *                             forward AND backward in one pass over x (M, K), K <= 256:
+ *                               z = x.w + b;  *loss_sum += sum_i sw_i (max(z,0) - z y + log(1 + e^-|z|)) / M;
+ *                               dz = sw_i (sigmoid(z) - y) / M;  dx = dz w (zeroed where x <= 0 when mask_relu);
+ *                               dw += x^T dz;  *db += sum dz.      loss_sum / dw / db are ACCUMULATED (zero them first).
+ *   mm_dense_wgrad            dW (K, N) += X^T dZ,  db (N) += column sums of dZ   (db nullable; accumulated)
+ *   mm_dense_dgrad            dX (M, K) = dZ (M, N) W^T, W the Keras kernel (K, N), N <= 128; `mask` (M, K) nullable:
+ *                             dX is zeroed where mask <= 0 (mask = the layer's input = the previous layer's relu
+ *                             output, so dX is that layer's pre-activation gradient)
+ *   mm_dlrm_interact_backward backward of mm_dlrm_lookup_interact (fp32 rows, replicated tables): dA (B, P + F(F-1)/2)
+ *                             -> grad_rows_host[t] (B, D): the IndexedSlices values of table t (indices = the
+ *                             batch's ids; duplicates NOT yet summed), and d_bottom (B, D) = gradient of the bottom
+ *                             vector (interaction rows + the shortcut dA[:, :P]; zeroed where bottom <= 0 when
+ *                             mask_bottom).  The table rows are looked up again (tables_host as in the forward call).
+ *   mm_sparse_rows_apply      optimizer step on IndexedSlices with duplicate ids as Keras applies it: duplicates are
+ *                             summed, then ONE update per unique row (OptimizerV2._resource_apply_sparse_duplicate_
+ *                             indices; Adam on touched rows only = LazyAdam, blocks/optimizer.py:342).  rep_map:
+ *                             (rows,) int32 scratch per table, all INT32_MAX between calls (mm_fill_i32 once);
+ *                             grad_rows is clobbered (duplicates are folded into the first occurrence's slice);
+ *                             `mirror`: operand-format copy of the table (mm_dlrm_lookup_interact MM_ROWS_OPERAND)
+ *                             kept in step with the weights, nullable.
+ *   mm_dense_apply            the same update rules over a flat fp32 arena; g is scaled by grad_scale and CLEARED.
+ *   mm_opt_tick               step counter += 1 and the Adam bias-corrected rate (once per step, before the applies)
+ * Update rules (hyper: device float[MM_HYPER_COUNT], so a captured CUDA graph follows a learning-rate schedule):
+ *   MM_OPT_SGD      w -= lr g
+ *   MM_OPT_ADAGRAD  a += g^2;  w -= lr g / (sqrt(a) + eps)                       (a starts at 0.1 in Keras)
+ *   MM_OPT_ADAM     m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  w -= lr_t m / (sqrt(v) + eps),
+ *                   lr_t = lr sqrt(1 - b2^t) / (1 - b1^t)
+ * ------------------------------------------------------------------------------------- */
+#define MM_OPT_SGD 0
+#define MM_OPT_ADAGRAD 1
+#define MM_OPT_ADAM 2
+#define MM_HYPER_LR 0
+#define MM_HYPER_BETA1 1
+#define MM_HYPER_BETA2 2
+#define MM_HYPER_EPS 3
+#define MM_HYPER_STEP 4
+#define MM_HYPER_LR_T 5
+#define MM_HYPER_COUNT 8
+typedef struct {
+  float* weights; /* (rows, D) */
+  int64_t rows;
+  const void* indices; /* (B,) ids, idx_bytes each (1, 2, 3, 4, 8) */
+  int32_t idx_bytes;
+  int32_t reserved;
+  float* grad_rows; /* (B, D) */
+  int32_t* rep_map; /* (rows,) */
+  float* state1;    /* Adagrad accumulator / Adam m, (rows, D); null for SGD */
+  float* state2;    /* Adam v; null otherwise */
+  void* mirror;     /* (rows, 2*D) bf16 [hi | lo] or null */
+} mm_sparse_table;
+
+int mm_bce_head_fwd_bwd(const float* x, int64_t M, int K, int64_t x_stride, const float* w, const float* bias,
+                        const void* targets, int target_dtype, const float* sample_weight, float* logits,
+                        float* loss_sum, float* dx, int64_t dx_stride, int mask_relu, float* dw, float* db, void* stream);
+int mm_dense_wgrad(const float* x, int64_t M, int K, int64_t x_stride, const float* dz, int N, int64_t dz_stride,
+                   float* dw, float* db, void* stream);
+int mm_dense_dgrad(const float* dz, int64_t M, int N, int64_t dz_stride, const float* w, int K, const float* mask,
+                   int64_t mask_stride, float* dx, int64_t dx_stride, void* stream);
+int mm_dlrm_interact_backward(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, const float* bottom,
+                              int64_t bottom_stride, int bottom_slot, int P, const float* dA, int64_t dA_stride,
+                              float* const* grad_rows_host, int64_t grad_stride, float* d_bottom,
+                              int64_t d_bottom_stride, int mask_bottom, void* stream);
+int mm_sparse_rows_apply(const mm_sparse_table* tables_host, int n_tables, int64_t B, int D, int opt,
+                         const float* hyper, void* stream);
+int mm_dense_apply(int opt, float* w, float* grad, float* state1, float* state2, int64_t n, const float* hyper,
+                   float grad_scale, void* stream);
+int mm_opt_tick(float* hyper, void* stream);
+int mm_fill_i32(int32_t* p, int64_t n, int32_t value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,8 @@ from .topk import (AvgPrecisionAt, BruteForce, MRRAt, NDCGAt, PrecisionAt, Recal
 from .loader import Loader, sample_batch  # noqa: F401
 from .graph import CompiledForward, HostBatch, PipelinedForward  # noqa: F401
 from .sharded import ShardedEmbeddings, shard_model  # noqa: F401
-from . import datasets, io, ops  # noqa: F401
+from .train import SGD, Adagrad, Adam, DLRMTrainer, LazyAdam  # noqa: F401
+from . import datasets, io, ops, train  # noqa: F401
 from .io import load_merlin_metadata, save_merlin_metadata  # noqa: F401
 
 __version__ = "0.1.0"

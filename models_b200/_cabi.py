@@ -47,6 +47,27 @@ class LookupTable(C.Structure):
     ]
 
 
+class SparseTable(C.Structure):
+    """mm_sparse_table (include/mm_b200.h)."""
+
+    _fields_ = [
+        ("weights", C.c_void_p),
+        ("rows", C.c_int64),
+        ("indices", C.c_void_p),
+        ("idx_bytes", C.c_int32),
+        ("reserved", C.c_int32),
+        ("grad_rows", C.c_void_p),
+        ("rep_map", C.c_void_p),
+        ("state1", C.c_void_p),
+        ("state2", C.c_void_p),
+        ("mirror", C.c_void_p),
+    ]
+
+
+OPTIMIZERS = {"sgd": 0, "adagrad": 1, "adam": 2}
+HYPER_LR, HYPER_BETA1, HYPER_BETA2, HYPER_EPS, HYPER_STEP, HYPER_LR_T, HYPER_COUNT = 0, 1, 2, 3, 4, 5, 8
+
+
 class ConcatPiece(C.Structure):
     """mm_concat_piece (include/mm_b200.h)."""
 
@@ -110,6 +131,15 @@ SIGNATURES = {
     "mm_inbatch_scores_tc": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _i, _f, _vp, _f, _vp, _i64, _vp]),
     "mm_inbatch_scores": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _f,
                                _vp, _i64, _vp]),
+    "mm_bce_head_fwd_bwd": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "mm_dense_wgrad": (_i, [_vp, _i64, _i, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
+    "mm_dense_dgrad": (_i, [_vp, _i64, _i, _i64, _vp, _i, _vp, _i64, _vp, _i64, _vp]),
+    "mm_dlrm_interact_backward": (_i, [C.POINTER(LookupTable), _i, _i64, _i, _vp, _i64, _i, _i, _vp, _i64,
+                                       C.POINTER(C.c_void_p), _i64, _vp, _i64, _i, _vp]),
+    "mm_sparse_rows_apply": (_i, [C.POINTER(SparseTable), _i, _i64, _i, _i, _vp, _vp]),
+    "mm_dense_apply": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _vp, _f, _vp]),
+    "mm_opt_tick": (_i, [_vp, _vp]),
+    "mm_fill_i32": (_i, [_vp, _i64, C.c_int32, _vp]),
 }
 
 

@@ -1,0 +1,566 @@
+// Backward of the DLRM lookup + interaction stage and the optimizer kernels of the training step.
+//
+//   mm_dlrm_interact_backward   per sample: X = the F staged rows (table rows looked up again + bottom vector),
+//       G = symmetric (F x F) matrix of the pair gradients dA[P + pair(i, j)], zero diagonal; dX = G X.
+//       Row `bottom_slot` of dX (+ the shortcut gradient dA[:D], masked by bottom > 0 when the bottom tower ends in
+//       relu) is the bottom tower's gradient; every other row is the gradient of ONE embedding row and leaves as the
+//       reference's IndexedSlices: values (B, D) per table, indices = the batch's ids (tf.GradientTape over
+//       tf.gather, inputs/embedding.py:401-471; DotProductInteraction blocks/interaction.py:86-116).
+//       One warp per sample on mma.sync (3-pass split-bf16 like the forward kernel): G is the A operand (built from the
+//       staged dA row through a per-lane offset table), X the B operand.
+//   mm_sparse_rows_*            the optimizer step on IndexedSlices with duplicate ids, as Keras applies it
+//       (`_resource_apply_sparse_duplicate_indices`: sum the duplicates, then ONE update per unique row;
+//       LazyAdam blocks/optimizer.py:342 touches only the looked-up rows).  Dedup without a sort: a per-row int32 map
+//       (rows x 4 B, HBM is plentiful) elects the smallest sample index of every id as its representative
+//       (atomicMin), the other duplicates add their slice into the representative's slice (vector reds), and
+//       the representatives apply the update and reset the map.
+//   mm_dense_apply              SGD / Adagrad / Adam over a flat parameter arena (+ clears the gradients).
+#include <cuda_bf16.h>
+
+#include <climits>
+#include <cstring>
+
+#include "mm_common.cuh"
+
+namespace mm {
+namespace trs {
+
+__device__ __align__(16) float g_zero_row[128];
+
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x - xh, y - yh);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16_if(bool pred, uint32_t dst, const void* src) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst),
+      "l"(src), "r"((uint32_t)pred)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async4_if(bool pred, uint32_t dst, const void* src) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}" ::"r"(dst),
+      "l"(src), "r"((uint32_t)pred)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ long long load_id(const void* base, int w, long long s) {
+  switch (w) {
+    case 1: return (long long)reinterpret_cast<const uint8_t*>(base)[s];
+    case 2: return (long long)reinterpret_cast<const uint16_t*>(base)[s];
+    case 3: {
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(base) + 3 * s;
+      return (long long)b[0] | ((long long)b[1] << 8) | ((long long)b[2] << 16);
+    }
+    case 8: return reinterpret_cast<const long long*>(base)[s];
+    default: return (long long)reinterpret_cast<const int32_t*>(base)[s];
+  }
+}
+
+struct IbwdParams {
+  long long B;
+  int F, P, bottom_slot;
+  const float* bottom;  // (B, D) fp32 rows, the forward's bottom vector (null: no bottom row)
+  long long bottom_stride;
+  const float* dA;  // (B, P + F(F-1)/2): gradient of [bottom | pairs]
+  long long dA_stride;
+  int dA_vec;  // 16-byte copies of a dA row are legal
+  float* d_bottom;
+  long long d_bottom_stride;
+  int mask_bottom;
+  float* grad[MM_LOOKUP_MAX_ROWS];  // per staged row: (B, D) slice values of that table (null: none)
+  long long grad_stride;
+  int n_warps;
+  unsigned buf_bytes, stage_off, stage_floats;
+};
+
+template <int KD>
+__global__ void __launch_bounds__(256, 1) interact_bwd_kernel(const __grid_constant__ LookupParams lk, const __grid_constant__ IbwdParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int D = KD;
+  constexpr int XS = D + 4;        // floats per staged row (+16 B: conflict-free column reads)
+  constexpr int L = D / 4;         // lanes per row in the copy loop
+  constexpr int R = 32 / L;        // rows per copy instruction
+  constexpr int NTL = D / 8;       // n-tiles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int F = p.F;
+  const int OW = p.P + F * (F - 1) / 2;
+  const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * (2u * p.buf_bytes);
+
+  // ---- rows >= F of both buffers and the zero slot of the dA stage stay zero for the whole kernel
+  {
+    float* mine = reinterpret_cast<float*>(smem + (size_t)warp * 2 * p.buf_bytes);
+    for (int e = lane; e < (int)(2 * p.buf_bytes / 4); e += 32) mine[e] = 0.0f;
+    __syncwarp();
+  }
+
+  // ---- G offsets (bytes into the dA stage) of this lane's A fragment elements: tile (mt, kt), register, element
+  uint32_t goff[2][2][4][2];
+  const uint32_t zero_slot = (p.stage_floats - 1) * 4u;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = 16 * mt + g + 8 * (r & 1);
+          const int j = 16 * kt + 2 * t + e + 8 * (r >> 1);
+          uint32_t off = zero_slot;
+          if (i != j && i < F && j < F) {
+            const int a = min(i, j), b = max(i, j);
+            off = (uint32_t)(p.P + a * (2 * F - a - 1) / 2 + (b - a - 1)) * 4u;
+          }
+          goff[mt][kt][r][e] = off;
+        }
+
+  // ---- owner role: lane r resolves the source of staged row r
+  const bool is_table = lane < F && lane != p.bottom_slot && lk.weights[lane] != nullptr;
+  const float* my_base = is_table ? lk.weights[lane] : nullptr;
+  const unsigned long long my_rows = is_table ? (unsigned long long)lk.rows[lane] : 0ull;
+  const int my_w = is_table ? lk.idx_bytes[lane] : 4;
+  const void* my_ids = is_table ? lk.indices[lane] : nullptr;
+
+  const int cl = lane % L, rl = lane / L;
+  float* gptr[4];
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    const int i = 8 * qd + g;
+    gptr[qd] = (i < F && i != p.bottom_slot) ? p.grad[i] : nullptr;
+  }
+
+  const long long stride_s = (long long)gridDim.x * p.n_warps;
+  const long long s_first = (long long)blockIdx.x * p.n_warps + warp;
+
+  auto issue = [&](long long s, uint32_t buf) {
+    const bool live = s < p.B;
+    const float* my_src = g_zero_row;
+    if (live) {
+      if (is_table) {
+        const unsigned long long idx = (unsigned long long)load_id(my_ids, my_w, s);
+        if (idx < my_rows) my_src = my_base + idx * D;
+      } else if (lane == p.bottom_slot && p.bottom) {
+        my_src = p.bottom + s * p.bottom_stride;
+      }
+    }
+    const uint32_t lo = (uint32_t)(uintptr_t)my_src, hi = (uint32_t)((uintptr_t)my_src >> 32);
+    const uint32_t xs = wbase + buf;
+    for (int r0 = 0; r0 < F; r0 += R) {
+      const int row = r0 + rl;
+      const uint32_t slo = __shfl_sync(0xffffffffu, lo, row & 31);
+      const uint32_t shi = __shfl_sync(0xffffffffu, hi, row & 31);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(((uintptr_t)shi << 32) | slo) + cl * 16;
+      cp_async16_if(live && row < F, xs + (uint32_t)(row * XS * 4 + cl * 16), src);
+    }
+    // the sample's dA row
+    const float* da = p.dA + s * p.dA_stride;
+    const uint32_t st = xs + p.stage_off;
+    if (p.dA_vec) {
+      for (int c = lane; c * 4 < OW; c += 32) cp_async16_if(live, st + (uint32_t)c * 16u, da + c * 4);
+    } else {
+      for (int c = lane; c < OW; c += 32) cp_async4_if(live, st + (uint32_t)c * 4u, da + c);
+    }
+    cp_async_commit();
+  };
+
+  issue(s_first, 0);
+  uint32_t buf = 0;
+  for (long long s = s_first; s < p.B; s += stride_s) {
+    issue(s + stride_s, buf ^ p.buf_bytes);
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint32_t xs = wbase + buf, st = xs + p.stage_off;
+    // a vector copy of the dA row may have written up to 3 floats past OW: the zero slot is the LAST stage float and
+    // the launcher keeps stage_floats >= roundup4(OW) + 4, so it is never touched.
+    // ---- A fragments of G
+    uint32_t ah[2][2][4], al[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          split_pair(lds32(st + goff[mt][kt][r][0]), lds32(st + goff[mt][kt][r][1]), ah[mt][kt][r], al[mt][kt][r]);
+    float acc[2][NTL][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.0f;
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        // B fragment: X[j][d], j = 16kt + {2t, 2t+1, 2t+8, 2t+9}, d = 8nt + g
+        const uint32_t a0 = xs + (uint32_t)(((16 * kt + 2 * t) * XS + 8 * nt + g) * 4);
+        uint32_t bh0, bl0, bh1, bl1;
+        split_pair(lds32(a0), lds32(a0 + XS * 4), bh0, bl0);
+        split_pair(lds32(a0 + 8 * XS * 4), lds32(a0 + 9 * XS * 4), bh1, bl1);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma16816(acc[mt][nt], ah[mt][kt], bl0, bl1);
+          mma16816(acc[mt][nt], al[mt][kt], bh0, bh1);
+          mma16816(acc[mt][nt], ah[mt][kt], bh0, bh1);
+        }
+      }
+    }
+    // ---- dX rows: acc[mt][nt][c] = dX[16mt + g + 8(c>>1)][8nt + 2t + (c&1)]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int qd = 2 * mt + h, i = 8 * qd + g;
+        if (i >= F) continue;
+        if (i == p.bottom_slot) {
+          if (p.d_bottom) {
+            float* drow = p.d_bottom + s * p.d_bottom_stride;
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+              const int d = 8 * nt + 2 * t;
+              float a = acc[mt][nt][2 * h], b = acc[mt][nt][2 * h + 1];
+              if (p.P > 0) {
+                a += lds32(st + (uint32_t)d * 4u);
+                b += lds32(st + (uint32_t)d * 4u + 4u);
+              }
+              if (p.mask_bottom) {
+                const uint32_t xa = xs + (uint32_t)((i * XS + d) * 4);
+                a = lds32(xa) > 0.0f ? a : 0.0f;
+                b = lds32(xa + 4u) > 0.0f ? b : 0.0f;
+              }
+              *reinterpret_cast<float2*>(drow + d) = make_float2(a, b);
+            }
+          }
+        } else if (gptr[qd]) {
+          float* drow = gptr[qd] + s * p.grad_stride;
+#pragma unroll
+          for (int nt = 0; nt < NTL; ++nt)
+            *reinterpret_cast<float2*>(drow + 8 * nt + 2 * t) = make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
+        }
+      }
+    __syncwarp();  // the buffer is refilled by the next iteration's copies
+    buf ^= p.buf_bytes;
+  }
+  cp_async_wait<0>();
+}
+
+template <int KD>
+static int launch_ibwd(const LookupParams& lk, IbwdParams p, cudaStream_t st) {
+  const int OW = p.P + p.F * (p.F - 1) / 2;
+  p.stage_off = 32u * (KD + 4) * 4u;
+  p.stage_floats = (unsigned)(((OW + 3) & ~3) + 4);
+  p.buf_bytes = (p.stage_off + p.stage_floats * 4u + 15u) & ~15u;
+  int warps = (int)((227u * 1024u) / (2u * p.buf_bytes));
+  if (warps > 8) warps = 8;
+  if (warps < 1) return MM_ERR_UNSUPPORTED;
+  p.n_warps = warps;
+  const size_t smem = (size_t)warps * 2 * p.buf_bytes;
+  auto kern = interact_bwd_kernel<KD>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("mm_dlrm_interact_backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  long long want = (p.B + warps - 1) / warps;
+  const long long sms = sm_count();
+  const unsigned grid = (unsigned)(want < sms ? want : sms);
+  kern<<<grid, 32 * warps, smem, st>>>(lk, p);
+  return check_launch("mm_dlrm_interact_backward");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse rows: dedup + optimizer
+// ---------------------------------------------------------------------------------------------------------------
+struct SparseTable {
+  float* w;
+  long long rows;
+  const void* ids;
+  int idx_bytes;
+  float* grad;  // (B, D) slice values (duplicates are folded into the representative's slice)
+  int* rep;     // (rows,) int32, INT_MAX when idle
+  float* s1;    // Adagrad accumulator / Adam m
+  float* s2;    // Adam v
+  __nv_bfloat16* mirror;  // operand-format copy of the table (rows, 2D) [hi | lo] or null
+};
+struct SparseParams {
+  SparseTable t[MM_LOOKUP_MAX_ROWS];
+  long long B;
+  int D;
+  int opt;
+  const float* hyper;  // device: see mm_b200.h MM_HYPER_*
+};
+
+__global__ void sparse_elect_kernel(const __grid_constant__ SparseParams p) {
+  const SparseTable& tb = p.t[blockIdx.y];
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const unsigned long long id = (unsigned long long)load_id(tb.ids, tb.idx_bytes, b);
+  if (id < (unsigned long long)tb.rows) atomicMin(tb.rep + id, (int)b);
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// one group of D/4 lanes per (sample, table)
+__global__ void sparse_fold_kernel(const __grid_constant__ SparseParams p) {
+  const SparseTable& tb = p.t[blockIdx.y];
+  const int L = p.D >> 2;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int c = threadIdx.x % L;
+  if (b >= p.B) return;
+  const unsigned long long id = (unsigned long long)load_id(tb.ids, tb.idx_bytes, b);
+  if (id >= (unsigned long long)tb.rows) return;
+  const int r = tb.rep[id];
+  if (r == (int)b) return;
+  const float4 v = *reinterpret_cast<const float4*>(tb.grad + b * p.D + 4 * c);
+  red_add_v4(tb.grad + (long long)r * p.D + 4 * c, v);
+}
+
+__device__ __forceinline__ float upd(int opt, float w, float g, float& s1, float& s2, const float* hy) {
+  const float lr = hy[MM_HYPER_LR];
+  if (opt == MM_OPT_SGD) return w - lr * g;
+  if (opt == MM_OPT_ADAGRAD) {
+    s1 += g * g;
+    return w - lr * g / (sqrtf(s1) + hy[MM_HYPER_EPS]);
+  }
+  // Adam (Keras: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), computed by mm_opt_tick)
+  const float b1 = hy[MM_HYPER_BETA1], b2 = hy[MM_HYPER_BETA2];
+  s1 = b1 * s1 + (1.0f - b1) * g;
+  s2 = b2 * s2 + (1.0f - b2) * g * g;
+  return w - hy[MM_HYPER_LR_T] * s1 / (sqrtf(s2) + hy[MM_HYPER_EPS]);
+}
+
+__global__ void sparse_apply_kernel(const __grid_constant__ SparseParams p) {
+  const SparseTable& tb = p.t[blockIdx.y];
+  const int L = p.D >> 2;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int c = threadIdx.x % L;
+  if (b >= p.B) return;
+  const unsigned long long id = (unsigned long long)load_id(tb.ids, tb.idx_bytes, b);
+  if (id >= (unsigned long long)tb.rows) return;
+  // every lane of the group reads the map BEFORE lane 0 resets it (the group sits inside one warp: D/4 <= 32)
+  const int r = tb.rep[id];
+  __syncwarp();
+  if (r != (int)b) return;
+  const long long off = (long long)id * p.D + 4 * c;
+  const float4 g = *reinterpret_cast<const float4*>(tb.grad + b * p.D + 4 * c);
+  float4 w = *reinterpret_cast<float4*>(tb.w + off);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), v = a;
+  if (p.opt != MM_OPT_SGD) a = *reinterpret_cast<float4*>(tb.s1 + off);
+  if (p.opt == MM_OPT_ADAM) v = *reinterpret_cast<float4*>(tb.s2 + off);
+  w.x = upd(p.opt, w.x, g.x, a.x, v.x, p.hyper);
+  w.y = upd(p.opt, w.y, g.y, a.y, v.y, p.hyper);
+  w.z = upd(p.opt, w.z, g.z, a.z, v.z, p.hyper);
+  w.w = upd(p.opt, w.w, g.w, a.w, v.w, p.hyper);
+  *reinterpret_cast<float4*>(tb.w + off) = w;
+  if (p.opt != MM_OPT_SGD) *reinterpret_cast<float4*>(tb.s1 + off) = a;
+  if (p.opt == MM_OPT_ADAM) *reinterpret_cast<float4*>(tb.s2 + off) = v;
+  if (tb.mirror) {
+    uint32_t h0, l0, h1, l1;
+    split_pair(w.x, w.y, h0, l0);
+    split_pair(w.z, w.w, h1, l1);
+    __nv_bfloat16* m = tb.mirror + (long long)id * 2 * p.D + 4 * c;
+    *reinterpret_cast<uint2*>(m) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(m + p.D) = make_uint2(l0, l1);
+  }
+  if (c == 0) tb.rep[id] = INT_MAX;
+}
+
+__global__ void dense_apply_kernel(int opt, float* __restrict__ w, float* __restrict__ g, float* __restrict__ s1,
+                                   float* __restrict__ s2, long long n, const float* __restrict__ hyper, float grad_scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float a = opt != MM_OPT_SGD ? s1[i] : 0.0f, v = opt == MM_OPT_ADAM ? s2[i] : 0.0f;
+    w[i] = upd(opt, w[i], g[i] * grad_scale, a, v, hyper);
+    if (opt != MM_OPT_SGD) s1[i] = a;
+    if (opt == MM_OPT_ADAM) s2[i] = v;
+    g[i] = 0.0f;
+  }
+}
+
+__global__ void opt_tick_kernel(float* hyper) {
+  const float t = hyper[MM_HYPER_STEP] + 1.0f;
+  hyper[MM_HYPER_STEP] = t;
+  const float b1 = hyper[MM_HYPER_BETA1], b2 = hyper[MM_HYPER_BETA2];
+  hyper[MM_HYPER_LR_T] = hyper[MM_HYPER_LR] * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+}
+
+__global__ void fill_i32_kernel(int* p, long long n, int v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace trs
+}  // namespace mm
+
+extern "C" {
+
+int mm_dlrm_interact_backward(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, const float* bottom,
+                              int64_t bottom_stride, int bottom_slot, int P, const float* dA, int64_t dA_stride,
+                              float* const* grad_rows_host, int64_t grad_stride, float* d_bottom, int64_t d_bottom_stride,
+                              int mask_bottom, void* stream) {
+  using namespace mm;
+  using namespace mm::trs;
+  MM_REQUIRE(tables_host && n_tables > 0 && dA && grad_rows_host && B >= 0, MM_ERR_ARG, "mm_dlrm_interact_backward: null pointer");
+  const int F = n_tables + (bottom ? 1 : 0);
+  MM_REQUIRE(F >= 2 && F <= MM_LOOKUP_MAX_ROWS, MM_ERR_UNSUPPORTED, "mm_dlrm_interact_backward: F=%d outside [2, 32]", F);
+  MM_REQUIRE(D == 16 || D == 32 || D == 64 || D == 128, MM_ERR_UNSUPPORTED, "mm_dlrm_interact_backward: D=%d not in {16,32,64,128}", D);
+  MM_REQUIRE(P == 0 || (P == D && bottom), MM_ERR_ARG, "mm_dlrm_interact_backward: P must be 0 or D (with a bottom vector)");
+  MM_REQUIRE(!bottom || (bottom_slot >= 0 && bottom_slot < F && bottom_stride >= D && (bottom_stride & 3) == 0 && ((uintptr_t)bottom & 15) == 0),
+             MM_ERR_ARG, "mm_dlrm_interact_backward: bad bottom slot / stride / alignment");
+  const int OW = P + F * (F - 1) / 2;
+  MM_REQUIRE(dA_stride >= OW, MM_ERR_ARG, "mm_dlrm_interact_backward: dA_stride < %d", OW);
+  MM_REQUIRE(grad_stride >= D && (grad_stride & 1) == 0, MM_ERR_ARG, "mm_dlrm_interact_backward: grad_stride must be even and >= D");
+  MM_REQUIRE(!d_bottom || (d_bottom_stride >= D && (d_bottom_stride & 1) == 0 && ((uintptr_t)d_bottom & 7) == 0), MM_ERR_ALIGN,
+             "mm_dlrm_interact_backward: d_bottom needs an even stride >= D and 8-byte alignment");
+  if (B == 0) return MM_OK;
+  LookupParams lk;
+  memset(&lk, 0, sizeof(lk));
+  lk.world = 1;
+  IbwdParams p;
+  memset(&p, 0, sizeof(p));
+  bool used[MM_LOOKUP_MAX_ROWS] = {};
+  if (bottom) used[bottom_slot] = true;
+  for (int i = 0; i < n_tables; ++i) {
+    const mm_lookup_table& tb = tables_host[i];
+    MM_REQUIRE(tb.weights && tb.indices && tb.rows > 0, MM_ERR_ARG, "mm_dlrm_interact_backward: table %d: null pointer or no rows", i);
+    MM_REQUIRE(tb.slot >= 0 && tb.slot < F && !used[tb.slot], MM_ERR_ARG, "mm_dlrm_interact_backward: table %d: bad or repeated slot %d", i, tb.slot);
+    MM_REQUIRE(tb.idx_bytes == 1 || tb.idx_bytes == 2 || tb.idx_bytes == 3 || tb.idx_bytes == 4 || tb.idx_bytes == 8, MM_ERR_ARG,
+               "mm_dlrm_interact_backward: table %d: idx_bytes %d", i, tb.idx_bytes);
+    MM_REQUIRE(!tb.peer_weights_host, MM_ERR_UNSUPPORTED, "mm_dlrm_interact_backward: row-sharded tables are not supported");
+    MM_REQUIRE(((uintptr_t)tb.weights & 15) == 0, MM_ERR_ALIGN, "mm_dlrm_interact_backward: table %d: weights must be 16-byte aligned", i);
+    used[tb.slot] = true;
+    lk.weights[tb.slot] = tb.weights;
+    lk.indices[tb.slot] = tb.indices;
+    lk.rows[tb.slot] = tb.rows;
+    lk.idx_bytes[tb.slot] = (unsigned char)tb.idx_bytes;
+    float* gr = grad_rows_host[i];
+    MM_REQUIRE(!gr || ((uintptr_t)gr & 7) == 0, MM_ERR_ALIGN, "mm_dlrm_interact_backward: grad_rows[%d] must be 8-byte aligned", i);
+    p.grad[tb.slot] = gr;
+  }
+  p.B = B;
+  p.F = F;
+  p.P = P;
+  p.bottom_slot = bottom ? bottom_slot : -1;
+  p.bottom = bottom;
+  p.bottom_stride = bottom_stride;
+  p.dA = dA;
+  p.dA_stride = dA_stride;
+  p.dA_vec = ((dA_stride & 3) == 0 && ((uintptr_t)dA & 15) == 0 && dA_stride >= ((OW + 3) & ~3)) ? 1 : 0;
+  p.d_bottom = d_bottom;
+  p.d_bottom_stride = d_bottom_stride;
+  p.mask_bottom = mask_bottom;
+  p.grad_stride = grad_stride;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (D) {
+    case 16: return launch_ibwd<16>(lk, p, st);
+    case 32: return launch_ibwd<32>(lk, p, st);
+    case 64: return launch_ibwd<64>(lk, p, st);
+    default: return launch_ibwd<128>(lk, p, st);
+  }
+}
+
+int mm_sparse_rows_apply(const mm_sparse_table* tables_host, int n_tables, int64_t B, int D, int opt, const float* hyper,
+                         void* stream) {
+  using namespace mm;
+  using namespace mm::trs;
+  MM_REQUIRE(tables_host && n_tables > 0 && n_tables <= MM_LOOKUP_MAX_ROWS && hyper && B >= 0, MM_ERR_ARG,
+             "mm_sparse_rows_apply: null pointer or n_tables outside [1, %d]", MM_LOOKUP_MAX_ROWS);
+  MM_REQUIRE(D >= 4 && D <= 128 && (D & 3) == 0 && (32 % (D / 4)) == 0, MM_ERR_UNSUPPORTED, "mm_sparse_rows_apply: D=%d (needs D %% 4 == 0, D/4 a divisor of 32)", D);
+  MM_REQUIRE(opt == MM_OPT_SGD || opt == MM_OPT_ADAGRAD || opt == MM_OPT_ADAM, MM_ERR_ARG, "mm_sparse_rows_apply: unknown optimizer %d", opt);
+  MM_REQUIRE(B < (int64_t)INT_MAX, MM_ERR_UNSUPPORTED, "mm_sparse_rows_apply: batch too large for the int32 representative map");
+  if (B == 0) return MM_OK;
+  SparseParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < n_tables; ++i) {
+    const mm_sparse_table& s = tables_host[i];
+    MM_REQUIRE(s.weights && s.indices && s.grad_rows && s.rep_map && s.rows > 0, MM_ERR_ARG, "mm_sparse_rows_apply: table %d: null pointer", i);
+    MM_REQUIRE(opt == MM_OPT_SGD || s.state1, MM_ERR_ARG, "mm_sparse_rows_apply: table %d: optimizer state missing", i);
+    MM_REQUIRE(opt != MM_OPT_ADAM || s.state2, MM_ERR_ARG, "mm_sparse_rows_apply: table %d: second optimizer state missing", i);
+    MM_REQUIRE((((uintptr_t)s.weights | (uintptr_t)s.grad_rows | (uintptr_t)s.state1 | (uintptr_t)s.state2) & 15) == 0, MM_ERR_ALIGN,
+               "mm_sparse_rows_apply: table %d: 16-byte alignment", i);
+    p.t[i].w = s.weights;
+    p.t[i].rows = s.rows;
+    p.t[i].ids = s.indices;
+    p.t[i].idx_bytes = s.idx_bytes;
+    p.t[i].grad = s.grad_rows;
+    p.t[i].rep = s.rep_map;
+    p.t[i].s1 = s.state1;
+    p.t[i].s2 = s.state2;
+    p.t[i].mirror = (__nv_bfloat16*)s.mirror;
+  }
+  p.B = B;
+  p.D = D;
+  p.opt = opt;
+  p.hyper = hyper;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = D / 4;
+  const unsigned bx1 = (unsigned)((B + 255) / 256), bxl = (unsigned)((B * L + 255) / 256);
+  sparse_elect_kernel<<<dim3(bx1, n_tables), 256, 0, st>>>(p);
+  int rc = check_launch("mm_sparse_rows_apply(elect)");
+  if (rc) return rc;
+  sparse_fold_kernel<<<dim3(bxl, n_tables), 256, 0, st>>>(p);
+  rc = check_launch("mm_sparse_rows_apply(fold)");
+  if (rc) return rc;
+  sparse_apply_kernel<<<dim3(bxl, n_tables), 256, 0, st>>>(p);
+  return check_launch("mm_sparse_rows_apply(apply)");
+}
+
+int mm_dense_apply(int opt, float* w, float* grad, float* state1, float* state2, int64_t n, const float* hyper, float grad_scale,
+                   void* stream) {
+  MM_REQUIRE(w && grad && hyper && n >= 0, MM_ERR_ARG, "mm_dense_apply: null pointer");
+  MM_REQUIRE(opt == MM_OPT_SGD || opt == MM_OPT_ADAGRAD || opt == MM_OPT_ADAM, MM_ERR_ARG, "mm_dense_apply: unknown optimizer %d", opt);
+  MM_REQUIRE(opt == MM_OPT_SGD || state1, MM_ERR_ARG, "mm_dense_apply: optimizer state missing");
+  MM_REQUIRE(opt != MM_OPT_ADAM || state2, MM_ERR_ARG, "mm_dense_apply: second optimizer state missing");
+  if (n == 0) return MM_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = 8LL * mm::sm_count();
+  if (blocks > cap) blocks = cap;
+  mm::trs::dense_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(opt, w, grad, state1, state2, (long long)n, hyper, grad_scale);
+  return mm::check_launch("mm_dense_apply");
+}
+
+int mm_opt_tick(float* hyper, void* stream) {
+  MM_REQUIRE(hyper, MM_ERR_ARG, "mm_opt_tick: null pointer");
+  mm::trs::opt_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+  return mm::check_launch("mm_opt_tick");
+}
+
+int mm_fill_i32(int32_t* p, int64_t n, int32_t value, void* stream) {
+  MM_REQUIRE(p && n >= 0, MM_ERR_ARG, "mm_fill_i32: null pointer");
+  if (n == 0) return MM_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = 16LL * mm::sm_count();
+  if (blocks > cap) blocks = cap;
+  mm::trs::fill_i32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, (long long)n, value);
+  return mm::check_launch("mm_fill_i32");
+}
+
+}  // extern "C"

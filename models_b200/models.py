@@ -15,7 +15,7 @@ import torch
 from . import ops
 from .blocks import (MLP, CrossBlock, CrossBlockSeq, DLRM, DLRMBlock, MLPBlock, _Dense, dense_engine,
                      run_dense_chain)
-from .core import Block, Prediction, TabularData, default_device, to_device, unique_name
+from .core import Block, Prediction, TabularData, batch_size_of, default_device, to_device, unique_name
 from .inputs import EmbeddingOptions, EmbeddingsBlock, InputBlockV2
 from .retrieval import ItemRetrievalTask, TwoTowerBlock
 from .schema import Schema, Tags
@@ -96,7 +96,7 @@ class Model(Block):
         self.schema = schema
         self._pinned: Dict[str, torch.Tensor] = {}
 
-    _TRANSIENT = {"_pinned": {}}
+    _TRANSIENT = {"_pinned": {}, "_trainer": None}
 
     @property
     def blocks(self) -> List[Block]:
@@ -176,6 +176,76 @@ class Model(Block):
         x = self.body(inputs, training=training, testing=testing)
         return self.prediction(x, features=inputs, targets=targets, training=training, testing=testing)
 
+    # -- training (models_b200/train.py; reference: models/base.py:1121-1231) ------------------
+    def _compile_training(self, optimizer, loss=None) -> None:
+        from .train import get_optimizer
+
+        if loss not in (None, "binary_crossentropy"):
+            raise NotImplementedError(f"loss {loss!r}: only the BinaryOutput default (binary cross-entropy) is implemented")
+        self.optimizer = get_optimizer(optimizer)
+        self._trainer = None
+
+    def trainer(self, batch_size: int, group=None):
+        """The static-buffer training engine for batches of (up to) `batch_size` samples (train.DLRMTrainer)."""
+        from .train import DLRMTrainer
+
+        if getattr(self, "optimizer", None) is None:
+            raise RuntimeError("compile() the model with an optimizer before training it")
+        tr = getattr(self, "_trainer", None)
+        if tr is None or tr.B < batch_size or tr.group is not group:
+            if tr is not None:
+                raise NotImplementedError("the training batch size grew after the first step: compile for the largest batch "
+                                          "(model.trainer(batch_size) before the first train_step)")
+            tr = self._trainer = DLRMTrainer(self, self.optimizer, batch_size, group=group)
+        return tr
+
+    def train_step(self, data) -> Dict[str, torch.Tensor]:
+        """One optimizer step on `data` = (inputs, targets[, sample_weight]); returns the reference's step metrics
+        {"loss", "loss_batch", "regularization_loss"} as device scalars (models/base.py:1121-1177)."""
+        if getattr(self, "optimizer", None) is None:
+            raise RuntimeError("compile() the model with an optimizer before training it")
+        if not isinstance(data, (tuple, list)) or len(data) < 2:
+            raise ValueError("train_step expects (inputs, targets) or (inputs, targets, sample_weight)")
+        x, y = data[0], data[1]
+        sw = data[2] if len(data) > 2 else None
+        if isinstance(y, dict):
+            if len(y) != 1:
+                raise NotImplementedError("multi-task targets are not implemented in the training step")
+            y = next(iter(y.values()))
+        if y is None:
+            raise ValueError("train_step needs targets")
+        self._check_inputs(x)
+        tr = self.trainer(batch_size_of(x))
+        loss = tr.step(x, y, sw)
+        return {"loss": loss[0], "loss_batch": loss[0], "regularization_loss": torch.zeros((), device=loss.device)}
+
+    def fit(self, x=None, y=None, batch_size: Optional[int] = None, epochs: int = 1, steps_per_epoch: Optional[int] = None,
+            verbose: int = 0, **kwargs):
+        """Keras `fit` over a models_b200.Loader (or any iterable of (inputs, targets)): returns a History-like object
+        whose `.history["loss"]` holds the mean batch loss of every epoch."""
+        if x is None:
+            raise ValueError("fit needs a loader / iterable of (inputs, targets) batches")
+        if y is not None:
+            raise NotImplementedError("fit(x, y): pass a Loader or an iterable of (inputs, targets) batches")
+        bs = batch_size or getattr(x, "batch_size", None)
+        history = {"loss": []}
+        for _ in range(int(epochs)):
+            total, n = None, 0
+            for inputs, targets in x:
+                if getattr(self, "_trainer", None) is None and bs:
+                    self._check_inputs(inputs)
+                    self.trainer(int(bs))
+                m = self.train_step((inputs, targets))
+                total = m["loss_batch"].clone() if total is None else total + m["loss_batch"]
+                n += 1
+                if steps_per_epoch and n >= steps_per_epoch:
+                    break
+            if n == 0:
+                raise ValueError("fit: the loader produced no batches")
+            history["loss"].append(float(total.item()) / n)
+        self.history = type("History", (), {"history": history})()
+        return self.history
+
     # -- CUDA-graph runtime (models_b200/graph.py) ---------------------------------------------
     def embedding_blocks(self) -> List[EmbeddingsBlock]:
         """Every EmbeddingsBlock of the model (they share one out-of-range index counter)."""
@@ -211,12 +281,24 @@ class Model(Block):
         for b in self.embedding_blocks():
             b.defer_check = bool(flag)
 
-    def compile(self, example: Union[Dict[str, np.ndarray], "HostBatch"], **call_kwargs) -> "CompiledForward":
-        """Capture this model's forward for `example`'s batch layout into a CUDA graph; the result
-        maps a packed pinned HostBatch to pinned host predictions with one H2D, one graph launch and
-        one D2H (see models_b200/graph.py)."""
-        from .graph import CompiledForward, HostBatch
+    def compile(self, example: Union[Dict[str, np.ndarray], "HostBatch", str, None] = None, *, optimizer=None, loss=None,
+                metrics=None, run_eagerly=None, **call_kwargs):
+        """Two uses, told apart by the argument:
 
+        * `compile(optimizer="adam")` / `compile("adagrad")` / `compile(optimizer=mm.Adagrad(0.01))` — Keras `compile`
+          (models/base.py: the reference's models are compiled before `fit`): picks the optimizer of the training step
+          (models_b200/train.py).  The loss is the prediction task's default (binary cross-entropy for BinaryOutput);
+          `metrics` / `run_eagerly` are accepted for signature parity.
+        * `compile(example_batch, **call_kwargs)` — capture this model's forward for `example`'s batch layout into a CUDA
+          graph; the result maps a packed pinned HostBatch to pinned host predictions with one H2D, one graph launch and
+          one D2H (models_b200/graph.py)."""
+        from .graph import CompiledForward, HostBatch
+        from .train import Optimizer
+
+        if optimizer is not None or isinstance(example, (str, Optimizer)) or example is None:
+            if example is not None and optimizer is not None:
+                raise ValueError("compile(): pass either an example batch (graph capture) or an optimizer (training)")
+            return self._compile_training(optimizer if optimizer is not None else (example or "adam"), loss)
         if not isinstance(example, HostBatch):
             example = HostBatch.like(example, self.input_columns())
         return CompiledForward(self, example, **call_kwargs)

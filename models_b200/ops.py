@@ -540,14 +540,18 @@ def split_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     return out
 
 
-def split_weights(W: torch.Tensor) -> torch.Tensor:
-    """Keras kernel (K, N) fp32 -> (Np, 2*Kp) bf16 K-major split (mm_split_weights); one-time."""
+def split_weights(W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Keras kernel (K, N) fp32 -> (Np, 2*Kp) bf16 K-major split (mm_split_weights); one-time (the training step refreshes
+    it in place through `out` after every optimizer update)."""
     _dev(W, "W", torch.float32)
     if W.dim() != 2 or not W.is_contiguous():
         raise ValueError("W must be a contiguous (K, N) matrix")
     K, N = W.shape
     Kp, Np = tc_padded_k(K), tc_padded_n(N)
-    out = torch.empty((Np, 2 * Kp), dtype=torch.bfloat16, device=W.device)
+    if out is None:
+        out = torch.empty((Np, 2 * Kp), dtype=torch.bfloat16, device=W.device)
+    elif tuple(out.shape) != (Np, 2 * Kp) or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous bf16 ({Np}, {2 * Kp}) matrix")
     _cabi.check(_lib().mm_split_weights(W.data_ptr(), K, N, out.data_ptr(), Kp, Np, _stream()), "mm_split_weights")
     return out
 
@@ -745,3 +749,155 @@ def dense_tc_head(a_split: torch.Tensor, K: int, w_split: torch.Tensor, N: int, 
                                 out.data_ptr(), _stream()),
         "mm_dense_tc_head")
     return out
+
+
+# ---- training step (include/mm_b200.h K14) -----------------------------------------------------------------------
+_TARGET_DTYPES = {torch.int32: MM_I32, torch.int64: MM_I64, torch.float32: _cabi.MM_F32, torch.float64: _cabi.MM_F64}
+
+
+def bce_head_fwd_bwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], targets: torch.Tensor,
+                     loss_sum: torch.Tensor, dx: Optional[torch.Tensor], dw: torch.Tensor, db: Optional[torch.Tensor],
+                     mask_relu: bool = True, sample_weight: Optional[torch.Tensor] = None,
+                     logits: Optional[torch.Tensor] = None) -> None:
+    """Dense(K -> 1) + sigmoid + binary cross-entropy, forward and backward (mm_bce_head_fwd_bwd).  loss_sum (1,), dw (K,),
+    db (1,) are ACCUMULATED; dx (M, K) is written (zeroed where x <= 0 when mask_relu)."""
+    _dev(x, "x", torch.float32), _dev(w, "w", torch.float32), _dev(targets, "targets"), _dev(loss_sum, "loss_sum", torch.float32)
+    _dev(dw, "dw", torch.float32)
+    M, K = x.shape
+    if w.numel() != K or dw.numel() != K or not w.is_contiguous() or not dw.is_contiguous():
+        raise ValueError(f"w and dw must hold {K} contiguous values")
+    if targets.numel() != M or not targets.is_contiguous() or targets.dtype not in _TARGET_DTYPES:
+        raise ValueError(f"targets must be {M} contiguous int32 / int64 / float32 / float64 values")
+    if sample_weight is not None and (sample_weight.numel() != M or sample_weight.dtype != torch.float32 or not sample_weight.is_contiguous()):
+        raise ValueError("sample_weight must be (M,) contiguous float32")
+    if logits is not None and (logits.numel() != M or logits.dtype != torch.float32 or not logits.is_contiguous()):
+        raise ValueError("logits must be (M,) contiguous float32")
+    _cabi.check(
+        _lib().mm_bce_head_fwd_bwd(x.data_ptr(), M, K, _row_stride(x, "x"), w.data_ptr(), _ptr(bias), targets.data_ptr(),
+                                   _TARGET_DTYPES[targets.dtype], _ptr(sample_weight), _ptr(logits), loss_sum.data_ptr(), _ptr(dx),
+                                   0 if dx is None else _row_stride(_dev(dx, "dx", torch.float32), "dx"), 1 if mask_relu else 0,
+                                   dw.data_ptr(), _ptr(db), _stream()),
+        "mm_bce_head_fwd_bwd")
+
+
+def dense_wgrad(x: torch.Tensor, dz: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
+    """dw (K, N) += x^T dz;  db (N,) += column sums of dz  (mm_dense_wgrad; accumulated)."""
+    _dev(x, "x", torch.float32), _dev(dz, "dz", torch.float32), _dev(dw, "dw", torch.float32)
+    M, K = x.shape
+    N = dz.shape[1]
+    if dz.shape[0] != M or tuple(dw.shape) != (K, N) or not dw.is_contiguous():
+        raise ValueError(f"dz must be ({M}, N) and dw a contiguous ({K}, {N}) matrix")
+    if db is not None and (_dev(db, "db", torch.float32).numel() != N or not db.is_contiguous()):
+        raise ValueError(f"db must hold {N} contiguous values")
+    _cabi.check(_lib().mm_dense_wgrad(x.data_ptr(), M, K, _row_stride(x, "x"), dz.data_ptr(), N, _row_stride(dz, "dz"), dw.data_ptr(),
+                                      _ptr(db), _stream()), "mm_dense_wgrad")
+
+
+def dense_dgrad(dz: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx (M, K) = dz (M, N) @ W^T, W the Keras kernel (K, N), zeroed where mask <= 0 (mm_dense_dgrad; N <= 128)."""
+    _dev(dz, "dz", torch.float32), _dev(W, "W", torch.float32), _dev(dx, "dx", torch.float32)
+    M, N = dz.shape
+    if W.dim() != 2 or W.shape[1] != N or not W.is_contiguous():
+        raise ValueError(f"W must be a contiguous (K, {N}) matrix")
+    K = W.shape[0]
+    if dx.shape[0] != M or dx.shape[1] != K:
+        raise ValueError(f"dx must be ({M}, {K})")
+    if mask is not None and (_dev(mask, "mask", torch.float32).shape[0] != M or mask.shape[1] != K):
+        raise ValueError(f"mask must be ({M}, {K})")
+    _cabi.check(_lib().mm_dense_dgrad(dz.data_ptr(), M, N, _row_stride(dz, "dz"), W.data_ptr(), K, _ptr(mask),
+                                      0 if mask is None else _row_stride(mask, "mask"), dx.data_ptr(), _row_stride(dx, "dx"),
+                                      _stream()), "mm_dense_dgrad")
+    return dx
+
+
+def dlrm_interact_backward(weights, indices, slots, rows, D: int, bottom: Optional[torch.Tensor], bottom_slot: int,
+                           dA: torch.Tensor, grad_rows, d_bottom: Optional[torch.Tensor], mask_bottom: bool = True) -> None:
+    """Backward of dlrm_lookup_interact (fp32 rows, replicated tables): grad_rows[t] (B, D) <- IndexedSlices values of table t,
+    d_bottom (B, D) <- gradient of the bottom vector (mm_dlrm_interact_backward)."""
+    _dev(dA, "dA", torch.float32)
+    B = dA.shape[0]
+    n = len(weights)
+    if not (len(indices) == n and len(slots) == n and len(rows) == n and len(grad_rows) == n):
+        raise ValueError("weights / indices / slots / rows / grad_rows length mismatch")
+    arr = (_cabi.LookupTable * n)()
+    gp = (C.c_void_p * n)()
+    gstride = None
+    for t in range(n):
+        w = _dev(weights[t], f"weights[{t}]", torch.float32)
+        ix = _dev(indices[t], f"indices[{t}]")
+        if w.dim() != 2 or w.shape[1] != D or not w.is_contiguous():
+            raise ValueError(f"weights[{t}] must be a contiguous (rows, {D}) float32 matrix")
+        wb = index_bytes_of(ix)
+        if ix.numel() != B * (3 if wb == 3 else 1) or not ix.is_contiguous():
+            raise ValueError(f"indices[{t}] must be contiguous with {B} ids")
+        arr[t].weights, arr[t].indices, arr[t].rows, arr[t].slot, arr[t].idx_bytes = w.data_ptr(), ix.data_ptr(), int(rows[t]), int(slots[t]), wb
+        g = grad_rows[t]
+        if g is not None:
+            _dev(g, f"grad_rows[{t}]", torch.float32)
+            if g.shape[0] != B or g.shape[1] != D:
+                raise ValueError(f"grad_rows[{t}] must be ({B}, {D})")
+            st = _row_stride(g, f"grad_rows[{t}]")
+            if gstride not in (None, st):
+                raise ValueError("all grad_rows must share one row stride")
+            gstride = st
+            gp[t] = g.data_ptr()
+    P = 0
+    F = n + (1 if bottom is not None else 0)
+    if bottom is not None:
+        _dev(bottom, "bottom", torch.float32)
+        P = dA.shape[1] - F * (F - 1) // 2
+    _cabi.check(
+        _lib().mm_dlrm_interact_backward(arr, n, B, D, _ptr(bottom), 0 if bottom is None else _row_stride(bottom, "bottom"),
+                                         bottom_slot, P, dA.data_ptr(), _row_stride(dA, "dA"), gp, gstride or D, _ptr(d_bottom),
+                                         0 if d_bottom is None else _row_stride(_dev(d_bottom, "d_bottom", torch.float32), "d_bottom"),
+                                         1 if mask_bottom else 0, _stream()),
+        "mm_dlrm_interact_backward")
+
+
+def sparse_rows_apply(opt: str, tables, B: int, D: int, hyper: torch.Tensor) -> None:
+    """Optimizer step on IndexedSlices (mm_sparse_rows_apply).  tables: dicts with weights, indices, grad_rows, rep_map and, per
+    optimizer, state1 / state2, optionally mirror."""
+    _dev(hyper, "hyper", torch.float32)
+    n = len(tables)
+    arr = (_cabi.SparseTable * n)()
+    for t, tb in enumerate(tables):
+        w = _dev(tb["weights"], f"tables[{t}].weights", torch.float32)
+        ix = _dev(tb["indices"], f"tables[{t}].indices")
+        g = _dev(tb["grad_rows"], f"tables[{t}].grad_rows", torch.float32)
+        rep = _dev(tb["rep_map"], f"tables[{t}].rep_map", torch.int32)
+        if w.dim() != 2 or w.shape[1] != D or not w.is_contiguous() or tuple(g.shape) != (B, D) or not g.is_contiguous():
+            raise ValueError(f"tables[{t}]: weights must be contiguous (rows, {D}) and grad_rows contiguous ({B}, {D})")
+        if rep.numel() != w.shape[0]:
+            raise ValueError(f"tables[{t}]: rep_map must hold one int32 per row")
+        arr[t].weights, arr[t].rows, arr[t].indices, arr[t].idx_bytes = w.data_ptr(), w.shape[0], ix.data_ptr(), index_bytes_of(ix)
+        arr[t].grad_rows, arr[t].rep_map = g.data_ptr(), rep.data_ptr()
+        for key in ("state1", "state2"):
+            s = tb.get(key)
+            if s is not None and (_dev(s, f"tables[{t}].{key}", torch.float32).shape != w.shape or not s.is_contiguous()):
+                raise ValueError(f"tables[{t}].{key} must match the weights")
+            setattr(arr[t], key, _ptr(s))
+        m = tb.get("mirror")
+        if m is not None and (_dev(m, f"tables[{t}].mirror", torch.bfloat16).shape != (w.shape[0], 2 * D) or not m.is_contiguous()):
+            raise ValueError(f"tables[{t}].mirror must be contiguous bf16 (rows, {2 * D})")
+        arr[t].mirror = _ptr(m)
+    _cabi.check(_lib().mm_sparse_rows_apply(arr, n, B, D, _cabi.OPTIMIZERS[opt], hyper.data_ptr(), _stream()), "mm_sparse_rows_apply")
+
+
+def dense_apply(opt: str, w: torch.Tensor, grad: torch.Tensor, state1: Optional[torch.Tensor], state2: Optional[torch.Tensor],
+                hyper: torch.Tensor, grad_scale: float = 1.0) -> None:
+    """Optimizer step over a flat fp32 arena; grad is scaled by grad_scale and cleared (mm_dense_apply)."""
+    for n_, t_ in (("w", w), ("grad", grad), ("hyper", hyper)):
+        _dev(t_, n_, torch.float32)
+    if not (w.is_contiguous() and grad.is_contiguous() and w.numel() == grad.numel()):
+        raise ValueError("w and grad must be contiguous and equally sized")
+    _cabi.check(_lib().mm_dense_apply(_cabi.OPTIMIZERS[opt], w.data_ptr(), grad.data_ptr(), _ptr(state1), _ptr(state2), w.numel(),
+                                      hyper.data_ptr(), float(grad_scale), _stream()), "mm_dense_apply")
+
+
+def opt_tick(hyper: torch.Tensor) -> None:
+    _cabi.check(_lib().mm_opt_tick(_dev(hyper, "hyper", torch.float32).data_ptr(), _stream()), "mm_opt_tick")
+
+
+def fill_i32(t: torch.Tensor, value: int) -> torch.Tensor:
+    _cabi.check(_lib().mm_fill_i32(_dev(t, "t", torch.int32).data_ptr(), t.numel(), int(value), _stream()), "mm_fill_i32")
+    return t

@@ -22,6 +22,9 @@ and runs the reference's module files unmodified, from where they lie:
   torch/models/ranking.py   DLRMModel and DCNModel END TO END including BinaryOutput (Linear(1) + sigmoid): the
                             model-level outputs {target: (B, 1)} (pytorch_lightning.LightningModule is replaced by
                             an empty torch.nn.Module subclass)
+  torch/models/ranking.py + torch/outputs/classification.py:44   ONE TRAINING STEP's gradients of that DLRMModel: the
+                            backend's default BinaryOutput loss (nn.BCELoss on the sigmoid outputs) and torch.autograd
+                            through the reference's modules -> loss, d/d(every Linear kernel and bias), d/d(tables)
   torch/outputs/classification.py  EmbeddingTablePrediction (weight-tied catalog logits x @ E^T + bias) with the
                             backend's default loss nn.CrossEntropyLoss evaluated on them
   utils/schema_utils.py     infer_embedding_dim / get_embedding_size_from_cardinality (backend-independent host code,
@@ -317,6 +320,39 @@ def main():
              **pack("bottom", [m for n, m in L if ".continuous." in f".{n}."], "relu"),
              **pack("top", [m for n, m in L if ".continuous." not in f".{n}."][:2], "relu"),
              **pack("head", [L[-1][1]], "sigmoid"))
+
+    # ---- 9a. one TRAINING step's gradients of the same DLRMModel: the backend's default BinaryOutput loss (nn.BCELoss on
+    # the sigmoid outputs, torch/outputs/classification.py:44) and torch.autograd through the reference's own modules.
+    # Its own rng: the draws of the sections below must not move.
+    y_train = np.random.default_rng(914).integers(0, 2, Bm).astype(np.float32)
+    loss_mods = [m for m in dm.modules() if isinstance(m, torch.nn.BCELoss)]
+    assert len(loss_mods) == 1, loss_mods
+    dm.zero_grad()
+    train_loss = loss_mods[0](dout, torch.from_numpy(y_train).reshape(-1, 1))
+    train_loss.backward()
+
+    def pack_grads(tag, lins):
+        d = {}
+        for i, l in enumerate(lins):
+            d[f"grad_{tag}_kernel_{i}"] = l.weight.grad.detach().numpy().T.copy()
+            d[f"grad_{tag}_bias_{i}"] = l.bias.grad.detach().numpy().copy()
+        return d
+
+    tgrads = {}
+    for name, m in dm.named_modules():
+        if isinstance(m, torch.nn.Embedding):
+            feat = [n for n, _ in cats if f".{n}." in f".{name}."][0]
+            tgrads[f"grad_table_{feat}"] = m.weight.grad.detach().numpy().copy()
+    np.savez(OUT / "ref_torch_dlrm_train.npz", kind="dlrm_train", cat_names=np.array([n for n, _ in cats]),
+             cat_max=np.array([mx for _, mx in cats], dtype=np.int64), cont_names=np.array(conts), dim=np.int64(dim),
+             out=dout.detach().numpy(), targets=y_train, loss=np.float32(train_loss.item()),
+             **{f"batch_{k}": v for k, v in batch.items()}, **tables_of(dm),
+             **pack("bottom", [m for n, m in L if ".continuous." in f".{n}."], "relu"),
+             **pack("top", [m for n, m in L if ".continuous." not in f".{n}."][:2], "relu"),
+             **pack("head", [L[-1][1]], "sigmoid"),
+             **pack_grads("bottom", [m for n, m in L if ".continuous." in f".{n}."]),
+             **pack_grads("top", [m for n, m in L if ".continuous." not in f".{n}."][:2]),
+             **pack_grads("head", [L[-1][1]]), **tgrads)
 
     torch.manual_seed(12)
     cm = ranking.DCNModel(mschema, depth=3, deep_block=mlpm.MLPBlock([32, 16]))

@@ -124,6 +124,21 @@ def check(path: Path) -> None:
             cross = [{"kernel": l["kernel"], "bias": l["bias"]} for l in unpack_layers(z, "cross")]
             got = oracle.dcn_forward(batch, tables, {n: n for n in cat}, cont, cross, unpack_layers(z, "deep"), head)
         np.testing.assert_allclose(got, z["out"], rtol=1e-4, atol=1e-5)
+    elif kind == "dlrm_train":
+        # one training step of the reference's torch DLRMModel: its default BinaryOutput loss + torch.autograd through its
+        # modules -> loss and the gradient of every variable
+        from oracle import oracle_train
+
+        cat = [str(n) for n in z["cat_names"]]
+        batch = {k[len("batch_"):]: z[k] for k in z if k.startswith("batch_")}
+        tables = {n: z[f"table_{n}"] for n in cat}
+        cont = [str(n) for n in z["cont_names"]]
+        loss, logits, grads = oracle_train.dlrm_loss_and_grads(batch, tables, {n: n for n in cat}, cont, unpack_layers(z, "bottom"),
+                                                                unpack_layers(z, "top"), unpack_layers(z, "head")[0], z["targets"])
+        np.testing.assert_allclose(1.0 / (1.0 + np.exp(-logits)), z["out"].reshape(-1), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(loss, float(z["loss"]), rtol=1e-5)
+        for name, want in train_grad_items(z):
+            np.testing.assert_allclose(grads[name], want, rtol=2e-4, atol=1e-7, err_msg=name)
     elif kind == "two_tower":
         # reference torch towers: TabularInputBlock(continuous + EmbeddingTables(mean combiner), agg="concat") -> MLPBlock,
         # then the backend's retrieval pieces on the tower outputs
@@ -163,6 +178,20 @@ def unpack_layers(z, name):
         b = z[f"{name}_bias_{i}"] if f"{name}_bias_{i}" in z else None
         out.append({"kernel": z[f"{name}_kernel_{i}"], "bias": b, "activation": str(z[f"{name}_act_{i}"])})
         i += 1
+    return out
+
+
+def train_grad_items(z):
+    """(oracle gradient name, golden array) pairs of a `dlrm_train` fixture."""
+    out = [(f"table/{str(n)}", z[f"grad_table_{str(n)}"]) for n in z["cat_names"]]
+    for tag in ("bottom", "top"):
+        i = 0
+        while f"grad_{tag}_kernel_{i}" in z:
+            out.append((f"{tag}/kernel_{i}", z[f"grad_{tag}_kernel_{i}"]))
+            out.append((f"{tag}/bias_{i}", z[f"grad_{tag}_bias_{i}"]))
+            i += 1
+    out.append(("head/kernel", z["grad_head_kernel_0"]))
+    out.append(("head/bias", z["grad_head_bias_0"]))
     return out
 
 
