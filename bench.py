@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the B200 hot path (BASELINE.json: DLRM & TwoTower fwd samples/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload all|dlrm|dlrm-sharded|twotower|dcn] [--batch B]
+                    [--workload all|dlrm|dlrm-sharded|twotower|dcn|dlrm-train] [--batch B]
 
 Headline workload = BASELINE.json configs[1]: mm.DLRMModel, Criteo shape (26 cat, 13 dense, emb 64,
 bundled cardinalities = 45.6 M rows / 11.7 GB of tables), batch 65 536, README MLP dims.
@@ -18,7 +18,8 @@ reference op sequence on this box's host cores (rank 0, N=1 only).
 The default `--workload all` adds to the same line:
   "secondary": {"twotower": {...}, "dcn": {...}} — configs[2] (10 M-item catalog, in-batch negatives,
       batch 16 384) and configs[4] (DCN-v2 depth 3 + MLP[256,128], batch 65 536), each with its own value,
-      e2e and roofline (the other half of BASELINE.json's metric), replicas under torchrun;
+      e2e and roofline (the other half of BASELINE.json's metric), replicas under torchrun; plus "dlrm_train":
+      one TRAINING step of the headline DLRM (forward + BCE + backward + Adagrad, SURVEY §8(f)-4) as one CUDA graph;
   "sharded": {...} (N > 1 only) — configs[3]: Criteo-TB-shape tables row-sharded over the N GPUs, lookup
       fused into the interaction kernel over NVLink peer memory, checked bit-exact against the unsharded
       model on the same box, with ms/step, NVLink GB/s per GPU and the staged (all-gather + push + barrier)
@@ -443,7 +444,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "dlrm", "dlrm-sharded", "twotower", "dcn"])
+    ap.add_argument("--workload", default="all", choices=["all", "dlrm", "dlrm-sharded", "twotower", "dcn", "dlrm-train"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=None, help="samples per CPU pass (default: the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -493,6 +494,11 @@ def main():
         rec.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "unit": "samples/s"})
         return finish(rec)
+    if args.workload == "dlrm-train":
+        rec = train_record(ctx)
+        rec.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None})
+        return finish(rec)
     if args.workload in ("twotower", "dcn"):
         rec = secondary_record(ctx, args.workload)
         rec.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
@@ -515,6 +521,11 @@ def main():
             except Exception as e:  # a secondary record must never take the headline down
                 line["secondary"][kind] = {"error": f"{type(e).__name__}: {e}"}
             free_device_memory()
+        try:
+            line["secondary"]["dlrm_train"] = train_record(ctx)
+        except Exception as e:
+            line["secondary"]["dlrm_train"] = {"error": f"{type(e).__name__}: {e}"}
+        free_device_memory()
         if world > 1:
             try:
                 line["sharded"] = sharded_record(ctx)
@@ -742,6 +753,97 @@ def sharded_record(ctx):
 # ---------------------------------------------------------------------------------------------
 # configs[2] and configs[4]: two-tower and DCN-v2 (replicas under torchrun)
 # ---------------------------------------------------------------------------------------------
+def train_record(ctx):
+    """ONE TRAINING STEP of the headline DLRM (forward with saved activations + binary cross-entropy +
+    backward + Adagrad update of every variable, embedding rows included) per batch of 65 536 samples — the reference's
+    `model.fit` inner loop (models/base.py:1121-1177).  Replicas under torchrun (each rank trains its own copy: no
+    gradient exchange is timed here).  `value`: CUDA-graph replay over rotating device-resident batches (a D2D refresh of
+    the static input buffer is part of the step); `e2e`: packed pinned host batch (ids + dense + labels) -> one H2D ->
+    graph -> D2H of the loss."""
+    import torch
+
+    args, mm, datasets, ops, dev, world = ctx.args, ctx.mm, ctx.datasets, ctx.ops, ctx.dev, ctx.world
+    B = args.batch if (args.batch and args.workload == "dlrm-train") else 65536
+    steps = args.steps
+    mm.set_seed(1)
+    schema, model = build_dlrm(mm, datasets)
+    model.build(dev)
+    model.compile(optimizer=mm.Adagrad(0.01))
+    n_bufs = 4
+    hosts = []
+    for i in range(n_bufs):
+        hosts.append(datasets.generate_batch(schema, B, seed=4321 + i + 1000 * ctx.rank, index_law="uniform", index_dtype=np.int32))
+    label = schema.select_by_tag(mm.Tags.TARGET).column_names[0]
+    names = model.input_columns() + [label]
+    hbs = [mm.HostBatch.like(h, names, id_bytes=model.id_bytes()) for h in hosts]
+    packed_dev = [hb.buffer.to(dev) for hb in hbs]
+    from models_b200.graph import _view
+
+    static = torch.empty(hbs[0].buffer.numel(), dtype=torch.uint8, device=dev)
+    static.copy_(packed_dev[0])
+    views = {name: _view(static, hbs[0].offsets[name], shp, dt) for name, (shp, dt) in hbs[0].spec.items()}
+    inputs = {k: v for k, v in views.items() if k != label}
+    tr = model.trainer(B)
+    # per-phase device times of the eager step (CUDA events around each phase)
+    phase = {}
+    for name, fn in (("forward_backward", lambda i: tr.forward_backward(inputs, views[label])), ("update", lambda i: tr.apply_gradients())):
+        phase[name + "_ms"] = event_times(fn, 10)
+    n0 = ops.launch_count()
+    tr.capture(inputs, views[label], clone=False)
+
+    def run(n):
+        for i in range(n):
+            static.copy_(packed_dev[i % n_bufs], non_blocking=True)
+            tr.replay()
+
+    run(args.warmup)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    run(steps)
+    t1.record()
+    ctx.barrier()
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1)
+    loss_end = float(tr.loss.item())
+    # e2e: pinned host batch -> H2D -> graph -> loss to the host
+    loss_host = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+
+    def e2e(n):
+        for i in range(n):
+            static.copy_(hbs[i % n_bufs].buffer, non_blocking=True)
+            tr.replay()
+            loss_host.copy_(tr.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e(3)
+    ctx.barrier()
+    w0 = time.perf_counter()
+    e2e(steps)
+    e2e_ms = (time.perf_counter() - w0) * 1e3
+    ctx.barrier()
+    ms_max, e2e_max = ctx.max_over_ranks(ms, e2e_ms)
+    rec = {
+        "metric": "DLRM TRAIN samples/sec (Criteo shape, batch 65536/GPU, forward + BCE + backward + Adagrad)",
+        "value": B * world * steps / (ms_max / 1e3), "unit": "samples/s", "ms_per_step": ms_max / steps,
+        "dtype": "fp32 variables and I/O; split-bf16 x3 GEMM work", "data": "synthetic (uniform indices; hash-initialised tables)",
+        "config": {"workload": "mm.DLRMModel Criteo-shape (26 cat, 13 dense, emb_dim 64), bottom [128,64], top [128,64,32]; "
+                               "model.compile(Adagrad(0.01)); one optimizer step per batch",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"replicas x{world} (no gradient exchange timed)",
+                   "l2": "4 rotating input batches; tables, activations and slices exceed L2",
+                   "runtime": "one CUDA graph per step (forward + backward + update), static buffers"},
+        "clocks": clocks, "gpu_launches": tr.launches_per_step * steps, "launches_per_step": tr.launches_per_step,
+        "eager_phase_ms": phase, "loss_after": loss_end,
+        "e2e": {"value": B * world * steps / (e2e_max / 1e3), "unit": "samples/s", "h2d_bytes_per_step": int(hbs[0].buffer.numel()),
+                "d2h_bytes_per_step": 4, "steps": steps},
+        "fwd_only_ratio_note": "compare with the headline `value` (forward only) of the same line",
+    }
+    del tr, model
+    return rec
+
+
 def secondary_record(ctx, kind):
     """BASELINE configs[2] (two-tower, 10 M-item catalog, in-batch negatives, B = 16 384) and configs[4]
     (DCN-v2, depth 3, deep [256,128], B = 65 536): same timing protocol as the DLRM arm (graph replay on two

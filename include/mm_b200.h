@@ -451,6 +451,10 @@ typedef struct {
   float* state1;    /* Adagrad accumulator / Adam m, (rows, D); null for SGD */
   float* state2;    /* Adam v; null otherwise */
   void* mirror;     /* (rows, 2*D) bf16 [hi | lo] or null */
+  float* dense_grad; /* (rows, D) fp32, all zero between calls, or null.  Non-null selects the dense path for tables with
+                      * few rows (every id repeated many times per batch): slices are summed into this accumulator (rows
+                      * <= 1024: each CTA first sorts its samples by row and sums the runs in registers), rep_map only
+                      * flags the touched rows, and the update walks the rows.  Null: the election path (rows >> batch: duplicates are rare). */
 } mm_sparse_table;
 
 int mm_bce_head_fwd_bwd(const float* x, int64_t M, int K, int64_t x_stride, const float* w, const float* bias,

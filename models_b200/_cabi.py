@@ -61,6 +61,7 @@ class SparseTable(C.Structure):
         ("state1", C.c_void_p),
         ("state2", C.c_void_p),
         ("mirror", C.c_void_p),
+        ("dense_grad", C.c_void_p),
     ]
 
 

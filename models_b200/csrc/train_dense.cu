@@ -147,6 +147,93 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   }
 }
 
+// K a multiple of 4 with 16-byte aligned rows: G = K/4 (rounded up to a power of two, <= 32) lanes own one row as
+// float4 pieces, a warp processes 32/G rows at a time (K = 32: 4 rows per warp, one 128-byte row per 8 lanes).
+template <int G>
+__global__ void __launch_bounds__(256) head_kernel_v4(const HeadParams p) {
+  const int lane = threadIdx.x & 31;
+  const int c = lane % G, sub = lane / G;
+  constexpr int RPW = 32 / G;  // rows per warp and iteration
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool on = 4 * c < p.K;
+  const float4 w = on ? *reinterpret_cast<const float4*>(p.w + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float b = p.bias ? p.bias[0] : 0.0f;
+  float loss = 0.0f, db = 0.0f;
+  const long long groups = (p.M + RPW - 1) / RPW;
+  for (long long gi = warp; gi < groups; gi += n_warps) {
+    const long long m = gi * RPW + sub;
+    const bool live = m < p.M;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && on) x = __ldg(reinterpret_cast<const float4*>(p.x + m * p.ldx + 4 * c));
+    float dot = x.x * w.x + x.y * w.y + x.z * w.z + x.w * w.w;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float z = dot + b;
+    float dz = 0.0f;
+    if (live) {
+      const float y = load_target(p.y, m, p.y_dtype);
+      const float sw = p.sample_w ? p.sample_w[m] : 1.0f;
+      const float e = expf(-fabsf(z));
+      const float sig = z >= 0.0f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+      dz = (sig - y) * sw * p.inv_m;
+      if (c == 0) {
+        loss += (fmaxf(z, 0.0f) - z * y + log1pf(e)) * sw * p.inv_m;
+        db += dz;
+        if (p.logits) p.logits[m] = z;
+      }
+    }
+    dw.x = fmaf(x.x, dz, dw.x);
+    dw.y = fmaf(x.y, dz, dw.y);
+    dw.z = fmaf(x.z, dz, dw.z);
+    dw.w = fmaf(x.w, dz, dw.w);
+    if (live && on && p.dx) {
+      float4 d;
+      d.x = (!p.mask_relu || x.x > 0.0f) ? dz * w.x : 0.0f;
+      d.y = (!p.mask_relu || x.y > 0.0f) ? dz * w.y : 0.0f;
+      d.z = (!p.mask_relu || x.z > 0.0f) ? dz * w.z : 0.0f;
+      d.w = (!p.mask_relu || x.w > 0.0f) ? dz * w.w : 0.0f;
+      *reinterpret_cast<float4*>(p.dx + m * p.lddx + 4 * c) = d;
+    }
+  }
+  // lanes with the same c hold partial sums of the same columns: fold the row groups of the warp, then the block
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) {
+    dw.x += __shfl_xor_sync(0xffffffffu, dw.x, o);
+    dw.y += __shfl_xor_sync(0xffffffffu, dw.y, o);
+    dw.z += __shfl_xor_sync(0xffffffffu, dw.z, o);
+    dw.w += __shfl_xor_sync(0xffffffffu, dw.w, o);
+    loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    db += __shfl_xor_sync(0xffffffffu, db, o);
+  }
+  __shared__ float red[8][4 * G + 2];
+  const int wid = threadIdx.x >> 5;
+  if (lane < G) {
+    red[wid][4 * lane] = dw.x;
+    red[wid][4 * lane + 1] = dw.y;
+    red[wid][4 * lane + 2] = dw.z;
+    red[wid][4 * lane + 3] = dw.w;
+  }
+  if (lane == 0) {
+    red[wid][4 * G] = db;
+    red[wid][4 * G + 1] = loss;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  for (int k = threadIdx.x; k < 4 * G + 2; k += blockDim.x) {
+    float s = 0.0f;
+    for (int i = 0; i < nw; ++i) s += red[i][k];
+    if (k < 4 * G) {
+      if (k < p.K && p.dw) atomicAdd(p.dw + k, s);
+    } else if (k == 4 * G) {
+      if (p.db) atomicAdd(p.db, s);
+    } else if (p.loss) {
+      atomicAdd(p.loss, s);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // wgrad:  dW[K, N] += sum_m X[m, :]^T dZ[m, :],  db[N] += sum_m dZ[m, :]
 // MMA view: M' = K (rows of dW), N' = N, K' = batch rows.  A CTA owns a (KS x NS) tile of dW and a contiguous slice of
@@ -366,7 +453,7 @@ constexpr int DG_SLAB = 128;  // output columns (rows of W) per CTA
 constexpr int DG_WARPS = 8;
 
 template <int KSTEPS>
-__global__ void __launch_bounds__(32 * DG_WARPS) dgrad_kernel(const DgradParams p) {
+__global__ void __launch_bounds__(32 * DG_WARPS, 2) dgrad_kernel(const DgradParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int NP = 16 * KSTEPS;        // padded N
   constexpr int SW = NP * 4 + 16;        // bytes per staged W row: [hi 0..NP | lo 0..NP] + pad
@@ -547,7 +634,19 @@ int mm_bce_head_fwd_bwd(const float* x, int64_t M, int K, int64_t x_stride, cons
   long long blocks = (M + 7) / 8;
   const long long cap = 4LL * mm::sm_count();
   if (blocks > cap) blocks = cap;
-  head_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (K & 3) == 0 && K <= 128 && (x_stride & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 &&
+                   (!dx || ((dx_stride & 3) == 0 && ((uintptr_t)dx & 15) == 0));
+  if (vec) {
+    const int g = K / 4;
+    if (g <= 2) head_kernel_v4<2><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else if (g <= 4) head_kernel_v4<4><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else if (g <= 8) head_kernel_v4<8><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else if (g <= 16) head_kernel_v4<16><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else head_kernel_v4<32><<<(unsigned)blocks, 256, 0, st>>>(p);
+  } else {
+    head_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+  }
   return mm::check_launch("mm_bce_head_fwd_bwd");
 }
 
@@ -575,7 +674,7 @@ int mm_dense_wgrad(const float* x, int64_t M, int K, int64_t x_stride, const flo
   const int ns = N > 64 ? 128 : N > 32 ? 64 : 32;
 #define MM_WG(KS_, NS_, WM, MT, WN, NT) \
   if (ks == KS_ && ns == NS_) return launch_wgrad<WM, MT, WN, NT>(p, st);
-  MM_WG(128, 128, 4, 2, 2, 8) MM_WG(128, 64, 4, 2, 2, 4) MM_WG(128, 32, 4, 2, 2, 2)
+  MM_WG(128, 128, 4, 2, 4, 4) MM_WG(128, 64, 4, 2, 2, 4) MM_WG(128, 32, 4, 2, 2, 2)
   MM_WG(64, 128, 2, 2, 4, 4) MM_WG(64, 64, 2, 2, 4, 2) MM_WG(64, 32, 4, 1, 2, 2)
   MM_WG(16, 128, 1, 1, 8, 2) MM_WG(16, 64, 1, 1, 8, 1) MM_WG(16, 32, 1, 1, 4, 1)
 #undef MM_WG

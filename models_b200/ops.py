@@ -856,7 +856,8 @@ def dlrm_interact_backward(weights, indices, slots, rows, D: int, bottom: Option
 
 def sparse_rows_apply(opt: str, tables, B: int, D: int, hyper: torch.Tensor) -> None:
     """Optimizer step on IndexedSlices (mm_sparse_rows_apply).  tables: dicts with weights, indices, grad_rows, rep_map and, per
-    optimizer, state1 / state2, optionally mirror."""
+    optimizer, state1 / state2, optionally mirror and dense_grad (a zeroed (rows, D) accumulator: selects the dense path for
+    tables with few rows, see include/mm_b200.h)."""
     _dev(hyper, "hyper", torch.float32)
     n = len(tables)
     arr = (_cabi.SparseTable * n)()
@@ -880,6 +881,10 @@ def sparse_rows_apply(opt: str, tables, B: int, D: int, hyper: torch.Tensor) -> 
         if m is not None and (_dev(m, f"tables[{t}].mirror", torch.bfloat16).shape != (w.shape[0], 2 * D) or not m.is_contiguous()):
             raise ValueError(f"tables[{t}].mirror must be contiguous bf16 (rows, {2 * D})")
         arr[t].mirror = _ptr(m)
+        dg = tb.get("dense_grad")
+        if dg is not None and (_dev(dg, f"tables[{t}].dense_grad", torch.float32).shape != w.shape or not dg.is_contiguous()):
+            raise ValueError(f"tables[{t}].dense_grad must match the weights")
+        arr[t].dense_grad = _ptr(dg)
     _cabi.check(_lib().mm_sparse_rows_apply(arr, n, B, D, _cabi.OPTIMIZERS[opt], hyper.data_ptr(), _stream()), "mm_sparse_rows_apply")
 
 

@@ -30,6 +30,7 @@ from .blocks import DLRM, MLP, _Dense
 from .core import default_device, get_feature
 
 INT32_MAX = 2**31 - 1
+DENSE_PATH_MAX_ROWS = 131072  # tables up to this size accumulate duplicate ids in a dense (rows, D) gradient
 
 
 class Optimizer:
@@ -233,6 +234,8 @@ class DLRMTrainer:
         self.rep = [ops.fill_i32(torch.empty(t.table.shape[0], dtype=torch.int32, device=self.device), INT32_MAX) for t in self.tables]
         self.tstate1 = [torch.full_like(t.table, optimizer.initial_accumulator_value) if optimizer.slots >= 1 else None for t in self.tables]
         self.tstate2 = [torch.zeros_like(t.table) if optimizer.slots >= 2 else None for t in self.tables]
+        # tables with few rows (every id repeats many times per batch) sum their slices into a dense accumulator
+        self.tdense = [torch.zeros_like(t.table) if t.table.shape[0] <= DENSE_PATH_MAX_ROWS else None for t in self.tables]
 
         # ---- activations and gradients
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -359,7 +362,7 @@ class DLRMTrainer:
         for t, tb in enumerate(self.tables):
             mirror = tb._mirror if (tb._mirror is not None and tb._mirror.shape[0] == tb.table.shape[0]) else None
             tabs.append(dict(weights=tb.table, indices=idx[t], grad_rows=slices[t], rep_map=self.rep[t], state1=self.tstate1[t],
-                             state2=self.tstate2[t], mirror=mirror))
+                             state2=self.tstate2[t], mirror=mirror, dense_grad=self.tdense[t]))
         ops.sparse_rows_apply(self.opt.kind, tabs, Bt, self.D, self.hyper)
         for l, ws in zip(self.bottom + self.top, self._wsplit):
             ops.split_weights(l.kernel, out=ws)
@@ -379,13 +382,14 @@ class DLRMTrainer:
         bump_weights_version()  # forward graphs captured earlier hold scalars / operand copies of the old variables
 
     # ---- CUDA-graph replay over static input buffers ------------------------------------------------------------
-    def capture(self, inputs: Dict[str, torch.Tensor], targets: torch.Tensor) -> None:
+    def capture(self, inputs: Dict[str, torch.Tensor], targets: torch.Tensor, clone: bool = True) -> None:
         """Capture forward + backward + update into ONE CUDA graph over copies of `inputs` / `targets` (single GPU; with a
-        process group the collectives stay eager between two graphs)."""
+        process group the collectives stay eager between two graphs).  clone=False: the given tensors ARE the static
+        buffers (e.g. views of one packed device buffer that a single H2D copy refreshes before replay())."""
         if self.world > 1:
             raise NotImplementedError("graph capture of the data-parallel step is not implemented")
-        self._static = {k: v.clone() for k, v in inputs.items()}
-        self._static_y = targets.clone()
+        self._static = {k: (v.clone() if clone else v) for k, v in inputs.items()}
+        self._static_y = targets.clone() if clone else targets
         self.model.defer_index_check(True)
         try:
             s = torch.cuda.Stream(device=self.device)
