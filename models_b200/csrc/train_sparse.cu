@@ -311,6 +311,7 @@ struct SparseParams {
   SparseTable t[MM_LOOKUP_MAX_ROWS];
   long long B;
   int D;
+  int lgL;  // log2(D / 4): lanes per row (a 64-bit division by a runtime value costs ~100 instructions and the XU pipe)
   int opt;
   const float* hyper;  // device: see mm_b200.h MM_HYPER_*
   int n;                                       // tables in t[]
@@ -333,8 +334,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
 __global__ void sparse_fold_kernel(const __grid_constant__ SparseParams p) {
   const SparseTable& tb = p.t[blockIdx.y];
   const int L = p.D >> 2;
-  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int c = threadIdx.x % L;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> p.lgL;
+  const int c = threadIdx.x & (L - 1);
   if (b >= p.B) return;
   const unsigned long long id = (unsigned long long)load_id(tb.ids, tb.idx_bytes, b);
   if (id >= (unsigned long long)tb.rows) return;
@@ -344,42 +345,55 @@ __global__ void sparse_fold_kernel(const __grid_constant__ SparseParams p) {
   red_add_v4(tb.grad + (long long)r * p.D + 4 * c, v);
 }
 
-__device__ __forceinline__ float upd(int opt, float w, float g, float& s1, float& s2, const float* hy) {
-  const float lr = hy[MM_HYPER_LR];
-  if (opt == MM_OPT_SGD) return w - lr * g;
+struct Hyper {
+  float lr, b1, b2, eps, lr_t;
+};
+__device__ __forceinline__ Hyper load_hyper(const float* hy) {
+  Hyper h;
+  h.lr = __ldg(hy + MM_HYPER_LR);
+  h.b1 = __ldg(hy + MM_HYPER_BETA1);
+  h.b2 = __ldg(hy + MM_HYPER_BETA2);
+  h.eps = __ldg(hy + MM_HYPER_EPS);
+  h.lr_t = __ldg(hy + MM_HYPER_LR_T);
+  return h;
+}
+__device__ __forceinline__ float upd(int opt, float w, float g, float& s1, float& s2, const Hyper& h) {
+  if (opt == MM_OPT_SGD) return w - h.lr * g;
   if (opt == MM_OPT_ADAGRAD) {
     s1 += g * g;
-    return w - lr * g / (sqrtf(s1) + hy[MM_HYPER_EPS]);
+    return w - h.lr * g / (sqrtf(s1) + h.eps);
   }
   // Adam (Keras: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), computed by mm_opt_tick)
-  const float b1 = hy[MM_HYPER_BETA1], b2 = hy[MM_HYPER_BETA2];
-  s1 = b1 * s1 + (1.0f - b1) * g;
-  s2 = b2 * s2 + (1.0f - b2) * g * g;
-  return w - hy[MM_HYPER_LR_T] * s1 / (sqrtf(s2) + hy[MM_HYPER_EPS]);
+  s1 = h.b1 * s1 + (1.0f - h.b1) * g;
+  s2 = h.b2 * s2 + (1.0f - h.b2) * g * g;
+  return w - h.lr_t * s1 / (sqrtf(s2) + h.eps);
 }
 
 __global__ void sparse_apply_kernel(const __grid_constant__ SparseParams p) {
   const SparseTable& tb = p.t[blockIdx.y];
   const int L = p.D >> 2;
-  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int c = threadIdx.x % L;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> p.lgL;
+  const int c = threadIdx.x & (L - 1);
   if (b >= p.B) return;
   const unsigned long long id = (unsigned long long)load_id(tb.ids, tb.idx_bytes, b);
   if (id >= (unsigned long long)tb.rows) return;
-  // every lane of the group reads the map BEFORE lane 0 resets it (the group sits inside one warp: D/4 <= 32)
-  const int r = tb.rep[id];
-  __syncwarp();
-  if (r != (int)b) return;
+  // The row and its slots are requested TOGETHER with the map entry (one dependent round trip less: id -> {map, row});
+  // for tables on this path nearly every sample is its id's representative, so almost nothing is fetched in vain.
+  // Every lane of the group reads the map BEFORE lane 0 resets it (the group sits inside one warp: D/4 <= 32).
   const long long off = (long long)id * p.D + 4 * c;
+  const int r = tb.rep[id];
   const float4 g = *reinterpret_cast<const float4*>(tb.grad + b * p.D + 4 * c);
   float4 w = *reinterpret_cast<float4*>(tb.w + off);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), v = a;
   if (p.opt != MM_OPT_SGD) a = *reinterpret_cast<float4*>(tb.s1 + off);
   if (p.opt == MM_OPT_ADAM) v = *reinterpret_cast<float4*>(tb.s2 + off);
-  w.x = upd(p.opt, w.x, g.x, a.x, v.x, p.hyper);
-  w.y = upd(p.opt, w.y, g.y, a.y, v.y, p.hyper);
-  w.z = upd(p.opt, w.z, g.z, a.z, v.z, p.hyper);
-  w.w = upd(p.opt, w.w, g.w, a.w, v.w, p.hyper);
+  __syncwarp();
+  if (r != (int)b) return;
+  const Hyper hy = load_hyper(p.hyper);
+  w.x = upd(p.opt, w.x, g.x, a.x, v.x, hy);
+  w.y = upd(p.opt, w.y, g.y, a.y, v.y, hy);
+  w.z = upd(p.opt, w.z, g.z, a.z, v.z, hy);
+  w.w = upd(p.opt, w.w, g.w, a.w, v.w, hy);
   *reinterpret_cast<float4*>(tb.w + off) = w;
   if (p.opt != MM_OPT_SGD) *reinterpret_cast<float4*>(tb.s1 + off) = a;
   if (p.opt == MM_OPT_ADAM) *reinterpret_cast<float4*>(tb.s2 + off) = v;
@@ -403,7 +417,7 @@ __global__ void sparse_apply_kernel(const __grid_constant__ SparseParams p) {
 // Criteo tables.  Instead the CTA counting-sorts its chunk of samples by row with INTEGER shared atomics (native), then
 // every group of D/4 lanes walks a contiguous piece of the sorted order, sums runs of equal rows in registers and
 // emits ONE vector red per run: rows + groups reds per CTA instead of one shared atomic per element.
-constexpr int SMALL_CHUNK = 2048;     // samples per CTA
+constexpr int SMALL_CHUNK = 1024;     // samples per CTA
 constexpr int SMALL_MAX_ROWS = 1024;  // rows of a "small" table (counter array in shared memory)
 __global__ void __launch_bounds__(256) sparse_scatter_small_kernel(const __grid_constant__ SparseParams p) {
   __shared__ int cnt[SMALL_MAX_ROWS + 1];
@@ -467,26 +481,37 @@ __global__ void __launch_bounds__(256) sparse_scatter_small_kernel(const __grid_
   __syncthreads();
   const int valid = cnt[rows];
   const int L = p.D >> 2;
-  const int c = threadIdx.x % L, grp = threadIdx.x / L, ngrp = blockDim.x / L;
+  const int c = threadIdx.x & (L - 1), grp = threadIdx.x >> p.lgL, ngrp = blockDim.x >> p.lgL;
   const int per = (valid + ngrp - 1) / ngrp;
   const int k0 = grp * per, k1 = min(valid, k0 + per);
   int cur = -1;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = k0; k < k1; ++k) {
-    const int r = orow[k];
-    const float4 v = *reinterpret_cast<const float4*>(tb.grad + (b0 + order[k]) * p.D + 4 * c);
-    if (r != cur) {
-      if (cur >= 0) {
-        red_add_v4(tb.dense + (long long)cur * p.D + 4 * c, acc);
-        if (c == 0) tb.rep[cur] = 0;  // touched
+  constexpr int U = 8;  // slices in flight per group (their addresses come from the sorted order: no prefetcher helps)
+  for (int k = k0; k < k1; k += U) {
+    int r[U];
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool on = k + u < k1;
+      r[u] = on ? (int)orow[k + u] : -1;
+      v[u] = on ? *reinterpret_cast<const float4*>(tb.grad + (b0 + order[k + u]) * p.D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r[u] < 0) continue;
+      if (r[u] != cur) {
+        if (cur >= 0) {
+          red_add_v4(tb.dense + (long long)cur * p.D + 4 * c, acc);
+          if (c == 0) tb.rep[cur] = 0;  // touched
+        }
+        cur = r[u];
+        acc = v[u];
+      } else {
+        acc.x += v[u].x;
+        acc.y += v[u].y;
+        acc.z += v[u].z;
+        acc.w += v[u].w;
       }
-      cur = r;
-      acc = v;
-    } else {
-      acc.x += v.x;
-      acc.y += v.y;
-      acc.z += v.z;
-      acc.w += v.w;
     }
   }
   if (cur >= 0) {
@@ -498,8 +523,8 @@ __global__ void __launch_bounds__(256) sparse_scatter_small_kernel(const __grid_
 __global__ void sparse_scatter_mid_kernel(const __grid_constant__ SparseParams p) {
   const SparseTable& tb = p.t[blockIdx.y];
   const int L = p.D >> 2;
-  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int c = threadIdx.x % L;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> p.lgL;
+  const int c = threadIdx.x & (L - 1);
   if (b >= p.B) return;
   const unsigned long long id = (unsigned long long)load_id(tb.ids, tb.idx_bytes, b);
   if (id >= (unsigned long long)tb.rows) return;
@@ -512,27 +537,29 @@ __global__ void sparse_scatter_mid_kernel(const __grid_constant__ SparseParams p
 // holds the prefix sums): touched rows are updated from the accumulator, which is cleared
 __global__ void sparse_apply_dense_kernel(const __grid_constant__ SparseParams p) {
   const int L = p.D >> 2;
-  const long long fr = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int c = threadIdx.x % L;
+  const long long fr = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> p.lgL;
+  const int c = threadIdx.x & (L - 1);
   if (fr >= p.row_start[p.n]) return;
   int t = 0;
   while (fr >= p.row_start[t + 1]) ++t;
   const SparseTable& tb = p.t[t];
   const long long row = fr - p.row_start[t];
-  const int flag = tb.rep[row];
-  __syncwarp();
-  if (flag != 0) return;
+  // flag, accumulator, row and slots are requested together (tables on this path have nearly all rows touched)
   const long long off = row * p.D + 4 * c;
+  const int flag = tb.rep[row];
   const float4 g = *reinterpret_cast<const float4*>(tb.dense + off);
-  *reinterpret_cast<float4*>(tb.dense + off) = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 w = *reinterpret_cast<float4*>(tb.w + off);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), v = a;
   if (p.opt != MM_OPT_SGD) a = *reinterpret_cast<float4*>(tb.s1 + off);
   if (p.opt == MM_OPT_ADAM) v = *reinterpret_cast<float4*>(tb.s2 + off);
-  w.x = upd(p.opt, w.x, g.x, a.x, v.x, p.hyper);
-  w.y = upd(p.opt, w.y, g.y, a.y, v.y, p.hyper);
-  w.z = upd(p.opt, w.z, g.z, a.z, v.z, p.hyper);
-  w.w = upd(p.opt, w.w, g.w, a.w, v.w, p.hyper);
+  __syncwarp();
+  if (flag != 0) return;
+  *reinterpret_cast<float4*>(tb.dense + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const Hyper hy = load_hyper(p.hyper);
+  w.x = upd(p.opt, w.x, g.x, a.x, v.x, hy);
+  w.y = upd(p.opt, w.y, g.y, a.y, v.y, hy);
+  w.z = upd(p.opt, w.z, g.z, a.z, v.z, hy);
+  w.w = upd(p.opt, w.w, g.w, a.w, v.w, hy);
   *reinterpret_cast<float4*>(tb.w + off) = w;
   if (p.opt != MM_OPT_SGD) *reinterpret_cast<float4*>(tb.s1 + off) = a;
   if (p.opt == MM_OPT_ADAM) *reinterpret_cast<float4*>(tb.s2 + off) = v;
@@ -551,9 +578,10 @@ __global__ void dense_apply_kernel(int opt, float* __restrict__ w, float* __rest
                                    float* __restrict__ s2, long long n, const float* __restrict__ hyper, float grad_scale) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const Hyper hy = load_hyper(hyper);
   for (; i < n; i += stride) {
     float a = opt != MM_OPT_SGD ? s1[i] : 0.0f, v = opt == MM_OPT_ADAM ? s2[i] : 0.0f;
-    w[i] = upd(opt, w[i], g[i] * grad_scale, a, v, hyper);
+    w[i] = upd(opt, w[i], g[i] * grad_scale, a, v, hy);
     if (opt != MM_OPT_SGD) s1[i] = a;
     if (opt == MM_OPT_ADAM) s2[i] = v;
     g[i] = 0.0f;
@@ -694,6 +722,8 @@ int mm_sparse_rows_apply(const mm_sparse_table* tables_host, int n_tables, int64
   for (SparseParams* q : {&pb, &ps, &pm, &pd}) {
     q->B = B;
     q->D = D;
+    q->lgL = 0;
+    while ((1 << q->lgL) < D / 4) ++q->lgL;
     q->opt = opt;
     q->hyper = hyper;
   }

@@ -163,8 +163,8 @@ def gather_slices(ids: torch.Tensor, slices: torch.Tensor, group) -> tuple:
     T, B = ids.shape
     all_ids = torch.empty((world, T, B), dtype=ids.dtype, device=ids.device)
     all_sl = torch.empty((world,) + tuple(slices.shape), dtype=slices.dtype, device=slices.device)
-    dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
-    dist.all_gather_into_tensor(all_sl, slices.contiguous(), group=group)
+    dist.all_gather([all_ids[r] for r in range(world)], ids.contiguous(), group=group)
+    dist.all_gather([all_sl[r] for r in range(world)], slices.contiguous(), group=group)
     return (all_ids.permute(1, 0, 2).reshape(T, world * B).contiguous(),
             all_sl.permute(1, 0, 2, 3).reshape(T, world * B, slices.shape[2]).contiguous())
 

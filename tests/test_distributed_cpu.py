@@ -126,3 +126,36 @@ def test_loader_shards_partition_the_dataset_across_ranks():
     result = mgr.dict()
     mp.spawn(_loader_worker, args=(world, port, result), nprocs=world, join=True)
     assert dict(result) == {0: True, 1: True}
+
+
+def _gather_worker(rank, world, port, result):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from models_b200.train import gather_slices
+
+        T, B, D = 3, 5, 4
+        ids = (torch.arange(T * B, dtype=torch.int32).reshape(T, B) + 100 * rank)
+        sl = torch.arange(T * B * D, dtype=torch.float32).reshape(T, B, D) + 1000.0 * rank
+        all_ids, all_sl = gather_slices(ids, sl, dist.group.WORLD)
+        ok = tuple(all_ids.shape) == (T, world * B) and tuple(all_sl.shape) == (T, world * B, D)
+        for r in range(world):  # table-major, then rank, then the rank's samples in order: one IndexedSlices per table
+            ok &= bool(torch.equal(all_ids[:, r * B:(r + 1) * B], torch.arange(T * B, dtype=torch.int32).reshape(T, B) + 100 * r))
+            ok &= bool(torch.equal(all_sl[:, r * B:(r + 1) * B], torch.arange(T * B * D, dtype=torch.float32).reshape(T, B, D) + 1000.0 * r))
+        # the dense arena is averaged with one all-reduce
+        g = torch.full((7,), float(rank + 1))
+        dist.all_reduce(g)
+        ok &= bool(torch.equal(g / world, torch.full((7,), (world + 1) / 2)))
+        result[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_gradient_exchange_world2_gloo():
+    """Host side of the data-parallel training step (models_b200/train.py): layout of the all-gathered IndexedSlices."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_gather_worker, args=(world, port, result), nprocs=world, join=True)
+    assert all(result[r] for r in range(world)), dict(result)

@@ -27,6 +27,12 @@ def test_sharded_dlrm_matches_unsharded():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_data_parallel_training_matches_single_gpu_twin():
+    r = _torchrun(2, ["tests/dist_train_check.py"])
+    assert r.returncode == 0 and "TRAIN_DP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_bench_replicas_two_gpus():
     r = _torchrun(2, ["bench.py", "--gpus", "2", "--steps", "5", "--warmup", "3", "--batch", "8192"], timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
