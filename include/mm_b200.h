@@ -415,6 +415,8 @@ int mm_init_uniform_hash_rows(float* w, int64_t local_rows, int D, uint64_t seed
  *                             batch's ids; duplicates NOT yet summed), and d_bottom (B, D) = gradient of the bottom
  *                             vector (interaction rows + the shortcut dA[:, :P]; zeroed where bottom <= 0 when
  *                             mask_bottom).  The table rows are looked up again (tables_host as in the forward call).
+ *                             row_format MM_ROWS_OPERAND (D = 64): `weights` and `bottom` are the split-bf16 rows of
+ *                             mm_dlrm_lookup_interact's operand format (mirrors kept in step by mm_sparse_rows_apply).
  *   mm_sparse_rows_apply      optimizer step on IndexedSlices with duplicate ids as Keras applies it: duplicates are
  *                             summed, then ONE update per unique row (OptimizerV2._resource_apply_sparse_duplicate_
  *                             indices; Adam on touched rows only = LazyAdam, blocks/optimizer.py:342).  rep_map:
@@ -462,12 +464,16 @@ int mm_bce_head_fwd_bwd(const float* x, int64_t M, int K, int64_t x_stride, cons
                         float* loss_sum, float* dx, int64_t dx_stride, int mask_relu, float* dw, float* db, void* stream);
 int mm_dense_wgrad(const float* x, int64_t M, int K, int64_t x_stride, const float* dz, int N, int64_t dz_stride,
                    float* dw, float* db, void* stream);
+/* mm_dense_wgrad with X given as split-bf16 rows (M, 2*Kp) = [hi | lo] (mm_split_rows layout, Kp = mm_tc_padded_k(K)): the
+ * operand the forward layer consumed — e.g. the interaction kernel's split output — so no fp32 copy of X has to exist. */
+int mm_dense_wgrad_split(const void* x_split, int64_t M, int K, int Kp, const float* dz, int N, int64_t dz_stride,
+                         float* dw, float* db, void* stream);
 int mm_dense_dgrad(const float* dz, int64_t M, int N, int64_t dz_stride, const float* w, int K, const float* mask,
                    int64_t mask_stride, float* dx, int64_t dx_stride, void* stream);
 int mm_dlrm_interact_backward(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, const float* bottom,
                               int64_t bottom_stride, int bottom_slot, int P, const float* dA, int64_t dA_stride,
                               float* const* grad_rows_host, int64_t grad_stride, float* d_bottom,
-                              int64_t d_bottom_stride, int mask_bottom, void* stream);
+                              int64_t d_bottom_stride, int mask_bottom, int row_format, void* stream);
 int mm_sparse_rows_apply(const mm_sparse_table* tables_host, int n_tables, int64_t B, int D, int opt,
                          const float* hyper, void* stream);
 int mm_dense_apply(int opt, float* w, float* grad, float* state1, float* state2, int64_t n, const float* hyper,

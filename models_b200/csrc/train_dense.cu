@@ -252,6 +252,8 @@ struct WgradParams {
   float* db;  // (N,) accumulated or null
   long long rows_per_cta;  // multiple of 32
   int x_vec, z_vec;        // 16-byte loads are legal
+  const __nv_bfloat16* x_split;  // XSPLIT: X as split-bf16 rows (M, 2*Kp) = [hi | lo] (mm_split_rows layout) instead of fp32
+  int Kp;
 };
 
 __device__ __forceinline__ float4 load4(const float* row, int c, int C, bool vec) {
@@ -264,7 +266,7 @@ __device__ __forceinline__ float4 load4(const float* row, int c, int C, bool vec
   return v;
 }
 
-template <int WM, int MT, int WN, int NT>
+template <int WM, int MT, int WN, int NT, bool XSPLIT>
 __global__ void __launch_bounds__(32 * WM * WN) wgrad_kernel(const WgradParams p) {
   constexpr int T = 32 * WM * WN;
   constexpr int KS = WM * MT * 16, NS = WN * NT * 8;
@@ -299,7 +301,18 @@ __global__ void __launch_bounds__(32 * WM * WN) wgrad_kernel(const WgradParams p
       const int e = tid + i * T;
       const int r = e / XQ, c = (e % XQ) * 4;
       const long long m = mb + r;
-      xr[i] = (e < 32 * XQ && m < m_end) ? load4(p.x + m * p.ldx, k0 + c, p.K, p.x_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (XSPLIT) {
+        // four bf16 hi values and four lo values, already split: bit patterns travel through the float4
+        uint2 h = make_uint2(0u, 0u), l = h;
+        if (e < 32 * XQ && m < m_end && k0 + c < p.Kp) {
+          const __nv_bfloat16* row = p.x_split + m * (2ll * p.Kp) + k0 + c;
+          h = __ldg(reinterpret_cast<const uint2*>(row));
+          l = __ldg(reinterpret_cast<const uint2*>(row + p.Kp));
+        }
+        xr[i] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
+      } else {
+        xr[i] = (e < 32 * XQ && m < m_end) ? load4(p.x + m * p.ldx, k0 + c, p.K, p.x_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int i = 0; i < ZV; ++i) {
@@ -316,8 +329,15 @@ __global__ void __launch_bounds__(32 * WM * WN) wgrad_kernel(const WgradParams p
       if (e < 32 * XQ) {
         const int r = e / XQ, c = (e % XQ) * 4;
         uint32_t h0, l0, h1, l1;
-        split_pair(xr[i].x, xr[i].y, h0, l0);
-        split_pair(xr[i].z, xr[i].w, h1, l1);
+        if (XSPLIT) {
+          h0 = __float_as_uint(xr[i].x);
+          h1 = __float_as_uint(xr[i].y);
+          l0 = __float_as_uint(xr[i].z);
+          l1 = __float_as_uint(xr[i].w);
+        } else {
+          split_pair(xr[i].x, xr[i].y, h0, l0);
+          split_pair(xr[i].z, xr[i].w, h1, l1);
+        }
         *reinterpret_cast<uint2*>(xh + r * SX + c * 2) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(xl + r * SX + c * 2) = make_uint2(l0, l1);
       }
@@ -426,7 +446,8 @@ static int launch_wgrad(WgradParams p, cudaStream_t st) {
   if (rows < 256) rows = 256;
   p.rows_per_cta = rows;
   const long long gx = (p.M + rows - 1) / rows;
-  wgrad_kernel<WM, MT, WN, NT><<<dim3((unsigned)gx, (unsigned)ky, (unsigned)nz), 32 * WM * WN, 0, st>>>(p);
+  if (p.x_split) wgrad_kernel<WM, MT, WN, NT, true><<<dim3((unsigned)gx, (unsigned)ky, (unsigned)nz), 32 * WM * WN, 0, st>>>(p);
+  else wgrad_kernel<WM, MT, WN, NT, false><<<dim3((unsigned)gx, (unsigned)ky, (unsigned)nz), 32 * WM * WN, 0, st>>>(p);
   return check_launch("mm_dense_wgrad");
 }
 
@@ -650,6 +671,21 @@ int mm_bce_head_fwd_bwd(const float* x, int64_t M, int K, int64_t x_stride, cons
   return mm::check_launch("mm_bce_head_fwd_bwd");
 }
 
+static int wgrad_dispatch(mm::trn::WgradParams p, void* stream) {
+  using namespace mm::trn;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = p.K, N = p.N;
+  const int ks = K > 64 ? 128 : K > 16 ? 64 : 16;
+  const int ns = N > 64 ? 128 : N > 32 ? 64 : 32;
+#define MM_WG(KS_, NS_, WM, MT, WN, NT) \
+  if (ks == KS_ && ns == NS_) return launch_wgrad<WM, MT, WN, NT>(p, st);
+  MM_WG(128, 128, 4, 2, 4, 4) MM_WG(128, 64, 4, 2, 2, 4) MM_WG(128, 32, 4, 2, 2, 2)
+  MM_WG(64, 128, 2, 2, 4, 4) MM_WG(64, 64, 2, 2, 4, 2) MM_WG(64, 32, 4, 1, 2, 2)
+  MM_WG(16, 128, 1, 1, 8, 2) MM_WG(16, 64, 1, 1, 8, 1) MM_WG(16, 32, 1, 1, 4, 1)
+#undef MM_WG
+  return MM_ERR_UNSUPPORTED;
+}
+
 int mm_dense_wgrad(const float* x, int64_t M, int K, int64_t x_stride, const float* dz, int N, int64_t dz_stride, float* dw,
                    float* db, void* stream) {
   using namespace mm::trn;
@@ -669,16 +705,29 @@ int mm_dense_wgrad(const float* x, int64_t M, int K, int64_t x_stride, const flo
   p.db = db;
   p.x_vec = ((x_stride & 3) == 0 && ((uintptr_t)x & 15) == 0) ? 1 : 0;
   p.z_vec = ((dz_stride & 3) == 0 && ((uintptr_t)dz & 15) == 0) ? 1 : 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int ks = K > 64 ? 128 : K > 16 ? 64 : 16;
-  const int ns = N > 64 ? 128 : N > 32 ? 64 : 32;
-#define MM_WG(KS_, NS_, WM, MT, WN, NT) \
-  if (ks == KS_ && ns == NS_) return launch_wgrad<WM, MT, WN, NT>(p, st);
-  MM_WG(128, 128, 4, 2, 4, 4) MM_WG(128, 64, 4, 2, 2, 4) MM_WG(128, 32, 4, 2, 2, 2)
-  MM_WG(64, 128, 2, 2, 4, 4) MM_WG(64, 64, 2, 2, 4, 2) MM_WG(64, 32, 4, 1, 2, 2)
-  MM_WG(16, 128, 1, 1, 8, 2) MM_WG(16, 64, 1, 1, 8, 1) MM_WG(16, 32, 1, 1, 4, 1)
-#undef MM_WG
-  return MM_ERR_UNSUPPORTED;
+  return wgrad_dispatch(p, stream);
+}
+
+int mm_dense_wgrad_split(const void* x_split, int64_t M, int K, int Kp, const float* dz, int N, int64_t dz_stride, float* dw,
+                         float* db, void* stream) {
+  using namespace mm::trn;
+  MM_REQUIRE(x_split && dz && dw && M >= 0 && K >= 1 && N >= 1 && dz_stride >= N, MM_ERR_ARG, "mm_dense_wgrad_split: null pointer or bad shape");
+  MM_REQUIRE(Kp == mm_tc_padded_k(K) && ((uintptr_t)x_split & 15) == 0, MM_ERR_ARG,
+             "mm_dense_wgrad_split: Kp must be mm_tc_padded_k(K)=%d and x_split 16-byte aligned", mm_tc_padded_k(K));
+  if (M == 0) return MM_OK;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.x_split = (const __nv_bfloat16*)x_split;
+  p.Kp = Kp;
+  p.dz = dz;
+  p.ldz = dz_stride;
+  p.M = M;
+  p.K = K;
+  p.N = N;
+  p.dw = dw;
+  p.db = db;
+  p.z_vec = ((dz_stride & 3) == 0 && ((uintptr_t)dz & 15) == 0) ? 1 : 0;
+  return wgrad_dispatch(p, stream);
 }
 
 int mm_dense_dgrad(const float* dz, int64_t M, int N, int64_t dz_stride, const float* w, int K, const float* mask,

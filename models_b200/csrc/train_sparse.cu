@@ -293,6 +293,256 @@ static int launch_ibwd(const LookupParams& lk, IbwdParams p, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Operand-format variant (D = 64): the tables' mirrors and the bottom vector are split-bf16 rows [hi(0..63) | lo(0..63)]
+// (mm_split_rows, the format the forward kernel reads with MM_ROWS_OPERAND and the optimizer kernels keep in step).
+// First version above: 1 124 warp instructions per sample at 8 warps per SM (254 registers) — 64 + 192 of them only to
+// load and split the X fragments, 128 to assemble the G fragments through a 32-register offset table.  Here
+//   * the rows land in shared memory with the forward kernel's 128-byte XOR swizzle and the B fragments (X, k = feature
+//     row, n = embedding column) come from ldmatrix.trans: 16 instructions, no conversion;
+//   * G is built once per sample as two (32 x 32) bf16 matrices (hi, lo) in shared memory — lane e handles pairs
+//     e, e+32, ...: one load of dA, one split, four 2-byte stores (both triangles) — and the A fragments come from ldmatrix;
+//   * a sample buffer holds only the F live rows (ldmatrix rows >= F point at a zero row of the CTA); ONE buffer per warp,
+//     16 warps per SM: the other warps hide a warp's copy latency.  (Tried and slower: double-buffered rows with the G
+//     fragments assembled in registers through a packed offset table, 12 warps at 168 registers: 241 us against 217 us —
+//     it is the dependent instruction chains of the compute phase, not the copy latency, that occupancy has to hide.)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+
+constexpr int PS_WARPS = 16;
+constexpr unsigned PS_G_STRIDE = 80;  // bytes per row of a G matrix (64 + 16: conflict-free ldmatrix)
+constexpr unsigned PS_G_BYTES = 2 * 32 * PS_G_STRIDE;
+
+__global__ void __launch_bounds__(32 * PS_WARPS, 1)
+interact_bwd_ps_kernel(const __grid_constant__ LookupParams lk, const __grid_constant__ IbwdParams p) {
+  extern __shared__ __align__(256) uint8_t smem[];
+  constexpr int D = 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int F = p.F;
+  const int npairs = F * (F - 1) / 2;
+  const int OW = p.P + npairs;
+  // CTA: [zero row 256 B | pair table] then per warp [F rows of 256 B | dA stage | G hi | G lo]
+  const uint32_t zrow = (uint32_t)__cvta_generic_to_shared(smem);
+  uint16_t* pair_ij = reinterpret_cast<uint16_t*>(smem + 256);
+  uint8_t* mine = smem + p.stage_off + (size_t)warp * p.buf_bytes;  // stage_off: bytes of the CTA-wide header
+  const uint32_t xs = (uint32_t)__cvta_generic_to_shared(mine);
+  const uint32_t st = xs + (uint32_t)F * 256u;
+  const uint32_t gs = st + p.stage_floats * 4u;
+  for (int e = threadIdx.x; e < 64; e += blockDim.x) reinterpret_cast<uint32_t*>(smem)[e] = 0u;
+  for (int e = lane; e < (int)(p.buf_bytes / 4); e += 32) reinterpret_cast<uint32_t*>(mine)[e] = 0u;  // G diagonal, padding
+  for (int e = threadIdx.x; e < npairs; e += blockDim.x) {  // pair e -> (i, j)
+    int i = 0, rem = e;
+    while (rem >= F - 1 - i) {
+      rem -= F - 1 - i;
+      ++i;
+    }
+    pair_ij[e] = (uint16_t)((i << 8) | (i + 1 + rem));
+  }
+  __syncthreads();
+
+  const bool is_table = lane < F && lane != p.bottom_slot && lk.weights[lane] != nullptr;
+  const float* my_base = is_table ? lk.weights[lane] : nullptr;  // mirror rows: 64 "floats" = 256 bytes each
+  const unsigned long long my_rows = is_table ? (unsigned long long)lk.rows[lane] : 0ull;
+  const int my_w = is_table ? lk.idx_bytes[lane] : 4;
+  const void* my_ids = is_table ? lk.indices[lane] : nullptr;
+  const int cl = lane & 15, rl = lane >> 4;
+  float* gptr[4];
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    const int i = 8 * qd + g;
+    gptr[qd] = (i < F && i != p.bottom_slot) ? p.grad[i] : nullptr;
+  }
+  // ldmatrix lane addresses
+  const int q = lane >> 3, r8 = lane & 7;
+  // A (G): matrices (i 0-7, j 0-7) (i 8-15, j 0-7) (i 0-7, j 8-15) (i 8-15, j 8-15) of m-tile mt, k-tile kt
+  const uint32_t a_lane = (uint32_t)(((q & 1) * 8 + r8) * PS_G_STRIDE + (q >> 1) * 16);
+  // B (X): matrices (j 0-7, nt 2u) (j 8-15, nt 2u) (j 0-7, nt 2u+1) (j 8-15, nt 2u+1); chunk nt of row j sits at
+  // nt ^ (j & 7); rows >= F read the CTA's zero row
+  const int b_nt = q >> 1;
+  uint32_t brow[2];
+#pragma unroll
+  for (int kt = 0; kt < 2; ++kt) {
+    const int j = 16 * kt + (q & 1) * 8 + r8;
+    brow[kt] = j < F ? xs + (uint32_t)j * 256u : zrow;
+  }
+  // accumulator row (0..3) of this lane that is the bottom row, or -1
+  const int bq = (p.bottom_slot >= 0 && (p.bottom_slot & 7) == g) ? (p.bottom_slot >> 3) : -1;
+
+  const long long stride_s = (long long)gridDim.x * p.n_warps;
+  const long long s_first = (long long)blockIdx.x * p.n_warps + warp;
+  // Branch-free id fetch (lanes carry ids of different widths: a switch would serialise one global load per width): the
+  // aligned 32-bit word(s) holding the id, one sample ahead; decoded with a funnel shift like the forward kernel.
+  const uint32_t my_mask = my_w >= 4 ? 0xffffffffu : (0xffffffffu >> (32 - 8 * my_w));
+  const bool my_64 = my_w == 8;
+  const uint8_t* id_ptr = is_table ? reinterpret_cast<const uint8_t*>(my_ids) + (size_t)s_first * my_w : nullptr;
+  const long long id_step = stride_s * my_w;
+  uint32_t raw_a = 0, raw_b = 0, raw_sh = 0;
+  auto fetch_id = [&](long long s) {
+    raw_a = raw_b = raw_sh = 0;
+    if (is_table && s < p.B) {
+      const uintptr_t ad = reinterpret_cast<uintptr_t>(id_ptr);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+      raw_sh = 8u * (uint32_t)(ad & 3);
+      raw_a = __ldg(wp);
+      if (my_64 || (int)(ad & 3) + my_w > 4) raw_b = __ldg(wp + 1);
+    }
+    id_ptr += id_step;
+  };
+  fetch_id(s_first);
+  const bool bottom_lane = lane == p.bottom_slot && p.bottom != nullptr;
+  for (long long s = s_first; s < p.B; s += stride_s) {
+    // ---- rows + dA row -> shared memory
+    {
+      const uint32_t v = __funnelshift_r(raw_a, raw_b, raw_sh) & my_mask;
+      const uint32_t vhi = my_64 ? raw_b : (uint32_t)((int)v >> 31);
+      const unsigned long long idx = ((unsigned long long)vhi << 32) | v;
+      fetch_id(s + stride_s);  // the next sample's id is in flight while this one is computed
+      const float* my_src = (is_table && idx < my_rows) ? my_base + idx * D : bottom_lane ? p.bottom + s * p.bottom_stride : g_zero_row;
+      const uint32_t lo = (uint32_t)(uintptr_t)my_src, hi = (uint32_t)((uintptr_t)my_src >> 32);
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 2) {  // no branch: rows >= F are shuffled for nothing and their copy is predicated off
+        const int row = r0 + rl;
+        const uint32_t slo = __shfl_sync(0xffffffffu, lo, row);
+        const uint32_t shi = __shfl_sync(0xffffffffu, hi, row);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(((uintptr_t)shi << 32) | slo) + cl * 16;
+        cp_async16_if(row < F, xs + (uint32_t)(row * 256 + ((cl ^ (row & 7)) << 4)), src);
+      }
+      const float* da = p.dA + s * p.dA_stride;
+      if (p.dA_vec) {
+        for (int c = lane; c * 4 < OW; c += 32) cp_async16_if(true, st + (uint32_t)c * 16u, da + c * 4);
+      } else {
+        for (int c = lane; c < OW; c += 32) cp_async4_if(true, st + (uint32_t)c * 4u, da + c);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+    }
+    // ---- G (hi, lo) from the pair gradients
+#pragma unroll 4
+    for (int e = lane; e < npairs; e += 32) {
+      const float v = lds32(st + (uint32_t)(p.P + e) * 4u);
+      const uint32_t ij = pair_ij[e];
+      const uint32_t i = ij >> 8, j = ij & 255u;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      const uint32_t a1 = gs + i * PS_G_STRIDE + j * 2, a2 = gs + j * PS_G_STRIDE + i * 2;
+      const unsigned short hb = __bfloat16_as_ushort(h), lb = __bfloat16_as_ushort(l);
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(a1), "h"(hb) : "memory");
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2), "h"(hb) : "memory");
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(a1 + 32 * PS_G_STRIDE), "h"(lb) : "memory");
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2 + 32 * PS_G_STRIDE), "h"(lb) : "memory");
+    }
+    __syncwarp();
+    float acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.0f;
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t a = gs + a_lane + (uint32_t)(mt * 16 * PS_G_STRIDE + kt * 32);
+        ldsm_x4(a, ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3]);
+        ldsm_x4(a + 32 * PS_G_STRIDE, al[mt][0], al[mt][1], al[mt][2], al[mt][3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t bh[4], bl[4];
+        const uint32_t b = brow[kt] + (uint32_t)((((2 * u + b_nt) ^ r8) & 7) << 4);
+        ldsm_x4_t(b, bh[0], bh[1], bh[2], bh[3]);
+        ldsm_x4_t(b + 128u, bl[0], bl[1], bl[2], bl[3]);
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int nt = 2 * u + v;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma16816(acc[mt][nt], ah[mt], bl[2 * v], bl[2 * v + 1]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma16816(acc[mt][nt], al[mt], bh[2 * v], bh[2 * v + 1]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma16816(acc[mt][nt], ah[mt], bh[2 * v], bh[2 * v + 1]);
+        }
+      }
+    }
+    // ---- dX rows.  Table rows: predicated vector stores, no branches (gptr is null for the bottom row and rows >= F)
+    const long long goffs = s * p.grad_stride + 2 * t;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float* drow = gptr[2 * mt + h] + goffs;
+        const uint32_t on = gptr[2 * mt + h] != nullptr;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(drow + 8 * nt),
+                       "f"(acc[mt][nt][2 * h]), "f"(acc[mt][nt][2 * h + 1]), "r"(on)
+                       : "memory");
+      }
+    // the bottom row (one accumulator row of the lanes with g == bottom_slot % 8): + shortcut gradient, relu mask
+    if (bq >= 0 && p.d_bottom) {
+      float* drow = p.d_bottom + s * p.d_bottom_stride + 2 * t;
+      const int i = p.bottom_slot;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float a = bq == 0 ? acc[0][nt][0] : bq == 1 ? acc[0][nt][2] : bq == 2 ? acc[1][nt][0] : acc[1][nt][2];
+        float b = bq == 0 ? acc[0][nt][1] : bq == 1 ? acc[0][nt][3] : bq == 2 ? acc[1][nt][1] : acc[1][nt][3];
+        if (p.P > 0) {
+          a += lds32(st + (uint32_t)(8 * nt + 2 * t) * 4u);
+          b += lds32(st + (uint32_t)(8 * nt + 2 * t) * 4u + 4u);
+        }
+        if (p.mask_bottom) {
+          // bottom[d] > 0  <=>  its bf16 hi part > 0 (relu outputs are >= 0; hi = 0 only for denormal-sized values)
+          const uint32_t xa = xs + (uint32_t)(i * 256 + (((nt ^ (i & 7)) & 7) << 4) + 4 * t);
+          uint32_t hv;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hv) : "r"(xa));
+          a = __uint_as_float(hv << 16) > 0.0f ? a : 0.0f;
+          b = __uint_as_float(hv & 0xffff0000u) > 0.0f ? b : 0.0f;
+        }
+        *reinterpret_cast<float2*>(drow + 8 * nt) = make_float2(a, b);
+      }
+    }
+    __syncwarp();  // the buffer is refilled by the next iteration's copies
+  }
+}
+
+static int launch_ibwd_ps(const LookupParams& lk, IbwdParams p, cudaStream_t st) {
+  const int npairs = p.F * (p.F - 1) / 2;
+  const int OW = p.P + npairs;
+  p.stage_floats = (unsigned)(((OW + 3) & ~3) + 4);
+  p.stage_off = (256u + (unsigned)npairs * 2u + 255u) & ~255u;  // CTA-wide header: zero row + pair table
+  p.buf_bytes = ((unsigned)p.F * 256u + p.stage_floats * 4u + PS_G_BYTES + 15u) & ~15u;
+  int warps = (int)((227u * 1024u - p.stage_off) / p.buf_bytes);
+  if (warps > PS_WARPS) warps = PS_WARPS;
+  if (warps < 1) return MM_ERR_UNSUPPORTED;
+  p.n_warps = warps;
+  const size_t smem = (size_t)p.stage_off + (size_t)warps * p.buf_bytes;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(interact_bwd_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("mm_dlrm_interact_backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  long long want = (p.B + warps - 1) / warps;
+  const long long sms = sm_count();
+  const unsigned grid = (unsigned)(want < sms ? want : sms);
+  interact_bwd_ps_kernel<<<grid, 32 * warps, smem, st>>>(lk, p);
+  return check_launch("mm_dlrm_interact_backward");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Sparse rows: dedup + optimizer
 // ---------------------------------------------------------------------------------------------------------------
 struct SparseTable {
@@ -609,7 +859,7 @@ extern "C" {
 int mm_dlrm_interact_backward(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, const float* bottom,
                               int64_t bottom_stride, int bottom_slot, int P, const float* dA, int64_t dA_stride,
                               float* const* grad_rows_host, int64_t grad_stride, float* d_bottom, int64_t d_bottom_stride,
-                              int mask_bottom, void* stream) {
+                              int mask_bottom, int row_format, void* stream) {
   using namespace mm;
   using namespace mm::trs;
   MM_REQUIRE(tables_host && n_tables > 0 && dA && grad_rows_host && B >= 0, MM_ERR_ARG, "mm_dlrm_interact_backward: null pointer");
@@ -617,6 +867,8 @@ int mm_dlrm_interact_backward(const mm_lookup_table* tables_host, int n_tables, 
   MM_REQUIRE(F >= 2 && F <= MM_LOOKUP_MAX_ROWS, MM_ERR_UNSUPPORTED, "mm_dlrm_interact_backward: F=%d outside [2, 32]", F);
   MM_REQUIRE(D == 16 || D == 32 || D == 64 || D == 128, MM_ERR_UNSUPPORTED, "mm_dlrm_interact_backward: D=%d not in {16,32,64,128}", D);
   MM_REQUIRE(P == 0 || (P == D && bottom), MM_ERR_ARG, "mm_dlrm_interact_backward: P must be 0 or D (with a bottom vector)");
+  MM_REQUIRE(row_format == MM_ROWS_F32 || (row_format == MM_ROWS_OPERAND && D == 64), MM_ERR_UNSUPPORTED,
+             "mm_dlrm_interact_backward: operand-format rows need D = 64");
   MM_REQUIRE(!bottom || (bottom_slot >= 0 && bottom_slot < F && bottom_stride >= D && (bottom_stride & 3) == 0 && ((uintptr_t)bottom & 15) == 0),
              MM_ERR_ARG, "mm_dlrm_interact_backward: bad bottom slot / stride / alignment");
   const int OW = P + F * (F - 1) / 2;
@@ -663,6 +915,7 @@ int mm_dlrm_interact_backward(const mm_lookup_table* tables_host, int n_tables, 
   p.mask_bottom = mask_bottom;
   p.grad_stride = grad_stride;
   cudaStream_t st = (cudaStream_t)stream;
+  if (row_format == MM_ROWS_OPERAND) return launch_ibwd_ps(lk, p, st);
   switch (D) {
     case 16: return launch_ibwd<16>(lk, p, st);
     case 32: return launch_ibwd<32>(lk, p, st);

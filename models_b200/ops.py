@@ -793,6 +793,22 @@ def dense_wgrad(x: torch.Tensor, dz: torch.Tensor, dw: torch.Tensor, db: Optiona
                                       _ptr(db), _stream()), "mm_dense_wgrad")
 
 
+def dense_wgrad_split(x_split: torch.Tensor, K: int, dz: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
+    """dense_wgrad with x given as the split-bf16 operand (M, 2*Kp) the forward layer consumed (mm_dense_wgrad_split)."""
+    _dev(x_split, "x_split", torch.bfloat16), _dev(dz, "dz", torch.float32), _dev(dw, "dw", torch.float32)
+    M = x_split.shape[0]
+    Kp = tc_padded_k(K)
+    N = dz.shape[1]
+    if tuple(x_split.shape) != (M, 2 * Kp) or not x_split.is_contiguous():
+        raise ValueError(f"x_split must be a contiguous bf16 ({M}, {2 * Kp}) matrix")
+    if dz.shape[0] != M or tuple(dw.shape) != (K, N) or not dw.is_contiguous():
+        raise ValueError(f"dz must be ({M}, N) and dw a contiguous ({K}, {N}) matrix")
+    if db is not None and (_dev(db, "db", torch.float32).numel() != N or not db.is_contiguous()):
+        raise ValueError(f"db must hold {N} contiguous values")
+    _cabi.check(_lib().mm_dense_wgrad_split(x_split.data_ptr(), M, K, Kp, dz.data_ptr(), N, _row_stride(dz, "dz"), dw.data_ptr(), _ptr(db),
+                                            _stream()), "mm_dense_wgrad_split")
+
+
 def dense_dgrad(dz: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dx (M, K) = dz (M, N) @ W^T, W the Keras kernel (K, N), zeroed where mask <= 0 (mm_dense_dgrad; N <= 128)."""
     _dev(dz, "dz", torch.float32), _dev(W, "W", torch.float32), _dev(dx, "dx", torch.float32)
@@ -811,9 +827,11 @@ def dense_dgrad(dz: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, mask: Optio
 
 
 def dlrm_interact_backward(weights, indices, slots, rows, D: int, bottom: Optional[torch.Tensor], bottom_slot: int,
-                           dA: torch.Tensor, grad_rows, d_bottom: Optional[torch.Tensor], mask_bottom: bool = True) -> None:
-    """Backward of dlrm_lookup_interact (fp32 rows, replicated tables): grad_rows[t] (B, D) <- IndexedSlices values of table t,
-    d_bottom (B, D) <- gradient of the bottom vector (mm_dlrm_interact_backward)."""
+                           dA: torch.Tensor, grad_rows, d_bottom: Optional[torch.Tensor], mask_bottom: bool = True,
+                           operand_rows: bool = False) -> None:
+    """Backward of dlrm_lookup_interact (replicated tables): grad_rows[t] (B, D) <- IndexedSlices values of table t,
+    d_bottom (B, D) <- gradient of the bottom vector (mm_dlrm_interact_backward).  operand_rows=True (D = 64): `weights`
+    and `bottom` are bf16 split rows (rows, 2*D) = [hi | lo], as in dlrm_lookup_interact."""
     _dev(dA, "dA", torch.float32)
     B = dA.shape[0]
     n = len(weights)
@@ -822,11 +840,12 @@ def dlrm_interact_backward(weights, indices, slots, rows, D: int, bottom: Option
     arr = (_cabi.LookupTable * n)()
     gp = (C.c_void_p * n)()
     gstride = None
+    wdt, wcols = (torch.bfloat16, 2 * D) if operand_rows else (torch.float32, D)
     for t in range(n):
-        w = _dev(weights[t], f"weights[{t}]", torch.float32)
+        w = _dev(weights[t], f"weights[{t}]", wdt)
         ix = _dev(indices[t], f"indices[{t}]")
-        if w.dim() != 2 or w.shape[1] != D or not w.is_contiguous():
-            raise ValueError(f"weights[{t}] must be a contiguous (rows, {D}) float32 matrix")
+        if w.dim() != 2 or w.shape[1] != wcols or not w.is_contiguous():
+            raise ValueError(f"weights[{t}] must be a contiguous (rows, {wcols}) {wdt} matrix")
         wb = index_bytes_of(ix)
         if ix.numel() != B * (3 if wb == 3 else 1) or not ix.is_contiguous():
             raise ValueError(f"indices[{t}] must be contiguous with {B} ids")
@@ -843,14 +862,18 @@ def dlrm_interact_backward(weights, indices, slots, rows, D: int, bottom: Option
             gp[t] = g.data_ptr()
     P = 0
     F = n + (1 if bottom is not None else 0)
+    bstride = 0
     if bottom is not None:
-        _dev(bottom, "bottom", torch.float32)
+        _dev(bottom, "bottom", wdt)
+        if bottom.shape[0] != B or bottom.shape[1] != wcols:
+            raise ValueError(f"bottom must be ({B}, {wcols}) {wdt}")
+        bstride = _row_stride(bottom, "bottom") // (2 if operand_rows else 1)
         P = dA.shape[1] - F * (F - 1) // 2
     _cabi.check(
-        _lib().mm_dlrm_interact_backward(arr, n, B, D, _ptr(bottom), 0 if bottom is None else _row_stride(bottom, "bottom"),
-                                         bottom_slot, P, dA.data_ptr(), _row_stride(dA, "dA"), gp, gstride or D, _ptr(d_bottom),
+        _lib().mm_dlrm_interact_backward(arr, n, B, D, _ptr(bottom), bstride, bottom_slot, P, dA.data_ptr(), _row_stride(dA, "dA"), gp,
+                                         gstride or D, _ptr(d_bottom),
                                          0 if d_bottom is None else _row_stride(_dev(d_bottom, "d_bottom", torch.float32), "d_bottom"),
-                                         1 if mask_bottom else 0, _stream()),
+                                         1 if mask_bottom else 0, 1 if operand_rows else 0, _stream()),
         "mm_dlrm_interact_backward")
 
 

@@ -238,16 +238,25 @@ class DLRMTrainer:
         self.tdense = [torch.zeros_like(t.table) if t.table.shape[0] <= DENSE_PATH_MAX_ROWS else None for t in self.tables]
 
         # ---- activations and gradients
+        # operand-format rows for the lookup + interaction kernels (forward and backward) (D = 64, mirrors enabled): the tables' mirrors (the
+        # optimizer kernels keep them in step) and the bottom vector as the last bottom layer's split output
+        from .blocks import table_mirror
+
+        self.operand_rows = bool(D == 64 and table_mirror())
+        if self.operand_rows:
+            for t in self.tables:
+                t.operand_mirror()
         f32 = dict(dtype=torch.float32, device=self.device)
         self.K0 = len(body.continuous.features)
         self.x0 = torch.zeros((B, self.K0), **f32)
         self.x0_split = torch.zeros((B, 2 * ops.tc_padded_k(self.K0)), dtype=torch.bfloat16, device=self.device)
         self.h = [torch.zeros((B, l.units), **f32) for l in self.bottom]
-        self.h_split = [torch.zeros((B, 2 * ops.tc_padded_k(l.units)), dtype=torch.bfloat16, device=self.device) for l in self.bottom[:-1]]
+        n_split = len(self.bottom) if self.operand_rows else len(self.bottom) - 1
+        self.h_split = [torch.zeros((B, 2 * ops.tc_padded_k(l.units)), dtype=torch.bfloat16, device=self.device) for l in self.bottom[:n_split]]
         F = len(self.slots)
         self.OW = D + F * (F - 1) // 2
         self.ldA = (self.OW + 3) // 4 * 4
-        self.A = torch.zeros((B, self.ldA), **f32)
+        self.A = None if self.operand_rows else torch.zeros((B, self.ldA), **f32)
         self.dA = torch.zeros((B, self.ldA), **f32)
         self.A_split = torch.zeros((B, 2 * ops.tc_padded_k(self.OW)), dtype=torch.bfloat16, device=self.device)
         self.t = [torch.zeros((B, l.units), **f32) for l in self.top]
@@ -296,7 +305,7 @@ class DLRMTrainer:
         # -- bottom tower
         op, K = v(self.x0_split), self.K0
         for i, l in enumerate(self.bottom):
-            nxt = v(self.h_split[i]) if i < nb - 1 else None
+            nxt = v(self.h_split[i]) if i < len(self.h_split) else None
             ops.dense_tc(op, K, self._wsplit[i], l.units, l.bias, l.activation, out_f32=h[i], out_split=nxt)
             op, K = nxt, l.units
         # -- lookup + interaction (fp32 rows)
@@ -305,9 +314,16 @@ class DLRMTrainer:
         rows = [t.shape[0] for t in tabs]
         tslots = [self.slots[f] for f in self.feats]
         bslot = self.slots["bottom_block"]
-        A_view, dA_view = self.A[:b, :self.OW], self.dA[:b, :self.OW]
-        ops.dlrm_lookup_interact(tabs, idx, tslots, rows, D, h[-1], bslot, A_view, self.oob)
-        ops.split_rows(A_view, out=v(self.A_split))
+        dA_view = self.dA[:b, :self.OW]
+        if self.operand_rows:
+            # operand-format rows in, split-bf16 operand of the top tower out: no fp32 copy of [bottom | interactions] exists
+            A_view = None
+            ops.dlrm_lookup_interact([t._mirror for t in self.tables], idx, tslots, rows, D, v(self.h_split[-1]), bslot,
+                                     v(self.A_split), self.oob, operand_rows=True)
+        else:
+            A_view = self.A[:b, :self.OW]
+            ops.dlrm_lookup_interact(tabs, idx, tslots, rows, D, h[-1], bslot, A_view, self.oob)
+            ops.split_rows(A_view, out=v(self.A_split))
         # -- top tower
         op, K = v(self.A_split), self.OW
         for i, l in enumerate(self.top):
@@ -322,16 +338,22 @@ class DLRMTrainer:
         # -- top tower backward
         for i in range(nt - 1, -1, -1):
             l = self.top[i]
-            x = t_[i - 1] if i > 0 else A_view
-            ops.dense_wgrad(x, dt[i], a.view(a.grad, nb + i, "kernel"), a.view(a.grad, nb + i, "bias"))
+            if i == 0 and A_view is None:
+                ops.dense_wgrad_split(v(self.A_split), self.OW, dt[0], a.view(a.grad, nb, "kernel"), a.view(a.grad, nb, "bias"))
+            else:
+                ops.dense_wgrad(t_[i - 1] if i > 0 else A_view, dt[i], a.view(a.grad, nb + i, "kernel"), a.view(a.grad, nb + i, "bias"))
             if i > 0:
                 ops.dense_dgrad(dt[i], l.kernel, dt[i - 1], mask=t_[i - 1] if self.top[i - 1].activation == "relu" else None)
             else:
                 ops.dense_dgrad(dt[0], l.kernel, dA_view)
         # -- interaction + lookup backward
         self._slices = [self.slices[t][:b] for t in range(len(tabs))]
-        ops.dlrm_interact_backward(tabs, idx, tslots, rows, D, h[-1], bslot, dA_view, self._slices, dh[-1],
-                                   mask_bottom=self.bottom[-1].activation == "relu")
+        if self.operand_rows:
+            ops.dlrm_interact_backward([t._mirror for t in self.tables], idx, tslots, rows, D, v(self.h_split[-1]), bslot, dA_view,
+                                       self._slices, dh[-1], mask_bottom=self.bottom[-1].activation == "relu", operand_rows=True)
+        else:
+            ops.dlrm_interact_backward(tabs, idx, tslots, rows, D, h[-1], bslot, dA_view, self._slices, dh[-1],
+                                       mask_bottom=self.bottom[-1].activation == "relu")
         # -- bottom tower backward
         for i in range(nb - 1, -1, -1):
             l = self.bottom[i]

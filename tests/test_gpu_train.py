@@ -53,6 +53,11 @@ def test_dense_wgrad_and_dgrad(device, M, K, N):
     close(db, dz.double().sum(0), what="db")
     ops.dense_wgrad(x, dz, dw, db)  # accumulates
     close(dw, 2 * (x.double().t() @ dz.double()), what="dW accumulated")
+    dw.zero_()
+    db.zero_()
+    ops.dense_wgrad_split(ops.split_rows(x), K, dz, dw, db)  # X as the split-bf16 operand of the forward layer
+    close(dw, x.double().t() @ dz.double(), what="dW from the split operand")
+    close(db, dz.double().sum(0), what="db (split operand)")
     if N <= 128:
         dxb = torch.full((M, ldx), 7.0, dtype=torch.float32, device=device)
         dx = dxb[:, :K]
@@ -154,6 +159,18 @@ def test_interact_backward(device, D, T, B):
     close(d_bottom, ref_bottom * (bottom > 0), what="d_bottom (masked)")
     ops.dlrm_interact_backward(tables, ids, slots, rows_n, D, bottom, slot_b, dA, [grads[t] for t in range(T)], d_bottom, mask_bottom=False)
     close(d_bottom, ref_bottom, what="d_bottom")
+    if D == 64:
+        # operand-format rows (the tables' split-bf16 mirrors + the bottom vector as split rows): same gradients
+        mirrors = [ops.split_rows(w) for w in tables]
+        bsplit = ops.split_rows(bottom)
+        for mask in (True, False):
+            grads.fill_(9.0)
+            d_bottom.fill_(9.0)
+            ops.dlrm_interact_backward(mirrors, ids, slots, rows_n, D, bsplit, slot_b, dA, [grads[t] for t in range(T)], d_bottom,
+                                       mask_bottom=mask, operand_rows=True)
+            for t in range(T):
+                close(grads[t], ref_rows[t], what=f"operand rows: slices of table {t}")
+            close(d_bottom, ref_bottom * (bottom > 0) if mask else ref_bottom, what="operand rows: d_bottom")
 
 
 def test_interact_backward_out_of_range_ids_read_zero_rows(device):
