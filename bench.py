@@ -840,8 +840,69 @@ def train_record(ctx):
                 "d2h_bytes_per_step": 4, "steps": steps},
         "fwd_only_ratio_note": "compare with the headline `value` (forward only) of the same line",
     }
+    # roofline of the step's largest kernel (lookup + interaction backward), timed alone with CUDA events on this stream
+    try:
+        if tr.operand_rows:
+            F_n = len(tr.slots)
+            tabs = [t._mirror for t in tr.tables]
+            rows = [t.table.shape[0] for t in tr.tables]
+            tslots = [tr.slots[f] for f in tr.feats]
+            idx = tr._indices(inputs)
+            dA_view = tr.dA[:, :tr.OW]
+            sl = [tr.slices[t] for t in range(len(tabs))]
+            k_ms = event_times(lambda i: ops.dlrm_interact_backward(tabs, idx, tslots, rows, tr.D, tr.h_split[-1], tr.slots["bottom_block"], dA_view,
+                                                                     sl, tr.dh[-1], mask_bottom=True, operand_rows=True), 20)
+            id_bytes = sum(ops.index_bytes_of(i) for i in idx)
+            T = len(tabs)
+            per_sample = (T + 1) * 256 + tr.OW * 4 + T * 256 + 256 + id_bytes  # rows + bottom in, dA in, slices + d_bottom out, ids
+            peak, peak_src = measured_peaks()
+            ach = per_sample * B / (k_ms * 1e-3) / 1e9
+            rec["roofline"] = {"bound": "hbm", "kernel": "interact_bwd_ps_kernel (mm_dlrm_interact_backward, operand-format rows)",
+                               "unit": "GB/s", "achieved": ach, "peak": peak, "peak_source": peak_src, "frac": ach / peak, "kernel_ms": k_ms,
+                               "algorithmic_bytes_per_launch": per_sample * B,
+                               "traffic": 749990144.0, "dram_frac": 749990144.0 / (k_ms * 1e-3) / 1e9 / peak, "traffic_source": "profiles/r02_ncu_train_kernels.txt (ncu --set full, dram read + write of one launch)",
+                               "share_of_step": k_ms / (ms_max / steps)}
+    except Exception as e:  # evidence, never fatal
+        rec["roofline"] = {"error": f"{type(e).__name__}: {e}"}
+    if world == 1 and not args.no_cpu_baseline and ctx.rank == 0:
+        try:
+            rec["cpu_baseline"] = train_cpu_baseline(model, hosts[0], label, min(args.cpu_sample or 16384, B), usable_cores())
+        except Exception as e:
+            rec["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     del tr, model
     return rec
+
+
+def train_cpu_baseline(model, host_batch, label, sample_rows, cores, budget_s=8.0):
+    """The same training step on the host cores (oracle/oracle_torch.py:DLRMTrainCPU: autograd with sparse embedding
+    gradients + Adagrad) on a bounded sample of the batch — a reported baseline, not a target."""
+    import torch
+    from oracle import oracle_torch
+
+    torch.set_num_threads(cores)
+    body = model.body
+    tables = {n: t.embeddings.cpu() for n, t in body.embeddings.tables.items()}
+    f2t = {f: t.table_name for f, t in body.embeddings.feature_to_table.items()}
+    layers = lambda mlp: [{"kernel": l.kernel.cpu(), "bias": l.bias.cpu(), "activation": l.activation} for l in mlp.dense_layers]
+    hd = model.prediction.to_call
+    cpu = oracle_torch.DLRMTrainCPU(tables, f2t, layers(body.bottom_block), layers(body.top_block),
+                                    {"kernel": hd.kernel.cpu(), "bias": hd.bias.cpu(), "activation": "linear"}, lr=0.01)
+    del tables
+    idx = {n: torch.from_numpy(host_batch[n][:sample_rows]) for n in f2t}
+    dense = {n: torch.from_numpy(host_batch[n][:sample_rows]) for n in body.continuous.features}
+    y = torch.from_numpy(host_batch[label][:sample_rows])
+    cpu.step(idx, dense, y)  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        cpu.step(idx, dense, y)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 20:
+            break
+    return {"value": sample_rows * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} training steps on {sample_rows} samples of the same batch (PyTorch-CPU: autograd with sparse embedding "
+                      "gradients + Adagrad; the reference's TF-CPU train_step is not runnable here)"}
 
 
 def secondary_record(ctx, kind):

@@ -192,16 +192,20 @@ class Model(Block):
         if getattr(self, "optimizer", None) is None:
             raise RuntimeError("compile() the model with an optimizer before training it")
         tr = getattr(self, "_trainer", None)
-        if tr is None or tr.B < batch_size or tr.group is not group:
-            if tr is not None:
-                raise NotImplementedError("the training batch size grew after the first step: compile for the largest batch "
-                                          "(model.trainer(batch_size) before the first train_step)")
-            tr = self._trainer = DLRMTrainer(self, self.optimizer, batch_size, group=group)
+        if tr is not None:
+            if group is not None and tr.group is not group:
+                raise ValueError("this model already trains with another process group")
+            if tr.B < batch_size:
+                raise NotImplementedError("the training batch size grew after the first step: create the engine for the largest "
+                                          "batch first (model.trainer(batch_size) before the first train_step)")
+            return tr
+        tr = self._trainer = DLRMTrainer(self, self.optimizer, batch_size, group=group)
         return tr
 
     def train_step(self, data) -> Dict[str, torch.Tensor]:
         """One optimizer step on `data` = (inputs, targets[, sample_weight]); returns the reference's step metrics
-        {"loss", "loss_batch", "regularization_loss"} as device scalars (models/base.py:1121-1177)."""
+        {"loss", "loss_batch", "regularization_loss"} as device scalars (models/base.py:1121-1177).  The loss scalars are
+        views of the engine's loss buffer: valid until the next step (clone to keep)."""
         if getattr(self, "optimizer", None) is None:
             raise RuntimeError("compile() the model with an optimizer before training it")
         if not isinstance(data, (tuple, list)) or len(data) < 2:
@@ -243,7 +247,10 @@ class Model(Block):
             if n == 0:
                 raise ValueError("fit: the loader produced no batches")
             history["loss"].append(float(total.item()) / n)
-        self.history = type("History", (), {"history": history})()
+            self._trainer.check_indices()
+        from .train import History
+
+        self.history = History(history)
         return self.history
 
     # -- CUDA-graph runtime (models_b200/graph.py) ---------------------------------------------

@@ -33,6 +33,14 @@ INT32_MAX = 2**31 - 1
 DENSE_PATH_MAX_ROWS = 131072  # tables up to this size accumulate duplicate ids in a dense (rows, D) gradient
 
 
+class History:
+    """What Keras `fit` returns: `.history["loss"]` = mean batch loss of every epoch."""
+
+    def __init__(self, history: Dict[str, List[float]]):
+        self.history = history
+        self.epoch = list(range(len(history.get("loss", []))))
+
+
 class Optimizer:
     """Hyper-parameters of one of the update rules in include/mm_b200.h (Keras argument names and defaults)."""
 
@@ -221,12 +229,11 @@ class DLRMTrainer:
         self.slots = body.slots()
         self.D = body.embedding_dim
         self.tables = [emb.feature_to_table[f] for f in self.feats]
-        uniq, seen = [], set()
+        seen = set()
         for t in self.tables:
             if id(t) in seen:
                 raise NotImplementedError("training with a table shared between features is not implemented")
             seen.add(id(t))
-            uniq.append(t)
             if not t.trainable:
                 raise NotImplementedError("frozen embedding tables are not implemented in the training step")
         T, B, D = len(self.tables), self.B, self.D
@@ -470,6 +477,17 @@ class DLRMTrainer:
         self._graph.replay()
         self._after_step()
         return self.loss
+
+    def check_indices(self) -> None:
+        """Raise IndexError if any batch since the last check carried an id outside its table (the forward read a zero
+        row for it and its gradient was dropped).  One device-to-host read: `fit` calls it once per epoch, not per step."""
+        if self.oob is None:
+            return
+        n = int(self.oob.item())
+        if n:
+            self.oob.zero_()
+            raise IndexError(f"{n} indices out of range for the embedding tables "
+                             "(TF raises InvalidArgumentError: indices[...] is not in [0, rows))")
 
     def set_learning_rate(self, lr: float) -> None:
         self.opt.learning_rate = float(lr)

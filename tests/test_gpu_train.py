@@ -485,6 +485,29 @@ def test_fit_with_loader_learns_a_planted_rule(device, tmp_path):
     y = click[16000:]
     auc_pairs = (p[y == 1][:, None] > p[y == 0][None, :]).mean()
     assert auc_pairs > 0.6, auc_pairs
+    # a trained (compiled) model goes through the checkpoint boundary like any other: variables are views of the
+    # trainer's arena, the optimizer and the History object ride along in the structure file
+    model.save(tmp_path / "export")
+    loaded = mm.Model.load(tmp_path / "export")
+    np.testing.assert_array_equal(loaded(held).cpu().numpy().reshape(-1), p)
+    assert loaded.optimizer.kind == "adam" and loaded.history.history["loss"] == losses
+
+
+def test_out_of_range_ids_are_counted_and_reported(device):
+    schema, model = _small_model(device, D=16)
+    model.compile(optimizer="sgd")
+    b = datasets.generate_batch(schema, 64, seed=2, index_law="uniform")
+    feats, targets = datasets.split_targets(schema, b)
+    feats["C1"] = feats["C1"].copy()
+    feats["C1"][3] = 10**6
+    y = torch.from_numpy(np.asarray(next(iter(targets.values())))).to(device)
+    before = model.body.embeddings.feature_to_table["C1"].embeddings.clone()
+    model.train_step((H.device_batch(feats, device), y))
+    assert torch.isfinite(model._trainer.loss).all()
+    with pytest.raises(IndexError, match="1 indices out of range"):
+        model._trainer.check_indices()
+    model._trainer.check_indices()  # the counter was reset
+    assert before.shape == model.body.embeddings.feature_to_table["C1"].embeddings.shape  # no row was added or touched out of bounds
 
 
 def test_compile_validation(device):

@@ -147,3 +147,59 @@ def test_golden_fixture(name):
     from tests.golden import replay
 
     replay.check(GOLDEN / name)
+
+
+def test_training_port_matches_oracle_train():
+    """oracle_torch.DLRMTrainCPU (the timed CPU baseline of bench.py's training record: sparse-gradient autograd +
+    torch.optim.Adagrad) against oracle_train (float64 autograd + the Keras update rule restated in NumPy)."""
+    import torch
+
+    from oracle import oracle_torch, oracle_train
+
+    rng = np.random.default_rng(0)
+    tabs = {"a": rng.normal(size=(7, 8)).astype(np.float32), "b": rng.normal(size=(5, 8)).astype(np.float32)}
+    f2t = {"a": "a", "b": "b"}
+
+    def layer(k, n, act):
+        return {"kernel": (rng.normal(size=(k, n)) * 0.3).astype(np.float32), "bias": np.zeros(n, np.float32), "activation": act}
+
+    bottom, top, head = [layer(2, 8, "relu")], [layer(8 + 3, 6, "relu")], layer(6, 1, "linear")
+    B = 16
+    batch = {"a": rng.integers(0, 7, B), "b": rng.integers(0, 5, B), "x": rng.random(B).astype(np.float32), "y": rng.random(B).astype(np.float32)}
+    t = rng.integers(0, 2, B)
+    loss, _, g = oracle_train.dlrm_loss_and_grads(batch, tabs, f2t, ["x", "y"], bottom, top, head, t)
+    tt = lambda ls: [{k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in l.items()} for l in ls]
+    cpu = oracle_torch.DLRMTrainCPU({k: torch.from_numpy(v) for k, v in tabs.items()}, f2t, tt(bottom), tt(top), tt([head])[0], lr=0.1)
+    got = cpu.step({k: torch.from_numpy(batch[k]) for k in f2t}, {k: torch.from_numpy(batch[k]) for k in ("x", "y")}, torch.from_numpy(t))
+    np.testing.assert_allclose(got, loss, rtol=1e-6)
+    for name in ("a", "b"):
+        uniq = np.unique(batch[name])
+        ref = oracle_train.sparse_update("adagrad", tabs[name], uniq, g[f"table/{name}"][uniq], {"a": np.full(tabs[name].shape, 0.1)}, 0.1)
+        np.testing.assert_allclose(cpu.tables[name].detach().numpy(), ref, rtol=0, atol=1e-6)
+    ref_k = oracle_train.dense_update("adagrad", top[0]["kernel"], g["top/kernel_0"], {"a": np.full(top[0]["kernel"].shape, 0.1)}, 0.1)
+    np.testing.assert_allclose(cpu.layers["top"][0]["kernel"].detach().numpy(), ref_k, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("opt", ["sgd", "adagrad"])
+def test_optimizer_rules_match_torch_optim(opt):
+    """The Keras update rules restated in oracle_train coincide with torch.optim for SGD and Adagrad (dense and, with
+    duplicate ids summed first, sparse)."""
+    import torch
+
+    from oracle import oracle_train
+
+    rng = np.random.default_rng(3)
+    w = rng.normal(size=(9, 4))
+    ids = np.array([1, 1, 5, 8, 1, 5])
+    vals = rng.normal(size=(6, 4))
+    p = torch.nn.Parameter(torch.from_numpy(w.copy()))
+    o = torch.optim.SGD([p], lr=0.1) if opt == "sgd" else torch.optim.Adagrad([p], lr=0.1, initial_accumulator_value=0.1, eps=1e-7)
+    state = {} if opt == "sgd" else {"a": np.full(w.shape, 0.1)}
+    ref = w
+    for _ in range(2):
+        dense = np.zeros_like(w)
+        np.add.at(dense, ids, vals)
+        p.grad = torch.from_numpy(dense.copy())
+        o.step()
+        ref = oracle_train.sparse_update(opt, ref, ids, vals, state, 0.1)
+        np.testing.assert_allclose(p.detach().numpy(), ref, rtol=1e-12, atol=1e-12)
