@@ -552,14 +552,14 @@ def usable_cores() -> int:
         return os.cpu_count() or 1
 
 
-def pick_threads(run, cores):
+def pick_threads(run, cores, candidates=None):
     """The CPU leg should use 'all the host threads it can use' — but more OpenMP threads than the
     small per-op work can feed makes PyTorch-CPU slower, not faster (128 threads: 4.7 s per 16 384-sample
     pass vs 37 ms at 8).  Time one pass at a few thread counts and keep the fastest."""
     import torch
 
     best, best_t = 1, float("inf")
-    for n in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+    for n in sorted(candidates or {cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
         torch.set_num_threads(n)
         run()
         t0 = time.perf_counter()
@@ -879,7 +879,7 @@ def train_cpu_baseline(model, host_batch, label, sample_rows, cores, budget_s=8.
     import torch
     from oracle import oracle_torch
 
-    torch.set_num_threads(cores)
+    torch.set_num_threads(min(cores, 32))
     body = model.body
     tables = {n: t.embeddings.cpu() for n, t in body.embeddings.tables.items()}
     f2t = {f: t.table_name for f, t in body.embeddings.feature_to_table.items()}
@@ -891,7 +891,8 @@ def train_cpu_baseline(model, host_batch, label, sample_rows, cores, budget_s=8.
     idx = {n: torch.from_numpy(host_batch[n][:sample_rows]) for n in f2t}
     dense = {n: torch.from_numpy(host_batch[n][:sample_rows]) for n in body.continuous.features}
     y = torch.from_numpy(host_batch[label][:sample_rows])
-    cpu.step(idx, dense, y)  # warm-up
+    # 128 OpenMP threads make these small ops ~100x slower than 8-32 (see pick_threads): only the small counts are tried
+    cores = pick_threads(lambda: cpu.step(idx, dense, y), cores, candidates={min(cores, 32), min(cores, 16), min(cores, 8)})
     t0 = time.perf_counter()
     n = 0
     while True:
