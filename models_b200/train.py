@@ -6,9 +6,10 @@ blocks/optimizer.py:342).
 What a step launches (DLRM, bottom [.., D], top [...], BinaryOutput):
 
     forward   concat+split -> dense_tc per bottom layer (fp32 activation saved + operand of the next layer) -> fused
-              lookup + interaction (fp32 rows) -> split -> dense_tc per top layer
+              lookup + interaction -> dense_tc per top layer.  D = 64 with table mirrors: the kernel reads operand-format
+              rows and writes the top tower's split operand directly; otherwise fp32 rows + one split pass
     loss      mm_bce_head_fwd_bwd: output Dense(1) + sigmoid + BCE forward AND backward in one pass
-    backward  per Dense layer mm_dense_wgrad (dW, db) + mm_dense_dgrad (input gradient, relu mask fused);
+    backward  per Dense layer mm_dense_wgrad[_split] (dW, db) + mm_dense_dgrad (input gradient, relu mask fused);
               mm_dlrm_interact_backward: pair gradients -> IndexedSlices per table + bottom-vector gradient
     update    mm_opt_tick, [DP: all-reduce of the dense gradient arena, all-gather of the slices], mm_dense_apply over the flat
               parameter arena, mm_sparse_rows_apply (duplicate ids summed, one update per touched row), mm_split_weights
@@ -16,7 +17,7 @@ What a step launches (DLRM, bottom [.., D], top [...], BinaryOutput):
 
 All Dense variables of the model are re-homed into ONE flat fp32 arena (gradients and optimizer slots mirror its layout), so
 the dense update is one launch and data-parallel training needs one all-reduce.  Every buffer is static: a step can be
-captured into a CUDA graph (`capture=True`), the learning rate lives in device memory.
+captured into a CUDA graph (`DLRMTrainer.capture()` / `replay()`), the learning rate lives in device memory.
 """
 from __future__ import annotations
 
