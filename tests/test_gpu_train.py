@@ -343,7 +343,8 @@ def _flat_state(model):
 def test_training_steps_match_oracle(device, opt, D):
     """Three optimizer steps (different batches, heavy id duplication: tables of <= 300 rows) against autograd of the
     restated forward + the Keras update rules in float64.  What is compared is the UPDATE of every variable (after -
-    before): 5e-2 in the Frobenius norm, 0.3 of the largest element.  A relu unit whose pre-activation is within rounding
+    before): 0.1 in the Frobenius norm (observed: <= 2.4e-2), 0.5 of the largest element (observed: <= 8e-2; a wrong
+    rule or sign gives >= 1).  A relu unit whose pre-activation is within rounding
     of zero may be on in one implementation and off in the other (about one unit per step at this size); that changes ONE
     sample's gradient by a few percent — visible in the rows that sample touched (max norm), negligible in the
     Frobenius norm.  The kernels' own accuracy (3e-4) is asserted by the tests above and by the reference golden."""
@@ -401,8 +402,8 @@ def test_training_steps_match_oracle(device, opt, D):
         assert np.max(np.abs(upd_ref)) > 0, i  # every variable trains
         upd = np.asarray(a, dtype=np.float64) - b0
         fro = float(np.linalg.norm(upd - upd_ref) / np.linalg.norm(upd_ref))
-        assert fro < 5e-2, f"update of variable {i} after 3 {opt} steps: relative Frobenius error {fro:.3e}"
-        close(upd, upd_ref, 0.3, f"update of variable {i} after 3 {opt} steps")
+        assert fro < 0.1, f"update of variable {i} after 3 {opt} steps: relative Frobenius error {fro:.3e}"
+        close(upd, upd_ref, 0.5, f"update of variable {i} after 3 {opt} steps")
     # rows no batch looked up did not move (lazy / sparse semantics), nor did their slots matter
     tr = model._trainer
     for t, f in enumerate(tr.feats):
