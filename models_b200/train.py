@@ -256,7 +256,6 @@ class DLRMTrainer:
                 t.operand_mirror()
         f32 = dict(dtype=torch.float32, device=self.device)
         self.K0 = len(body.continuous.features)
-        self.x0 = torch.zeros((B, self.K0), **f32)
         self.x0_split = torch.zeros((B, 2 * ops.tc_padded_k(self.K0)), dtype=torch.bfloat16, device=self.device)
         self.h = [torch.zeros((B, l.units), **f32) for l in self.bottom]
         n_split = len(self.bottom) if self.operand_rows else len(self.bottom) - 1
@@ -307,9 +306,8 @@ class DLRMTrainer:
         def v(t):
             return t[:b]
 
-        x0, h, t_, dt, dh = v(self.x0), [v(x) for x in self.h], [v(x) for x in self.t], [v(x) for x in self.dt], [v(x) for x in self.dh]
-        ops.concat_columns(pieces, x0)
-        ops.concat_split(pieces, out=v(self.x0_split))
+        h, t_, dt, dh = [v(x) for x in self.h], [v(x) for x in self.t], [v(x) for x in self.dt], [v(x) for x in self.dh]
+        ops.concat_split(pieces, out=v(self.x0_split))  # the concatenated continuous columns exist only as this operand
         # -- bottom tower
         op, K = v(self.x0_split), self.K0
         for i, l in enumerate(self.bottom):
@@ -365,8 +363,10 @@ class DLRMTrainer:
         # -- bottom tower backward
         for i in range(nb - 1, -1, -1):
             l = self.bottom[i]
-            x = h[i - 1] if i > 0 else x0
-            ops.dense_wgrad(x, dh[i], a.view(a.grad, i, "kernel"), a.view(a.grad, i, "bias"))
+            if i > 0:
+                ops.dense_wgrad(h[i - 1], dh[i], a.view(a.grad, i, "kernel"), a.view(a.grad, i, "bias"))
+            else:
+                ops.dense_wgrad_split(v(self.x0_split), self.K0, dh[0], a.view(a.grad, 0, "kernel"), a.view(a.grad, 0, "bias"))
             if i > 0:
                 ops.dense_dgrad(dh[i], l.kernel, dh[i - 1], mask=h[i - 1] if self.bottom[i - 1].activation == "relu" else None)
         self._idx, self._b = idx, b
