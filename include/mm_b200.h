@@ -470,6 +470,9 @@ int mm_dense_wgrad_split(const void* x_split, int64_t M, int K, int Kp, const fl
                          float* dw, float* db, void* stream);
 int mm_dense_dgrad(const float* dz, int64_t M, int N, int64_t dz_stride, const float* w, int K, const float* mask,
                    int64_t mask_stride, float* dx, int64_t dx_stride, void* stream);
+/* x (B, D) = mask > 0 ? x : 0, in place: the relu derivative on a gradient that did not come out of mm_dense_dgrad (layers
+ * wider than 128 units take dX = dZ W^T through mm_dense_tc on the transposed kernel). */
+int mm_relu_mask(float* x, int64_t B, int D, int64_t x_stride, const float* mask, int64_t mask_stride, void* stream);
 int mm_dlrm_interact_backward(const mm_lookup_table* tables_host, int n_tables, int64_t B, int D, const float* bottom,
                               int64_t bottom_stride, int bottom_slot, int P, const float* dA, int64_t dA_stride,
                               float* const* grad_rows_host, int64_t grad_stride, float* d_bottom,

@@ -136,6 +136,7 @@ SIGNATURES = {
     "mm_dense_wgrad": (_i, [_vp, _i64, _i, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
     "mm_dense_wgrad_split": (_i, [_vp, _i64, _i, _i, _vp, _i, _i64, _vp, _vp, _vp]),
     "mm_dense_dgrad": (_i, [_vp, _i64, _i, _i64, _vp, _i, _vp, _i64, _vp, _i64, _vp]),
+    "mm_relu_mask": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp]),
     "mm_dlrm_interact_backward": (_i, [C.POINTER(LookupTable), _i, _i64, _i, _vp, _i64, _i, _i, _vp, _i64,
                                        C.POINTER(C.c_void_p), _i64, _vp, _i64, _i, _i, _vp]),
     "mm_sparse_rows_apply": (_i, [C.POINTER(SparseTable), _i, _i64, _i, _i, _vp, _vp]),

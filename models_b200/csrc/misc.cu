@@ -136,6 +136,17 @@ __global__ void scale_shift_kernel(const float* __restrict__ x, long long B, int
 }
 
 
+// x = mask > 0 ? x : 0 in place over (B, D) row-major views: the relu derivative applied to a gradient (training step; the
+// narrow-layer dgrad kernel fuses it, the tensor-core path for wide layers applies it afterwards)
+__global__ void relu_mask_kernel(float* __restrict__ x, long long B, int D, long long sx, const float* __restrict__ mask, long long sm) {
+  const long long total = B * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D;
+    const int k = (int)(i - r * D);
+    if (!(mask[r * sm + k] > 0.0f)) x[r * sx + k] = 0.0f;
+  }
+}
+
 // out = a * b + c elementwise over (B, D) row-major views (the DCN-v2 cross combine x0 * projection + x when the
 // projection is not produced by a GEMM with the fused cross epilogue: low-rank kernels on the exact-fp32 engine)
 __global__ void fma3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
@@ -235,6 +246,17 @@ int mm_scale_shift(const float* x, int64_t B, int D, int64_t x_stride, const flo
   mm::scale_shift_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(x, B, D, x_stride, scale, shift, out,
                                                                                out_stride);
   return mm::check_launch("mm_scale_shift");
+}
+
+int mm_relu_mask(float* x, int64_t B, int D, int64_t x_stride, const float* mask, int64_t mask_stride, void* stream) {
+  MM_REQUIRE(x && mask && B >= 0 && D > 0 && x_stride >= D && mask_stride >= D, MM_ERR_ARG, "mm_relu_mask: null pointer, D<=0 or stride < D");
+  if (B == 0) return MM_OK;
+  const int threads = 256;
+  long long blocks = (B * D + threads - 1) / threads;
+  const long long cap = (long long)mm::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  mm::relu_mask_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(x, B, D, x_stride, mask, mask_stride);
+  return mm::check_launch("mm_relu_mask");
 }
 
 int mm_cross_combine(const float* x0, const float* proj, const float* x, int64_t B, int D, int64_t x0_stride,

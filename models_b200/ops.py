@@ -826,6 +826,16 @@ def dense_dgrad(dz: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, mask: Optio
     return dx
 
 
+def relu_mask(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """x = mask > 0 ? x : 0, in place (mm_relu_mask)."""
+    _dev(x, "x", torch.float32), _dev(mask, "mask", torch.float32)
+    if x.shape != mask.shape:
+        raise ValueError("x and mask must have the same shape")
+    _cabi.check(_lib().mm_relu_mask(x.data_ptr(), x.shape[0], x.shape[1], _row_stride(x, "x"), mask.data_ptr(), _row_stride(mask, "mask"),
+                                    _stream()), "mm_relu_mask")
+    return x
+
+
 def dlrm_interact_backward(weights, indices, slots, rows, D: int, bottom: Optional[torch.Tensor], bottom_slot: int,
                            dA: torch.Tensor, grad_rows, d_bottom: Optional[torch.Tensor], mask_bottom: bool = True,
                            operand_rows: bool = False) -> None:

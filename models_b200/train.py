@@ -213,8 +213,6 @@ class DLRMTrainer:
         for l in self.bottom + self.top:
             if l.activation not in ("relu", "linear"):
                 raise NotImplementedError(f"{l.name}: training supports relu / linear tower activations, got {l.activation!r}")
-            if l.units > 128:
-                raise NotImplementedError(f"{l.name}: training supports layers of <= 128 units")
         if self.head.input_dim > 256:
             raise NotImplementedError("the output layer's input must be <= 256 wide")
         self.arena = DenseArena(self.bottom + self.top + [self.head], optimizer, self.device)
@@ -223,6 +221,15 @@ class DLRMTrainer:
         for l, ws in zip(self.bottom + self.top, self._wsplit):
             l._w_split = ws  # the forward path of this model keeps reading the refreshed operand copies
         self.hyper = torch.from_numpy(optimizer.hyper()).to(self.device)
+        # layers wider than mm_dense_dgrad's 128 units take dX = dZ W^T through the tensor-core forward GEMM on the transposed
+        # kernel: per such layer a transposed copy, its split operand and the split of dZ
+        self._wide: Dict[int, dict] = {}
+        for li, l in enumerate(self.bottom + self.top):
+            if l.units > 128 and li != 0:  # the first bottom layer needs no input gradient
+                K, N = l.kernel.shape
+                wT = torch.empty((N, K), dtype=torch.float32, device=self.device)
+                self._wide[li] = dict(wT=wT, wT_split=torch.zeros((ops.tc_padded_n(K), 2 * ops.tc_padded_k(N)), dtype=torch.bfloat16, device=self.device),
+                                      dz_split=torch.zeros((self.B, 2 * ops.tc_padded_k(N)), dtype=torch.bfloat16, device=self.device))
 
         # ---- tables
         emb = body.embeddings
@@ -349,9 +356,9 @@ class DLRMTrainer:
             else:
                 ops.dense_wgrad(t_[i - 1] if i > 0 else A_view, dt[i], a.view(a.grad, nb + i, "kernel"), a.view(a.grad, nb + i, "bias"))
             if i > 0:
-                ops.dense_dgrad(dt[i], l.kernel, dt[i - 1], mask=t_[i - 1] if self.top[i - 1].activation == "relu" else None)
+                self._dgrad(nb + i, l, dt[i], dt[i - 1], t_[i - 1] if self.top[i - 1].activation == "relu" else None)
             else:
-                ops.dense_dgrad(dt[0], l.kernel, dA_view)
+                self._dgrad(nb, l, dt[0], dA_view, None)
         # -- interaction + lookup backward
         self._slices = [self.slices[t][:b] for t in range(len(tabs))]
         if self.operand_rows:
@@ -368,8 +375,23 @@ class DLRMTrainer:
             else:
                 ops.dense_wgrad_split(v(self.x0_split), self.K0, dh[0], a.view(a.grad, 0, "kernel"), a.view(a.grad, 0, "bias"))
             if i > 0:
-                ops.dense_dgrad(dh[i], l.kernel, dh[i - 1], mask=h[i - 1] if self.bottom[i - 1].activation == "relu" else None)
+                self._dgrad(i, l, dh[i], dh[i - 1], h[i - 1] if self.bottom[i - 1].activation == "relu" else None)
         self._idx, self._b = idx, b
+
+    def _dgrad(self, li: int, layer: _Dense, dz: torch.Tensor, dx: torch.Tensor, mask: Optional[torch.Tensor]) -> None:
+        """dx = dz W^T (zeroed where mask <= 0) for layer `li` of bottom + top."""
+        wide = self._wide.get(li)
+        if wide is None:
+            ops.dense_dgrad(dz, layer.kernel, dx, mask=mask)
+            return
+        K, N = layer.kernel.shape
+        b = dz.shape[0]
+        wide["wT"].copy_(layer.kernel.t())
+        ops.split_weights(wide["wT"], out=wide["wT_split"])
+        ops.split_rows(dz, out=wide["dz_split"][:b])
+        ops.dense_tc(wide["dz_split"][:b], N, wide["wT_split"], K, None, None, out_f32=dx)
+        if mask is not None:
+            ops.relu_mask(dx, mask)
 
     def apply_gradients(self) -> None:
         a = self.arena

@@ -419,6 +419,46 @@ def test_training_steps_match_oracle(device, opt, D):
     assert H.rel_err(got, H.oracle_dlrm(model, feats)) < 2e-4
 
 
+def test_wide_towers_train_through_the_tensor_core_dgrad(device):
+    """Layers wider than 128 units (mm_dense_dgrad's limit) take dX = dZ W^T through mm_dense_tc on the transposed kernel +
+    mm_relu_mask: one step's loss and every gradient against the oracle."""
+    schema, model = _small_model(device, seed=9, D=16, cap=200, bottom=(160, 16), top=(256, 192, 32))
+    st = _oracle_state(model)
+    model.compile(optimizer=mm.SGD(0.0))
+    B = 200
+    batch = datasets.generate_batch(schema, B, seed=77, index_law="uniform")
+    feats, targets = datasets.split_targets(schema, batch)
+    y = np.asarray(next(iter(targets.values())))
+    tr = model.trainer(B)
+    assert sorted(tr._wide) == [2, 3]  # the two wide top layers (a wide FIRST bottom layer needs no input gradient)
+    tr.forward_backward(H.device_batch(feats, device), torch.from_numpy(y).to(device))
+    loss, _, grads = oracle_train.dlrm_loss_and_grads(feats, st["tables"], st["f2t"], st["cont"], st["bottom"], st["top"], st["head"], y)
+    np.testing.assert_allclose(tr.loss.item(), loss, rtol=2e-5)
+    got = tr.gradients()
+
+    def fro(a, b, what):  # Frobenius norm: a relu unit within rounding of zero may flip and move ONE sample's contribution
+        a = a.detach().cpu().numpy().astype(np.float64)
+        err = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+        assert err < 1e-2, f"{what}: relative Frobenius error {err:.3e}"
+
+    names = [("bottom", 0), ("bottom", 1), ("top", 0), ("top", 1), ("top", 2)]
+    for l, (tag, i) in zip(tr.arena.layers[:-1], names):
+        fro(got[f"{l.name}/kernel"], grads[f"{tag}/kernel_{i}"], f"{tag} kernel {i}")
+        fro(got[f"{l.name}/bias"], grads[f"{tag}/bias_{i}"], f"{tag} bias {i}")
+    fro(got[f"{tr.arena.layers[-1].name}/kernel"], grads["head/kernel"], "head kernel")
+    for t, f in enumerate(tr.feats):
+        tname = st["f2t"][f]
+        fro(_table_grad(tr, t, st["tables"][tname].shape[0]), grads[f"table/{tname}"], f"table {f}")
+
+
+def test_relu_mask_kernel(device):
+    x = torch.randn((37, 50), device=device)
+    big = torch.randn((37, 64), device=device)
+    m = big[:, :50]  # strided mask
+    want = torch.where(m > 0, x, torch.zeros_like(x))
+    assert torch.equal(ops.relu_mask(x.clone(), m), want)
+
+
 def test_graph_replay_equals_eager_steps_and_partial_batches(device):
     schema, model_a = _small_model(device, seed=11, D=32, top=(64, 32))
     _, model_b = _small_model(device, seed=11, D=32, top=(64, 32))
