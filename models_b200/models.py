@@ -86,8 +86,8 @@ def expected_input_columns(schema: Schema) -> List[str]:
 
 
 class Model(Block):
-    """models/base.py:1621-2245, forward only: model(inputs, targets=None, training=False,
-    testing=False) with `inputs` a dict keyed by schema column names."""
+    """models/base.py:1621-2245: model(inputs, targets=None, training=False, testing=False) with `inputs` a dict keyed by
+    schema column names; `compile(optimizer)` / `fit` / `train_step` for the DLRM path (models_b200/train.py)."""
 
     def __init__(self, body: Block, prediction: Block, schema: Schema):
         super().__init__(unique_name("model"))
