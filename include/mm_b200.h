@@ -484,6 +484,26 @@ int mm_dense_apply(int opt, float* w, float* grad, float* state1, float* state2,
 int mm_opt_tick(float* hyper, void* stream);
 int mm_fill_i32(int32_t* p, int64_t n, int32_t value, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K15  Factorization-machine heads (blocks/interaction.py:205-332; DeepFMModel models/ranking.py:171-279).
+ *   mm_fm_pairwise   FMPairwiseInteraction.call: x (B, A, K) -> out (B, K) = 0.5 ((sum_a x)^2 - sum_a x^2)
+ *   mm_deepfm_head   everything DeepFMModel does after its deep tower, one pass over the batch:
+ *       pairwise = sum_f 0.5 ((sum_d e_f[d])^2 - sum_d e_f[d]^2)   — FMBlock stacks the embeddings on the LAST axis, so
+ *                  FMPairwiseInteraction reduces over the D components of each feature (interaction.py:323-328);
+ *       wide     = sum_f wide_kernel[wide_offsets[f] + id_f] + sum_c wide_kernel[cont_offsets[c]] x_c + *wide_bias
+ *                  (Dense(1) over concat(one-hot categorical, continuous), :307-316: a row lookup in the Keras kernel);
+ *       z = pairwise + wide + addend[b]  (addend: the deep tower's logit, nullable);
+ *       out[b] = out_w ? act(z * *out_w + *out_b) : z       (BinaryOutput's Dense(1) on the 1-wide sum).
+ *   tables_host[f]: weights (rows, D) fp32, ids (B,) of idx_bytes each (slot / peers unused; one-hot features only);
+ *   cont_host[c]: one (B,) column (width 1, any mm_concat_piece dtype).  Ids outside [0, rows) contribute nothing and
+ *   bump *oob_count.  wide_bias / out_w / out_b are DEVICE scalars (a captured graph follows weight updates).
+ * ------------------------------------------------------------------------------------- */
+int mm_fm_pairwise(const float* x, int64_t B, int A, int K, float* out, void* stream);
+int mm_deepfm_head(const mm_lookup_table* tables_host, const int64_t* wide_offsets_host, int n_tables, int64_t B, int D,
+                   const mm_concat_piece* cont_host, const int64_t* cont_offsets_host, int n_cont,
+                   const float* wide_kernel, const float* wide_bias, const float* addend, int64_t addend_stride,
+                   const float* out_w, const float* out_b, int out_act, float* out, int32_t* oob_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,11 +15,11 @@ from .inputs import (ContinuousFeatures, EmbeddingOptions, Embeddings, Embedding
                      InputBlockV2, infer_embedding_dim)
 from .blocks import (CrossBlock, DLRMBlock, DotProductInteraction, MLPBlock, dense_engine,  # noqa: F401
                      set_dense_engine)
-from .blocks import BatchNormalization  # noqa: F401
+from .blocks import BatchNormalization, FMBlock, FMPairwiseInteraction  # noqa: F401
 from .retrieval import (CategoricalOutput, ContrastiveOutput, Encoder, InBatchSampler, InBatchSamplerV2,  # noqa: F401
                         ItemRetrievalScorer, ItemRetrievalTask, L2Norm, PopularityBasedSamplerV2, TwoTowerBlock,
                         log_uniform_sampling_probs)
-from .models import (BinaryClassificationTask, BinaryOutput, DCNModel, DLRMModel, Model,  # noqa: F401
+from .models import (BinaryClassificationTask, BinaryOutput, DCNModel, DeepFMModel, DLRMModel, Model,  # noqa: F401
                      RetrievalModel, RetrievalModelV2, TwoTowerModel, TwoTowerModelV2)
 from .topk import (AvgPrecisionAt, BruteForce, MRRAt, NDCGAt, PrecisionAt, RecallAt, TopKEncoder,  # noqa: F401
                    TopKIndexBlock, TopKPrediction, encode_candidates, unique_rows_by_features)

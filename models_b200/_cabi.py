@@ -132,6 +132,9 @@ SIGNATURES = {
     "mm_inbatch_scores_tc": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _i, _f, _vp, _f, _vp, _i64, _vp]),
     "mm_inbatch_scores": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _f,
                                _vp, _i64, _vp]),
+    "mm_fm_pairwise": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
+    "mm_deepfm_head": (_i, [C.POINTER(LookupTable), C.POINTER(C.c_int64), _i, _i64, _i, C.POINTER(ConcatPiece), C.POINTER(C.c_int64), _i,
+                            _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp]),
     "mm_bce_head_fwd_bwd": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "mm_dense_wgrad": (_i, [_vp, _i64, _i, _i64, _vp, _i, _i64, _vp, _vp, _vp]),
     "mm_dense_wgrad_split": (_i, [_vp, _i64, _i, _i, _vp, _i, _i64, _vp, _vp, _vp]),

@@ -464,6 +464,116 @@ def MLPBlock(dimensions: List[int], activation: Union[str, List[str]] = "relu", 
     return MLP(layers, filter_names=names, block_name=block_name, dropout=dropout)
 
 
+class FMPairwiseInteraction(Block):
+    """blocks/interaction.py:205-253: inputs (bs, n_features, embedding_dim) -> 0.5 * ((sum over axis 1)^2 - sum over axis 1
+    of the squares), shape (bs, embedding_dim)."""
+
+    def __init__(self, name: Optional[str] = None, **kwargs):
+        super().__init__(name or unique_name("fm_pairwise_interaction"))
+
+    def call(self, inputs: torch.Tensor, **kwargs) -> torch.Tensor:
+        assert inputs.dim() == 3, "inputs should be a 3-D tensor"
+        return ops.fm_pairwise(inputs.contiguous())
+
+
+class FM(Block):
+    """What FMBlock() returns (blocks/interaction.py:256-332): (B, 1) = wide + pairwise.
+
+    wide     `Dense(1, linear)` over concat(one-hot of every categorical feature, continuous features) in sorted-name order
+             (CategoryEncoding(multi_hot) + ToSparse + "concat", :307-316).  The Keras kernel has one row per category
+             of every feature (int_domain.max + 1 rows each) and one per continuous feature; the product with a one-hot
+             vector is a row lookup.
+    pairwise the embeddings (dim = factors_dim) are stacked on the LAST axis (StackFeatures(axis=-1)) before
+             FMPairwiseInteraction, which reduces axis 1: per feature 0.5 ((sum_d e)^2 - sum_d e^2), then summed over the
+             features (:323-328).  Restated as the reference computes it.
+    One-hot categorical features only (list columns would need the multi-hot wide encoding)."""
+
+    def __init__(self, schema: Schema, embeddings: EmbeddingsBlock, name: Optional[str] = None):
+        super().__init__(name or unique_name("fm_block"))
+        cat = schema.select_by_tag(Tags.CATEGORICAL).excluding_by_tag(Tags.TARGET)
+        cont = schema.select_by_tag(Tags.CONTINUOUS).excluding_by_tag(Tags.TARGET)
+        if not len(cat):
+            raise ValueError("FMBlock requires categorical features")
+        lists = [c.name for c in cat if c.is_list]
+        if lists:
+            raise NotImplementedError(f"FMBlock: list (multi-hot) categorical features {lists} are not implemented")
+        self.embeddings = embeddings
+        self.cat_names = [c.name for c in cat]
+        self.cont_names = [c.name for c in cont]
+        dims = {embeddings.feature_to_table[f].dim for f in self.cat_names}
+        if len(dims) != 1:
+            raise ValueError(f"FMBlock needs all embedding tables to share one dimension, got {sorted(dims)}")
+        self.dim = dims.pop()
+        # rows of the wide kernel: sorted over ALL feature names (ConcatFeatures, core/aggregation.py:54-66)
+        self.wide_offsets: Dict[str, int] = {}
+        off = 0
+        for n in sorted(self.cat_names + self.cont_names):
+            self.wide_offsets[n] = off
+            off += (int(schema.get(n).int_domain.max) + 1) if n in self.cat_names else 1
+        self.wide_width = off
+        self.wide = _Dense(1, activation="linear", use_bias=True, name=f"{self.name}/wide_logit")
+
+    def build(self, device=None):
+        self.embeddings.build(device)
+        self.wide.build(self.wide_width, device)
+        self.built = True
+        return self
+
+    def weights(self):
+        return {f"wide/{k}": v for k, v in self.wide.weights().items()}
+
+    def head(self, inputs: TabularData, addend: Optional[torch.Tensor] = None, out_layer: Optional["_Dense"] = None) -> torch.Tensor:
+        """(B, 1) = [out_layer](wide + pairwise [+ addend]) in one kernel (ops.deepfm_head)."""
+        from .core import get_feature
+        from .inputs import _as_index
+
+        dev = next(iter(inputs.values())).device
+        self.build(dev)
+        B = batch_size_of(inputs)
+        emb = self.embeddings
+        raw = [get_feature(inputs, f) for f in self.cat_names]
+        idx = [i if i.dtype in (torch.uint8, torch.uint16) else _as_index(i).reshape(-1) for i in raw]
+        tabs = [emb.feature_to_table[f].table for f in self.cat_names]
+        cont = []
+        for n in self.cont_names:
+            if n not in inputs:
+                raise ValueError(f"missing continuous feature {n!r}")
+            cont.append(inputs[n])
+        out = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        oob = emb.counter(dev)
+        ow = ob = act = None
+        if out_layer is not None:
+            out_layer.build(1, dev)
+            ow, ob, act = out_layer.kernel.reshape(-1), out_layer.bias, out_layer.activation
+        ops.deepfm_head(tabs, idx, [self.wide_offsets[f] for f in self.cat_names], cont, [self.wide_offsets[n] for n in self.cont_names],
+                        self.wide.kernel.reshape(-1), self.wide.bias, None if addend is None else addend.reshape(-1), ow, ob, act,
+                        out.reshape(-1), oob)
+        emb.finish_check(oob)
+        return out
+
+    def call(self, inputs: TabularData, **kwargs) -> torch.Tensor:
+        return self.head(inputs)
+
+
+def FMBlock(schema: Schema, fm_input_block=None, wide_input_block=None, wide_logit_block=None, factors_dim: Optional[int] = None,
+            **kwargs) -> FM:
+    """blocks/interaction.py:256-332 with the default wide blocks (custom wide_input_block / wide_logit_block are not
+    implemented).  fm_input_block: an InputBlockV2 / EmbeddingsBlock whose tables are used for the pairwise term;
+    default: Embeddings(categorical schema, dim=factors_dim)."""
+    if wide_input_block is not None or wide_logit_block is not None:
+        raise NotImplementedError("FMBlock: custom wide_input_block / wide_logit_block are not implemented")
+    cat = schema.select_by_tag(Tags.CATEGORICAL).excluding_by_tag(Tags.TARGET)
+    if fm_input_block is None:
+        if factors_dim is None:
+            raise ValueError("FMBlock needs `factors_dim` when no fm_input_block is given")
+        emb = Embeddings(cat, dim=factors_dim)
+    else:
+        emb = fm_input_block if isinstance(fm_input_block, EmbeddingsBlock) else getattr(fm_input_block, "embeddings", None)
+        if emb is None:
+            raise ValueError("fm_input_block must be an InputBlockV2 with embeddings or an Embeddings block")
+    return FM(schema, emb)
+
+
 _INTERACTION_TYPES = (None, "field_all", "field_each", "field_interaction")
 
 

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .blocks import (MLP, CrossBlock, CrossBlockSeq, DLRM, DLRMBlock, MLPBlock, _Dense, dense_engine,
+from .blocks import (FM, MLP, CrossBlock, CrossBlockSeq, DLRM, DLRMBlock, FMBlock, MLPBlock, _Dense, dense_engine,
                      run_dense_chain)
 from .core import Block, Prediction, TabularData, batch_size_of, default_device, to_device, unique_name
 from .inputs import EmbeddingOptions, EmbeddingsBlock, InputBlockV2
@@ -378,6 +378,8 @@ class RankingModel(Model):
             bottom = self.body.bottom_forward(inputs)
             x = self.body.interaction_forward(inputs, bottom)
             return run_dense_chain(x, layers)
+        if isinstance(self.body, DeepFMBody):
+            return self.body.forward(inputs, out_layer=self.prediction.to_call)
         if isinstance(self.body, DCNBody) and self.body.stacked:
             x = self.body.cross(self.body.input_block(inputs))
             layers, tail = self.body.deep.chain([self.prediction.to_call])
@@ -447,6 +449,69 @@ class DCNBody(Block):
                 raise ValueError("concat_order must be ('cross', 'deep') or ('deep', 'cross')")
             return tuple(forced)
         return ("cross", "deep") if self.cross.name < self.deep.name else ("deep", "cross")
+
+
+class DeepFMBody(Block):
+    """ParallelBlock({"fm": FMBlock, "deep": input_block -> deep_block -> deep_logit_block}, "element-wise-sum")
+    (models/ranking.py:250-274): (B, 1).  The deep tower is the usual concat + dense chain; the FM pairwise term, the wide
+    part, the sum with the deep logit and (from RankingModel) the output layer are ONE kernel (ops.deepfm_head)."""
+
+    def __init__(self, input_block: InputBlockV2, fm: FM, deep: MLP, deep_logit: MLP):
+        super().__init__(unique_name("deepfm_body"))
+        self.input_block, self.fm, self.deep, self.deep_logit = input_block, fm, deep, deep_logit
+        if deep.has_normalization or deep_logit.has_normalization:
+            raise NotImplementedError("DeepFMModel: normalization inside deep_block / deep_logit_block is not implemented")
+        if deep_logit.dense_layers[-1].units != 1:
+            raise ValueError("The last dimension of deep_logit_block needs to be 1")
+
+    def build(self, device=None):
+        self.input_block.build(device)
+        _, _, d = self.input_block.layout()
+        self.deep.build_from_width(d, device)
+        self.deep_logit.build_from_width(self.deep.dense_layers[-1].units, device)
+        self.fm.build(device)
+        self.built = True
+        return self
+
+    def output_width(self) -> int:
+        return 1
+
+    def weights(self):
+        out = {f"input/{k}": v for k, v in self.input_block.weights().items()}
+        out.update({f"fm/{k}": v for k, v in self.fm.weights().items()})
+        out.update({f"deep/{k}": v for k, v in self.deep.weights().items()})
+        out.update({f"deep_logit/{k}": v for k, v in self.deep_logit.weights().items()})
+        return out
+
+    def forward(self, inputs: TabularData, out_layer: Optional[_Dense] = None) -> torch.Tensor:
+        if not self.built:
+            self.build(next(iter(inputs.values())).device)
+        x0 = self.input_block(inputs)
+        deep = run_dense_chain(x0, self.deep.dense_layers + self.deep_logit.dense_layers)
+        return self.fm.head(inputs, addend=deep, out_layer=out_layer)
+
+    def call(self, inputs: TabularData, **kwargs) -> torch.Tensor:
+        return self.forward(inputs)
+
+
+def DeepFMModel(schema: Schema, embedding_dim: Optional[int] = None, deep_block: Optional[MLP] = None,
+                input_block: Optional[InputBlockV2] = None, wide_input_block=None, wide_logit_block=None,
+                deep_logit_block: Optional[MLP] = None, prediction_tasks=None, **kwargs) -> RankingModel:
+    """models/ranking.py:171-279: sigmoid(Dense(1)(FM(x) + deep(x))) with FM = wide + pairwise (blocks.FM), deep =
+    MLP over the concatenated embeddings and continuous features followed by MLPBlock([1], linear).  Defaults as the
+    reference: deep_block = MLPBlock([64]); one embedding dimension for every categorical feature (`embedding_dim`)."""
+    if input_block is None:
+        if embedding_dim is None:
+            raise ValueError("DeepFMModel needs `embedding_dim` (the FM term stacks the embeddings: one dimension for all tables)")
+        from .inputs import Embeddings
+
+        cat = schema.select_by_tag(Tags.CATEGORICAL).excluding_by_tag(Tags.TARGET)
+        input_block = InputBlockV2(schema, categorical=Embeddings(cat, dim=embedding_dim), **kwargs)
+    fm = FMBlock(schema, fm_input_block=input_block, wide_input_block=wide_input_block, wide_logit_block=wide_logit_block)
+    deep_block = deep_block if deep_block is not None else MLPBlock([64])
+    deep_logit_block = deep_logit_block if deep_logit_block is not None else MLPBlock([1], activation="linear", use_bias=True)
+    prediction = parse_prediction_blocks(schema, prediction_tasks)
+    return RankingModel(DeepFMBody(input_block, fm, deep_block, deep_logit_block), prediction, schema)
 
 
 def DCNModel(schema: Schema, depth: int, deep_block: Optional[MLP] = None, stacked: bool = True,

@@ -939,3 +939,58 @@ def opt_tick(hyper: torch.Tensor) -> None:
 def fill_i32(t: torch.Tensor, value: int) -> torch.Tensor:
     _cabi.check(_lib().mm_fill_i32(_dev(t, "t", torch.int32).data_ptr(), t.numel(), int(value), _stream()), "mm_fill_i32")
     return t
+
+
+# ---- factorization-machine heads (include/mm_b200.h K15) ---------------------------------------------------------
+def fm_pairwise(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FMPairwiseInteraction: x (B, A, K) -> (B, K) = 0.5 ((sum_a x)^2 - sum_a x^2)  (mm_fm_pairwise)."""
+    _dev(x, "x", torch.float32)
+    if x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("inputs should be a contiguous 3-D tensor")
+    B, A, K = x.shape
+    if out is None:
+        out = torch.empty((B, K), dtype=torch.float32, device=x.device)
+    _cabi.check(_lib().mm_fm_pairwise(x.data_ptr(), B, A, K, out.data_ptr(), _stream()), "mm_fm_pairwise")
+    return out
+
+
+def deepfm_head(weights, indices, wide_offsets, cont, cont_offsets, wide_kernel: torch.Tensor, wide_bias: Optional[torch.Tensor],
+                addend: Optional[torch.Tensor], out_w: Optional[torch.Tensor], out_b: Optional[torch.Tensor], out_act: Optional[str],
+                out: torch.Tensor, oob: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FM pairwise term + wide (one-hot Dense(1) as a row lookup) + deep logit (+ output layer) per sample (mm_deepfm_head)."""
+    _dev(out, "out", torch.float32), _dev(wide_kernel, "wide_kernel", torch.float32)
+    B = out.numel()
+    n = len(weights)
+    if not (len(indices) == n and len(wide_offsets) == n):
+        raise ValueError("weights / indices / wide_offsets length mismatch")
+    D = weights[0].shape[1]
+    arr = (_cabi.LookupTable * n)()
+    for t in range(n):
+        w = _dev(weights[t], f"weights[{t}]", torch.float32)
+        ix = _dev(indices[t], f"indices[{t}]")
+        if w.dim() != 2 or w.shape[1] != D or not w.is_contiguous():
+            raise ValueError(f"weights[{t}] must be a contiguous (rows, {D}) float32 matrix")
+        wb = index_bytes_of(ix)
+        if ix.numel() != B * (3 if wb == 3 else 1) or not ix.is_contiguous():
+            raise ValueError(f"indices[{t}] must be contiguous with {B} ids")
+        arr[t].weights, arr[t].indices, arr[t].rows, arr[t].slot, arr[t].idx_bytes = w.data_ptr(), ix.data_ptr(), w.shape[0], t, wb
+    woff = (C.c_int64 * n)(*[int(o) for o in wide_offsets])
+    m = len(cont)
+    if len(cont_offsets) != m:
+        raise ValueError("cont / cont_offsets length mismatch")
+    carr = (_cabi.ConcatPiece * max(m, 1))()
+    for c, t in enumerate(cont):
+        _dev(t, f"cont[{c}]")
+        if t.dtype not in _CONCAT_DTYPES or t.numel() != B:
+            raise ValueError(f"cont[{c}] must hold {B} int32 / int64 / float32 / float64 values")
+        v = t.reshape(-1)
+        carr[c].src, carr[c].src_stride, carr[c].width, carr[c].dtype, carr[c].out_col = v.data_ptr(), v.stride(0), 1, _CONCAT_DTYPES[t.dtype], c
+    coff = (C.c_int64 * max(m, 1))(*[int(o) for o in cont_offsets])
+    if addend is not None and (_dev(addend, "addend", torch.float32).numel() != B):
+        raise ValueError(f"addend must hold {B} values")
+    a_stride = 0 if addend is None else (addend.stride(0) if addend.dim() >= 1 else 1)
+    _cabi.check(
+        _lib().mm_deepfm_head(arr, woff, n, B, D, carr, coff, m, wide_kernel.data_ptr(), _ptr(wide_bias), _ptr(addend), a_stride,
+                              _ptr(out_w), _ptr(out_b), ACTIVATIONS[out_act], out.data_ptr(), _ptr(oob), _stream()),
+        "mm_deepfm_head")
+    return out

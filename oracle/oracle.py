@@ -301,6 +301,52 @@ def dcn_forward(batch, tables, feature_table, continuous, cross, deep, head, sta
     return dense(body, head["kernel"], head.get("bias"), head.get("activation", "sigmoid"))
 
 
+def fm_pairwise(x: np.ndarray) -> np.ndarray:
+    """FMPairwiseInteraction.call (blocks/interaction.py:217-236): x (bs, n_features, embedding_dim) ->
+    0.5 * ((sum over axis 1)^2 - sum over axis 1 of squares), shape (bs, embedding_dim)."""
+    x = np.asarray(x, dtype=np.float32)
+    assert x.ndim == 3, "inputs should be a 3-D tensor"
+    return (0.5 * (np.square(x.sum(axis=1)) - np.square(x).sum(axis=1))).astype(np.float32)
+
+
+def fm_block(batch, tables, feature_table, continuous, cardinalities, wide_kernel, wide_bias) -> np.ndarray:
+    """FMBlock (blocks/interaction.py:256-332) with its default blocks -> (B, 1).
+    first order: concat in sorted-name order of one-hot(categorical, depth = int_domain.max + 1; CategoryEncoding,
+    schema_utils.categorical_cardinalities) and the continuous columns -> Dense(1, linear).
+    pairwise: embeddings stacked with StackFeatures(axis=-1) -> (B, D, F), FMPairwiseInteraction over axis 1, then
+    reduce_sum over axis 1 keepdims (:323-328)."""
+    feats = prepare_features(batch)
+    names = sorted(list(feature_table) + list(continuous))
+    B = len(np.asarray(feats[names[0]]).reshape(-1))
+    cols = []
+    for n in names:
+        if n in feature_table:
+            ids = np.asarray(feats[n]).reshape(-1).astype(np.int64)
+            oh = np.zeros((B, int(cardinalities[n])), dtype=np.float32)
+            ok = (ids >= 0) & (ids < oh.shape[1])
+            oh[np.nonzero(ok)[0], ids[ok]] = 1.0
+            cols.append(oh)
+        else:
+            cols.append(np.asarray(feats[n], dtype=np.float32).reshape(B, 1))
+    first = dense(np.concatenate(cols, axis=1), wide_kernel, wide_bias, "linear")
+    emb = {n: embed_feature(tables[t], feats[n], None) for n, t in feature_table.items()}
+    stacked = np.stack([emb[k] for k in sorted(emb)], axis=-1)  # (B, D, F): StackFeatures(axis=-1)
+    pair = fm_pairwise(stacked).sum(axis=1, keepdims=True)
+    return (first + pair).astype(np.float32)
+
+
+def deepfm_forward(batch, tables, feature_table, continuous, cardinalities, wide_kernel, wide_bias, deep, deep_logit, head) -> np.ndarray:
+    """DeepFMModel (models/ranking.py:171-279): sum of the FM tower (fm_block) and the deep tower (sorted-name concat of
+    embeddings + continuous -> deep MLP -> MLPBlock([1], linear)), then BinaryOutput's Dense(1, sigmoid) on the 1-wide sum."""
+    feats = prepare_features(batch)
+    d = {name: embed_feature(tables[tname], feats[name], None) for name, tname in feature_table.items()}
+    for n in continuous:
+        d[n] = np.asarray(feats[n], dtype=np.float32)
+    deep_out = mlp(mlp(concat_features(d), deep), deep_logit)
+    z = fm_block(batch, tables, feature_table, continuous, cardinalities, wide_kernel, wide_bias) + deep_out
+    return dense(z, head["kernel"], head.get("bias"), head.get("activation", "sigmoid"))
+
+
 # ------------------------------------------------------------------------------------------------
 # a11-a13  two-tower + scorers
 # ------------------------------------------------------------------------------------------------

@@ -60,6 +60,16 @@ def oracle_dcn(model, batch):
                               stacked=body.stacked, branch_order=body.branch_order())
 
 
+def oracle_deepfm(model, batch):
+    body = model.body
+    tables, f2t = emb_tables(body.input_block.embeddings)
+    f2t = {f: t for f, t in f2t.items() if f in body.fm.cat_names}
+    card = {f: body.input_block.embeddings.feature_to_table[f].input_dim for f in body.fm.cat_names}
+    wide = body.fm.wide
+    return oracle.deepfm_forward(batch, tables, f2t, body.fm.cont_names, card, to_numpy(wide.kernel), to_numpy(wide.bias),
+                                 mlp_layers(body.deep), mlp_layers(body.deep_logit), head_layer(model.prediction))
+
+
 def oracle_tower(tower, batch, l2=False):
     tables, f2t = emb_tables(tower.inputs.embeddings) if tower.inputs.embeddings is not None else ({}, {})
     cont = tower.inputs.continuous.features if tower.inputs.continuous is not None else []

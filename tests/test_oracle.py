@@ -203,3 +203,24 @@ def test_optimizer_rules_match_torch_optim(opt):
         o.step()
         ref = oracle_train.sparse_update(opt, ref, ids, vals, state, 0.1)
         np.testing.assert_allclose(p.detach().numpy(), ref, rtol=1e-12, atol=1e-12)
+
+
+def test_fm_pairwise_and_fm_block_known_answers():
+    """tests/unit/tf/blocks/test_interactions.py:25-36: (100, 10, 64) -> (100, 64); and the FMBlock composition written out
+    by hand for three samples (one-hot wide Dense(1) = row lookup; pairwise over the D components of each feature, the
+    reference's StackFeatures(axis=-1) layout)."""
+    rng = np.random.default_rng(0)
+    x = rng.random((100, 10, 64)).astype(np.float32)
+    out = oracle.fm_pairwise(x)
+    assert out.shape == (100, 64)
+    np.testing.assert_allclose(out[3, 5], 0.5 * (x[3, :, 5].sum() ** 2 - (x[3, :, 5] ** 2).sum()), rtol=1e-5)
+    tabs = {"a": rng.normal(size=(4, 8)).astype(np.float32), "b": rng.normal(size=(6, 8)).astype(np.float32)}
+    batch = {"a": np.array([0, 3, 1]), "b": np.array([5, 5, 2]), "x": np.array([0.1, 0.2, 0.3], np.float32)}
+    wk = rng.normal(size=(4 + 6 + 1, 1)).astype(np.float32)
+    got = oracle.fm_block(batch, tabs, {"a": "a", "b": "b"}, ["x"], {"a": 4, "b": 6}, wk, np.array([0.5], np.float32))
+    want = []
+    for i in range(3):
+        w = wk[batch["a"][i], 0] + wk[4 + batch["b"][i], 0] + wk[10, 0] * batch["x"][i] + 0.5
+        p = sum(0.5 * (t[batch[n][i]].sum() ** 2 - (t[batch[n][i]] ** 2).sum()) for t, n in ((tabs["a"], "a"), (tabs["b"], "b")))
+        want.append(w + p)
+    np.testing.assert_allclose(got.reshape(-1), np.array(want), rtol=1e-5)
